@@ -1,0 +1,704 @@
+// Fused rollout step: HBM-resident synthetic Box envs + ObsNormalize + ActionScale + actor /
+// reward-critic / cost-critic forwards + Gaussian sample / log-prob + slab append + episode stats.
+//
+// One launch per environment step replaces, per step, the reference's
+//   ConstraintActorCritic.step        models/actor_critic/constraint_actor_critic.py:L84-109
+//   ActionScale.step / ObsNormalize.step   envs/wrapper.py:L510-514, L231-241
+//   Normalizer.normalize/_push        common/normalizer.py:L88-139
+//   VectorOnPolicyBuffer.store        common/buffer/vector_onpolicy_buffer.py:L96-99
+//   the per-env done loop             adapter/onpolicy_adapter.py:L114-136 (+ _log_value L155-157)
+//
+// Grid = (ceil(N/32) env tiles) x (3 networks).  Actor CTAs sample the action, run the env
+// transition, append the step to the time-major slabs and feed the running-normaliser sums; critic
+// CTAs write V_r / V_c and the bootstrap values of paths cut in the previous step.  The grid-wide
+// ObsNormalize reduction is done with order-independent fixed-point atomics and finalised by the
+// last actor CTA of the launch; the next launch (= kernel boundary = grid sync) consumes it.
+#include "common.cuh"
+#include "mlp.cuh"
+
+namespace osb {
+
+constexpr int RT = 32;                       // envs per tile
+constexpr double FIX_SCALE = 68719476736.0;  // 2^36 fixed point for the normaliser sums
+
+struct EnvSpec {
+    int O, A;
+    int max_episode_steps;
+    uint32_t seed;
+    uint32_t term_threshold;  // terminate iff hash < threshold (0 = never)
+    uint32_t env_id_offset;   // global env id of local env 0 (rank * N)
+    float cost_threshold;
+    int obs_normalize;
+};
+
+struct EnvState {
+    float* s_raw;        // [2][N][O] raw observation of the current state (by step parity:
+                         //   launch t reads buffer t&1 and writes buffer (t+1)&1)
+    float* final_raw;    // [2][N][O] raw final observation of envs that finished (by step parity)
+    int* ep_step;        // [N]
+    uint32_t* episode;   // [N]
+    uint32_t* gstep;     // [N] total env steps taken (termination hash counter)
+    float* ep_ret;       // [N] running episode return / cost / length (adapter bookkeeping)
+    float* ep_cost;      // [N]
+    int* ep_len;         // [N]
+    const float* bias;   // [O]
+};
+
+struct NormState {
+    float* mean;    // [O] running mean            (Normalizer._mean)
+    float* sumsq;   // [O] running sum of squares  (Normalizer._sumsq)
+    float* std;     // [O] max(sqrt(sumsq/(count-1)), 1e-2)
+    float* mean1;   // [O] stats after pushing only the final-observation rows
+    float* std1;    // [O]
+    long long* count;          // [2]: [0] running count, [1] count used for mean1/std1
+    long long* acc_all;        // [2][O] fixed-point sum x, sum x^2 over all next-obs rows
+    long long* acc_fin;        // [2][O] same over final-observation rows
+    int* fin_count;            // [1]
+    int* had_fin;              // [1] previous launch pushed final rows
+    unsigned int* ticket;      // [1]
+};
+
+struct Slabs {
+    float* obs;      // [T][N][O] normalised observation fed to the networks
+    float* act;      // [T][N][A]
+    float* logp;     // [T][N]
+    float* rew;      // [T][N]
+    float* cost;     // [T][N]
+    float* val_r;    // [T][N]
+    float* val_c;    // [T][N]
+    float* boot_r;   // [T][N] bootstrap values at truncated / epoch-end path ends
+    float* boot_c;   // [T][N]
+    uint8_t* flags;  // [T][N]
+    float* epfin;    // [3][T][N] (EpRet, EpCost, EpLen) written where an episode finished
+};
+
+// ---------------------------------------------------------------------------------------------
+// env arithmetic (bit-identical to oracle/synthetic_env.py)
+__device__ __forceinline__ float env_reset_value(const EnvSpec& e, uint32_t gid, uint32_t episode,
+                                                 int j) {
+    return u32_to_unit(hash4(e.seed, gid, episode, (uint32_t)j));
+}
+__device__ __forceinline__ float env_next_value(float s, float a, float b) {
+    float v = __fadd_rn(__fadd_rn(__fmul_rn(0.95f, s), __fmul_rn(0.1f, a)), b);
+    return fminf(fmaxf(v, -10.f), 10.f);
+}
+
+// Chan / Golub / LeVeque batched update as Normalizer._push writes it (normalizer.py:L102-120),
+// fp32 state, batch moments derived from the fixed-point sums.
+__device__ void norm_push(float& mean, float& sumsq, long long count_old, long long n,
+                          long long sx_fix, long long sxx_fix) {
+    const double sx = (double)sx_fix / FIX_SCALE, sxx = (double)sxx_fix / FIX_SCALE;
+    const double mraw = sx / (double)n;
+    double m2 = sxx - (double)n * mraw * mraw;
+    if (m2 < 0.0) m2 = 0.0;
+    const float mean_raw = (float)mraw, sumq_raw = (float)m2;
+    const long long count = count_old + n;
+    const float delta = __fadd_rn(mean_raw, -mean);
+    mean = __fadd_rn(mean, __fdiv_rn(__fmul_rn(delta, (float)n), (float)count));
+    const float d2 = __fmul_rn(delta, delta);
+    const float corr = __fdiv_rn(__fmul_rn(__fmul_rn(d2, (float)count_old), (float)n), (float)count);
+    sumsq = __fadd_rn(sumsq, __fadd_rn(sumq_raw, corr));
+}
+__device__ __forceinline__ float norm_std(float sumsq, long long count) {
+    const float var = __fdiv_rn(sumsq, (float)(count - 1));
+    return fmaxf(sqrtf(var), 1e-2f);
+}
+
+// Executed by the last-arriving actor CTA: fold the launch's sums into the running statistics.
+__device__ void norm_finalize(const NormState& ns, int O, long long n_all) {
+    __threadfence();
+    const int nfin = *((volatile int*)ns.fin_count);
+    long long count = ns.count[0];
+    for (int j = threadIdx.x; j < O; j += blockDim.x) {
+        float mean = ns.mean[j], sumsq = ns.sumsq[j];
+        long long c = count;
+        if (nfin > 0) {
+            norm_push(mean, sumsq, c, nfin, __ldcg(ns.acc_fin + j), __ldcg(ns.acc_fin + O + j));
+            c += nfin;
+            ns.mean1[j] = mean;
+            ns.std1[j] = norm_std(sumsq, c);
+        }
+        norm_push(mean, sumsq, c, n_all, __ldcg(ns.acc_all + j), __ldcg(ns.acc_all + O + j));
+        c += n_all;
+        ns.mean[j] = mean;
+        ns.sumsq[j] = sumsq;
+        ns.std[j] = norm_std(sumsq, c);
+        ns.acc_all[j] = 0; ns.acc_all[O + j] = 0;
+        ns.acc_fin[j] = 0; ns.acc_fin[O + j] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ns.count[1] = count + nfin;
+        ns.count[0] = count + nfin + n_all;
+        *ns.had_fin = nfin > 0 ? 1 : 0;
+        *ns.fin_count = 0;
+        *ns.ticket = 0u;
+    }
+}
+
+__device__ __forceinline__ long long to_fix(float x) { return __double2ll_rn((double)x * FIX_SCALE); }
+
+// ---------------------------------------------------------------------------------------------
+// reset of all envs (OnPolicyAdapter.rollout resets every epoch: onpolicy_adapter.py:L80) and the
+// normaliser push of the reset observations (ObsNormalize.reset, wrapper.py:L243-261).
+__global__ void __launch_bounds__(NTHREADS) env_reset_kernel(EnvSpec es, EnvState st, NormState ns,
+                                                             int N) {
+    __shared__ float sNew[RT][KC + 1];
+    __shared__ int s_last;
+    const int env0 = blockIdx.x * RT;
+    const int O = es.O;
+    const int e = threadIdx.x >> 3, q = threadIdx.x & 7;
+    const int env = env0 + e;
+    const bool ok = env < N;
+    uint32_t epi = 0;
+    if (ok) epi = st.episode[env] + 1u;
+    for (int c0 = 0; c0 < O; c0 += KC) {
+        for (int j = c0 + q; j < min(O, c0 + KC); j += 8) {
+            float v = 0.f;
+            if (ok) {
+                v = env_reset_value(es, es.env_id_offset + env, epi, j);
+                st.s_raw[(size_t)env * O + j] = v;  // buffer 0: step 0 reads parity 0
+            }
+            sNew[e][j - c0] = v;
+        }
+        __syncthreads();
+        if (es.obs_normalize) {
+            const int j = c0 + threadIdx.x;
+            if (threadIdx.x < KC && j < O) {
+                long long sx = 0, sxx = 0;
+                for (int r = 0; r < RT; ++r)
+                    if (env0 + r < N) {
+                        const float v = sNew[r][threadIdx.x];
+                        sx += to_fix(v);
+                        sxx += to_fix(__fmul_rn(v, v));
+                    }
+                atomicAdd((unsigned long long*)(ns.acc_all + j), (unsigned long long)sx);
+                atomicAdd((unsigned long long*)(ns.acc_all + O + j), (unsigned long long)sxx);
+            }
+        }
+        __syncthreads();
+    }
+    if (ok && q == 0) {
+        st.episode[env] = epi;
+        st.ep_step[env] = 0;
+        st.ep_ret[env] = 0.f;
+        st.ep_cost[env] = 0.f;
+        st.ep_len[env] = 0;
+    }
+    if (es.obs_normalize) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(ns.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) norm_finalize(ns, O, (long long)N);
+    }
+}
+
+// Philox4x32-10 (fast-mode noise); counter = (env gid, global step, lane block, 0).
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ float philox_normal(uint32_t seed, uint32_t gid, uint32_t step, int a) {
+    uint32_t c[4] = {gid, step, (uint32_t)(a >> 2), 0x0B200u};
+    uint32_t k0 = seed, k1 = 0xCAFEF00Du;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const int pair = (a & 3) >> 1;
+    const float u0 = ((float)(c[2 * pair] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u1 = ((float)(c[2 * pair + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u0));
+    float sn, cs;
+    sincosf(6.283185307179586f * u1, &sn, &cs);
+    return (a & 1) ? r * sn : r * cs;
+}
+
+struct StepArgs {
+    EnvSpec es;
+    EnvState st;
+    NormState ns;
+    Slabs sl;
+    const float* theta;   // flat [actor | critic_r | critic_c]
+    const float* eps;     // [N][A] noise of this step (parity mode) or null (Philox fast mode)
+    uint32_t noise_seed;
+    uint32_t global_step; // epoch * T + t, Philox counter
+    int t, T, N;
+    int is_tail;          // t == T: critics only (epoch-end bootstrap)
+};
+
+// normalise (or copy) a tile of raw observations into sX (chunk kc), zero padded.
+__device__ __forceinline__ void load_obs_tile(const float* __restrict__ raw, int env0, int N, int O,
+                                              int kc, const float* sMean, const float* sStd,
+                                              bool normalize, float* sX, float* obs_out) {
+    const int c0 = kc * KC;
+    for (int i = threadIdx.x; i < RT * KC; i += NTHREADS) {
+        const int e = i / KC, k = i % KC;
+        const int env = env0 + e, j = c0 + k;
+        float v = 0.f;
+        if (env < N && j < O) {
+            v = raw[(size_t)env * O + j];
+            if (normalize) {
+                v = __fdiv_rn(__fadd_rn(v, -sMean[j]), sStd[j]);
+                v = fminf(fmaxf(v, -5.f), 5.f);
+            }
+            if (obs_out) obs_out[(size_t)env * O + j] = v;
+        }
+        sX[e * LD + k] = v;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    NetSmem W;
+    float* base = carve_net_smem<false>(smem, W);
+    float* sX = base;  base += RT * LD;
+    float* sH1 = base; base += RT * LD;
+    float* sH2 = base; base += RT * LD;
+    float* sO = base;  base += RT * LDO;
+    float* sMean = base; base += p.es.O;
+    float* sStd = base;  base += p.es.O;
+    float* sAct = base;  base += RT * OUTP;
+    float* sNew = base;  base += RT * (KC + 1);
+    float* sFin = base;  base += RT * (KC + 1);
+    float* sRew = base;  base += RT;
+    float* sCost = base; base += RT;
+    int* sFlag = reinterpret_cast<int*>(base); base += RT;
+    __shared__ int s_last, s_anyfin;
+
+    const int net = p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y;
+    const int env0 = blockIdx.x * RT;
+    const int O = p.es.O, A = p.es.A, N = p.N, T = p.T, t = p.t;
+    const int nchunks = (O + KC - 1) / KC;
+    const NetLayout L = net_layout(net, O, A);
+    const float* theta = p.theta + net_offset(net, O, A);
+    const bool normalize = p.es.obs_normalize && p.ns.count[0] > 1;
+    const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
+    float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
+
+    load_net_rest<false>(theta, L, W);
+    load_w1_chunk(theta, L, 0, W);
+    auto load_chunk_cur = [&](int kc) {
+        load_w1_chunk(theta, L, kc, W);
+        for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean[j]; sStd[j] = p.ns.std[j]; }
+        load_obs_tile(s_cur, env0, N, O, kc, sMean, sStd, normalize, sX, nullptr);
+    };
+
+    // ---- bootstrap values of paths that ended in the previous step (critic CTAs only) --------
+    if (net != 0 && t > 0) {
+        if (threadIdx.x == 0) s_anyfin = 0;
+        __syncthreads();
+        if (threadIdx.x < RT && env0 + threadIdx.x < N) {
+            const unsigned f = p.sl.flags[(size_t)(t - 1) * N + env0 + threadIdx.x];
+            if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED)) s_anyfin = 1;
+        }
+        __syncthreads();
+        if (s_anyfin) {
+            const bool norm1 = p.es.obs_normalize && p.ns.count[1] > 1;
+            const float* fin = p.st.final_raw + (size_t)((t - 1) & 1) * N * O;
+            auto load_chunk_fin = [&](int kc) {
+                load_w1_chunk(theta, L, kc, W);
+                for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean1[j]; sStd[j] = p.ns.std1[j]; }
+                load_obs_tile(fin, env0, N, O, kc, sMean, sStd, norm1, sX, nullptr);
+            };
+            for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean1[j]; sStd[j] = p.ns.std1[j]; }
+            __syncthreads();
+            load_obs_tile(fin, env0, N, O, 0, sMean, sStd, norm1, sX, nullptr);
+            __syncthreads();
+            mlp_hidden<RT>(sX, sH1, sH2, W, nchunks, load_chunk_fin);
+            mlp_out<RT>(sH2, sO, W, 1);
+            if (threadIdx.x < RT && env0 + threadIdx.x < N) {
+                const size_t idx = (size_t)(t - 1) * N + env0 + threadIdx.x;
+                const unsigned f = p.sl.flags[idx];
+                if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED))
+                    (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = sO[threadIdx.x * LDO];
+            }
+            __syncthreads();
+            if (nchunks > 1) { load_w1_chunk(theta, L, 0, W); }
+        }
+    }
+
+    // ---- forward on the current observation ------------------------------------------------
+    for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean[j]; sStd[j] = p.ns.std[j]; }
+    __syncthreads();
+    if (net == 0 && nchunks > 1) {
+        // write the whole normalised observation row once (chunks > 0 are not revisited below)
+        for (int kc = 1; kc < nchunks; ++kc)
+            load_obs_tile(s_cur, env0, N, O, kc, sMean, sStd, normalize, sX,
+                          p.sl.obs + (size_t)t * N * O);
+        __syncthreads();
+    }
+    load_obs_tile(s_cur, env0, N, O, 0, sMean, sStd, normalize, sX,
+                  (net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr);
+    __syncthreads();
+    mlp_hidden<RT>(sX, sH1, sH2, W, nchunks, load_chunk_cur);
+    mlp_out<RT>(sH2, sO, W, L.out);
+
+    if (net != 0) {
+        if (threadIdx.x < RT && env0 + threadIdx.x < N) {
+            const float v = sO[threadIdx.x * LDO];
+            if (!p.is_tail) {
+                (net == 1 ? p.sl.val_r : p.sl.val_c)[(size_t)t * N + env0 + threadIdx.x] = v;
+            } else {
+                // epoch end: bootstrap with V(next obs) unless the path already ended at T-1
+                const size_t idx = (size_t)(T - 1) * N + env0 + threadIdx.x;
+                if (p.sl.flags[idx] == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
+            }
+        }
+    }
+
+    // ---- actor CTA: sample, log-prob ---------------------------------------------------------
+    if (net == 0) {
+        // thread -> (env e = tid / 8, lane q = tid % 8); action components a = q, q + 8
+        const int e = threadIdx.x >> 3, q = threadIdx.x & 7;
+        const int env = env0 + e;
+        const bool ok = env < N;
+        float lp = 0.f;
+        for (int a = q; a < A; a += 8) {
+            const float mu = sO[e * LDO + a];
+            const float sd = expf(__ldg(theta + L.off_logstd + a));
+            float eps = 0.f;
+            if (ok)
+                eps = p.eps ? p.eps[(size_t)env * A + a]
+                            : philox_normal(p.noise_seed, p.es.env_id_offset + env, p.global_step, a);
+            const float act = __fadd_rn(mu, __fmul_rn(sd, eps));   // Normal.rsample: loc + eps*scale
+            // Normal.log_prob: -((x-loc)^2)/(2 var) - log(scale) - log(sqrt(2 pi))
+            const float d = __fadd_rn(act, -mu);
+            const float var = __fmul_rn(sd, sd);
+            float term = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
+            term = __fadd_rn(__fadd_rn(term, -logf(sd)), -0.9189385332046727f);
+            lp += term;
+            sAct[e * OUTP + a] = act;
+            if (ok) p.sl.act[((size_t)t * N + env) * A + a] = act;
+        }
+        lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+        lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+        lp += __shfl_xor_sync(0xffffffffu, lp, 4);
+        if (ok && q == 0) p.sl.logp[(size_t)t * N + env] = lp;
+    }
+    __syncthreads();
+
+    // ---- env transition ----------------------------------------------------------------------
+    if (net == 0) {
+        const int e = threadIdx.x >> 3, q = threadIdx.x & 7;
+        const int env = env0 + e;
+        const bool ok = env < N;
+        const uint32_t gid = p.es.env_id_offset + env;
+        int ep_step = 0; uint32_t epi = 0, gstep = 0;
+        if (ok) { ep_step = p.st.ep_step[env]; epi = p.st.episode[env]; gstep = p.st.gstep[env]; }
+        const bool trunc = ok && (ep_step + 1 >= p.es.max_episode_steps);
+        const bool term = ok && p.es.term_threshold != 0u &&
+                          hash4(p.es.seed ^ 0xA5A5A5A5u, gid, gstep, 0xFFFFu) < p.es.term_threshold;
+        const bool fin = term || trunc;
+        float part = 0.f, s0n = 0.f;
+        float* finrow = p.st.final_raw + ((size_t)(t & 1) * N + (ok ? env : 0)) * O;
+        for (int c0 = 0; c0 < O; c0 += KC) {
+            for (int j = c0 + q; j < min(O, c0 + KC); j += 8) {
+                float nv = 0.f, fv = 0.f;
+                if (ok) {
+                    // ActionScale (wrapper.py:L510-512) from [-1,1] onto the env's [-1,1] box
+                    float a = sAct[e * OUTP + (j % A)];
+                    a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
+                    a = fminf(fmaxf(a, -1.f), 1.f);
+                    const float s = s_cur[(size_t)env * O + j];
+                    const float sn = env_next_value(s, a, __ldg(p.st.bias + j));
+                    part = __fadd_rn(part, __fmul_rn(sn, sn));
+                    if (j == 0) s0n = sn;
+                    fv = sn;
+                    nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
+                    s_nxt[(size_t)env * O + j] = nv;
+                    if (fin) finrow[j] = sn;
+                }
+                sNew[e * (KC + 1) + (j - c0)] = nv;
+                sFin[e * (KC + 1) + (j - c0)] = fin ? fv : 0.f;
+            }
+            if (c0 == 0 && q == 0) sFlag[e] = fin ? 1 : 0;
+            __syncthreads();
+            if (p.es.obs_normalize) {
+                const int j = c0 + threadIdx.x;
+                if (threadIdx.x < KC && j < O) {
+                    long long sx = 0, sxx = 0, fx = 0, fxx = 0;
+                    for (int r = 0; r < RT; ++r)
+                        if (env0 + r < N) {
+                            const float v = sNew[r * (KC + 1) + threadIdx.x];
+                            sx += to_fix(v); sxx += to_fix(__fmul_rn(v, v));
+                            if (sFlag[r]) {
+                                const float w = sFin[r * (KC + 1) + threadIdx.x];
+                                fx += to_fix(w); fxx += to_fix(__fmul_rn(w, w));
+                            }
+                        }
+                    atomicAdd((unsigned long long*)(p.ns.acc_all + j), (unsigned long long)sx);
+                    atomicAdd((unsigned long long*)(p.ns.acc_all + O + j), (unsigned long long)sxx);
+                    if (fx != 0 || fxx != 0) {
+                        atomicAdd((unsigned long long*)(p.ns.acc_fin + j), (unsigned long long)fx);
+                        atomicAdd((unsigned long long*)(p.ns.acc_fin + O + j), (unsigned long long)fxx);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // reward = 1 - mean_j s'_j^2 with the fixed summation tree shared with the oracle
+        part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 1));
+        part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 2));
+        part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 4));
+        if (ok && q == 0) {
+            const float rew = __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
+            const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
+            const size_t idx = (size_t)t * N + env;
+            p.sl.rew[idx] = rew;
+            p.sl.cost[idx] = cst;
+            p.sl.flags[idx] = (uint8_t)((term ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
+            // adapter bookkeeping: _log_value, _log_metrics, _reset_log (onpolicy_adapter.py:L138-175)
+            const float er = __fadd_rn(p.st.ep_ret[env], rew);
+            const float ec = __fadd_rn(p.st.ep_cost[env], cst);
+            const int el = p.st.ep_len[env] + 1;
+            if (fin) {
+                const size_t TN = (size_t)T * N;
+                p.sl.epfin[idx] = er;
+                p.sl.epfin[TN + idx] = ec;
+                p.sl.epfin[2 * TN + idx] = (float)el;
+                p.st.ep_ret[env] = 0.f; p.st.ep_cost[env] = 0.f; p.st.ep_len[env] = 0;
+                p.st.episode[env] = epi + 1u;
+                p.st.ep_step[env] = 0;
+            } else {
+                p.st.ep_ret[env] = er; p.st.ep_cost[env] = ec; p.st.ep_len[env] = el;
+                p.st.ep_step[env] = ep_step + 1;
+            }
+            p.st.gstep[env] = gstep + 1u;
+        }
+        if (p.es.obs_normalize && threadIdx.x == 0) {
+            int nf = 0;
+            for (int r = 0; r < RT; ++r) nf += (env0 + r < N) ? sFlag[r] : 0;
+            if (nf) atomicAdd(p.ns.fin_count, nf);
+        }
+    }
+    // every CTA (actor and critic) has now consumed the normaliser state of this step; the last
+    // one to arrive folds the step's sums into it for the next launch.
+    if (p.es.obs_normalize && !p.is_tail) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_last = (atomicAdd(p.ns.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) norm_finalize(p.ns, O, (long long)N);
+    }
+}
+
+// Window of the last <= W finished episodes in (step, env) append order: Logger deque semantics
+// (common/logger.py:L253-282 with window_lens; adapter/onpolicy_adapter.py:L159-175).
+// ring[3][W] holds (EpRet, EpCost, EpLen); meta[0] = number of valid entries, meta[1] = head.
+// Single CTA of 1024 threads: find the first row (from the end) after which >= W episodes finished,
+// then append rows in order with a block-wide ordered compaction (exclusive scan of counts).
+__global__ void __launch_bounds__(1024) episode_window_kernel(const uint8_t* __restrict__ flags,
+                                                              const float* __restrict__ epfin,
+                                                              int T, int N, int W,
+                                                              float* __restrict__ ring,
+                                                              int* __restrict__ meta) {
+    __shared__ int s_cnt, s_total, s_warp[32], s_base;
+    const size_t TN = (size_t)T * N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int seg = (N + 1023) / 1024;          // contiguous envs per thread
+    const int lo = min(N, tid * seg), hi = min(N, lo + seg);
+    if (tid == 0) s_total = 0;
+    int first_row = T;
+    for (int t = T - 1; t >= 0; --t) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int i = lo; i < hi; ++i) cnt += flags[(size_t)t * N + i] != 0;
+        if (cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        first_row = t;
+        if (tid == 0) s_total += s_cnt;
+        __syncthreads();
+        if (s_total >= W) break;
+    }
+    __syncthreads();
+    const int total_new = s_total;
+    if (total_new == 0) return;
+    const int head0 = meta[1], count0 = meta[0];
+    const int skip = total_new > W ? total_new - W : 0;   // only the last W appended entries survive
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int t = first_row; t < T; ++t) {
+        int cnt = 0;
+        for (int i = lo; i < hi; ++i) cnt += flags[(size_t)t * N + i] != 0;
+        // block exclusive scan of cnt
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            s_warp[lane] = wi - w;   // exclusive warp offsets
+            if (lane == 31) s_cnt = wi;  // row total
+        }
+        __syncthreads();
+        int seq = s_base + s_warp[wid] + incl - cnt;   // sequence index of my first entry
+        for (int i = lo; i < hi; ++i) {
+            const size_t idx = (size_t)t * N + i;
+            if (flags[idx] != 0) {
+                if (seq >= skip) {
+                    const int pos = (head0 + (seq - skip)) % W;
+                    ring[0 * W + pos] = epfin[idx];
+                    ring[1 * W + pos] = epfin[TN + idx];
+                    ring[2 * W + pos] = epfin[2 * TN + idx];
+                }
+                ++seq;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_base += s_cnt;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int kept = total_new - skip;
+        meta[1] = (head0 + kept) % W;
+        meta[0] = min(W, count0 + kept);
+    }
+}
+
+// window_sums[4] = {sum EpRet, sum EpCost, sum EpLen, count} over the ring (fp64).
+__global__ void window_sums_kernel(const float* __restrict__ ring, const int* __restrict__ meta,
+                                   int W, double* __restrict__ window_sums) {
+    if (threadIdx.x != 0) return;
+    const int count = meta[0];
+    double s[3] = {0, 0, 0};
+    for (int q = 0; q < 3; ++q)
+        for (int i = 0; i < count; ++i) s[q] += (double)ring[q * W + i];
+    window_sums[0] = s[0]; window_sums[1] = s[1]; window_sums[2] = s[2];
+    window_sums[3] = (double)count;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+static size_t rollout_smem_bytes(int O) {
+    size_t f = NETSMEM_FLOATS_FWD + 3 * RT * LD + RT * LDO + 2 * (size_t)O + RT * OUTP +
+               2 * RT * (KC + 1) + 3 * RT;
+    return f * sizeof(float);
+}
+
+extern "C" {
+
+int osb_episode_window(const unsigned char* flags, const float* epfin, int T, int N, int W,
+                       float* ring, int* meta, double* window_sums, void* stream);
+
+// Opaque-struct-free C ABI: the caller passes plain device pointers.
+int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned term_threshold,
+                  unsigned env_id_offset, float cost_threshold, int obs_normalize, int N,
+                  float* s_raw, float* final_raw, int* ep_step, unsigned* episode, unsigned* gstep,
+                  float* ep_ret, float* ep_cost, int* ep_len, const float* bias,
+                  float* norm_mean, float* norm_sumsq, float* norm_std, float* norm_mean1,
+                  float* norm_std1, long long* norm_count, long long* acc_all, long long* acc_fin,
+                  int* fin_count, int* had_fin, unsigned* ticket, void* stream) {
+    OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && N > 0, "bad dims (need 0 < A <= 16)");
+    EnvSpec es{O, A, max_episode_steps, seed, term_threshold, env_id_offset, cost_threshold, obs_normalize};
+    EnvState st{s_raw, final_raw, ep_step, episode, gstep, ep_ret, ep_cost, ep_len, bias};
+    NormState ns{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
+                 acc_fin, fin_count, had_fin, ticket};
+    env_reset_kernel<<<(N + RT - 1) / RT, NTHREADS, 0, (cudaStream_t)stream>>>(es, st, ns, N);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+static int launch_step(StepArgs& p, cudaStream_t stream) {
+    const size_t smem = rollout_smem_bytes(p.es.O);
+    static size_t attr = 0;
+    if (smem > attr) {
+        OSB_CUDA(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid((p.N + RT - 1) / RT, p.is_tail ? 2 : 3);
+    rollout_step_kernel<<<grid, NTHREADS, smem, stream>>>(p);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigned term_threshold,
+                     unsigned env_id_offset, float cost_threshold, int obs_normalize, int N, int T,
+                     int t, float* s_raw, float* final_raw, int* ep_step, unsigned* episode,
+                     unsigned* gstep, float* ep_ret, float* ep_cost, int* ep_len, const float* bias,
+                     float* norm_mean, float* norm_sumsq, float* norm_std, float* norm_mean1,
+                     float* norm_std1, long long* norm_count, long long* acc_all,
+                     long long* acc_fin, int* fin_count, int* had_fin, unsigned* ticket,
+                     float* obs, float* act, float* logp, float* rew, float* cost, float* val_r,
+                     float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
+                     const float* theta, const float* eps, unsigned noise_seed,
+                     unsigned global_step, void* stream) {
+    OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && N > 0 && T > 0, "bad dims (need 0 < A <= 16)");
+    OSB_CHECK_ARG(t >= 0 && t <= T, "step index out of range");
+    StepArgs p;
+    p.es = EnvSpec{O, A, max_episode_steps, seed, term_threshold, env_id_offset, cost_threshold, obs_normalize};
+    p.st = EnvState{s_raw, final_raw, ep_step, episode, gstep, ep_ret, ep_cost, ep_len, bias};
+    p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
+                     acc_fin, fin_count, had_fin, ticket};
+    p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
+    p.theta = theta; p.eps = eps; p.noise_seed = noise_seed; p.global_step = global_step;
+    p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0;
+    return launch_step(p, (cudaStream_t)stream);
+}
+
+int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsigned term_threshold,
+                      unsigned env_id_offset, float cost_threshold, int obs_normalize, int N, int T,
+                      float* s_raw, float* final_raw, int* ep_step, unsigned* episode,
+                      unsigned* gstep, float* ep_ret, float* ep_cost, int* ep_len, const float* bias,
+                      float* norm_mean, float* norm_sumsq, float* norm_std, float* norm_mean1,
+                      float* norm_std1, long long* norm_count, long long* acc_all,
+                      long long* acc_fin, int* fin_count, int* had_fin, unsigned* ticket,
+                      float* obs, float* act, float* logp, float* rew, float* cost, float* val_r,
+                      float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
+                      const float* theta, const float* eps_all, unsigned noise_seed,
+                      unsigned epoch_index, int W, float* ring, int* meta, double* window_sums,
+                      void* stream) {
+    OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && N > 0 && T > 0, "bad dims (need 0 < A <= 16)");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = osb_env_reset(O, A, max_episode_steps, seed, term_threshold, env_id_offset,
+                           cost_threshold, obs_normalize, N, s_raw, final_raw, ep_step, episode,
+                           gstep, ep_ret, ep_cost, ep_len, bias, norm_mean, norm_sumsq, norm_std,
+                           norm_mean1, norm_std1, norm_count, acc_all, acc_fin, fin_count, had_fin,
+                           ticket, stream);
+    if (rc) return rc;
+    StepArgs p;
+    p.es = EnvSpec{O, A, max_episode_steps, seed, term_threshold, env_id_offset, cost_threshold, obs_normalize};
+    p.st = EnvState{s_raw, final_raw, ep_step, episode, gstep, ep_ret, ep_cost, ep_len, bias};
+    p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
+                     acc_fin, fin_count, had_fin, ticket};
+    p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
+    p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N;
+    for (int t = 0; t <= T; ++t) {
+        p.t = t; p.is_tail = (t == T) ? 1 : 0;
+        p.eps = (eps_all && t < T) ? eps_all + (size_t)t * N * A : nullptr;
+        p.global_step = epoch_index * (unsigned)T + (unsigned)t;
+        rc = launch_step(p, s);
+        if (rc) return rc;
+    }
+    return osb_episode_window(flags, epfin, T, N, W, ring, meta, window_sums, stream);
+}
+
+int osb_episode_window(const unsigned char* flags, const float* epfin, int T, int N, int W,
+                       float* ring, int* meta, double* window_sums, void* stream) {
+    OSB_CHECK_ARG(flags && epfin && ring && meta && window_sums && W > 0, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    episode_window_kernel<<<1, 1024, 0, s>>>(flags, epfin, T, N, W, ring, meta);
+    OSB_LAUNCH_CHECK();
+    window_sums_kernel<<<1, 32, 0, s>>>(ring, meta, W, window_sums);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+}  // extern "C"

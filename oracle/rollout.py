@@ -1,0 +1,68 @@
+"""Oracle: one epoch of OnPolicyAdapter.rollout on the synthetic env (numpy + torch-CPU).
+
+TEST INFRASTRUCTURE ONLY.  Follows adapter/onpolicy_adapter.py:L58-136 (rollout loop, per-env
+done handling, bootstrap rules), envs/wrapper.py:L231-241 (ObsNormalize.step: final observations
+are pushed/normalised before the batch), envs/wrapper.py:L510-514 (ActionScale) and
+common/buffer/vector_onpolicy_buffer.py:L96-99 (store), vectorised over envs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import actor_critic as ac
+from oracle.gae import FLAG_TERMINATED, FLAG_TRUNCATED
+
+F32 = np.float32
+
+
+def action_scale(act, lo=-1.0, hi=1.0, mn=-1.0, mx=1.0):
+    """old_min + (old_max - old_min) * (action - min) / (max - min), fp32 left to right."""
+    act = np.asarray(act, F32)
+    t = (act - F32(mn)).astype(F32)
+    t = (F32(hi - lo) * t).astype(F32)
+    t = (t / F32(mx - mn)).astype(F32)
+    return (F32(lo) + t).astype(F32)
+
+
+def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_state=None):
+    """Returns time-major slabs (dict of [T, N, ...] float32 arrays + uint8 flags).
+
+    `eps` is the [T, N, A] standard-normal stream; `window` (list) receives (EpRet, EpCost, EpLen)
+    of finished episodes in (step, env) order, like the reference Logger deque."""
+    N, O, A = env.N, env.O, env.A
+    sl = {
+        'obs': np.zeros((T, N, O), F32), 'act': np.zeros((T, N, A), F32),
+        'logp': np.zeros((T, N), F32), 'rew': np.zeros((T, N), F32), 'cost': np.zeros((T, N), F32),
+        'val_r': np.zeros((T, N), F32), 'val_c': np.zeros((T, N), F32),
+        'boot_r': np.zeros((T, N), F32), 'boot_c': np.zeros((T, N), F32),
+        'flags': np.zeros((T, N), np.uint8),
+    }
+    ep_ret = np.zeros(N, F32); ep_cost = np.zeros(N, F32); ep_len = np.zeros(N, F32)
+    raw = env.reset()
+    obs = norm.normalize(raw) if obs_normalize else raw
+    for t in range(T):
+        act, v_r, v_c, logp = ac.step(theta, obs, eps[t], O, A)
+        nraw, rew, cost, term, trunc, final_raw, fin = env.step(action_scale(act))
+        final_norm = np.zeros((N, O), F32)
+        if fin.any():
+            final_norm[fin] = norm.normalize(final_raw[fin]) if obs_normalize else final_raw[fin]
+        nobs = norm.normalize(nraw) if obs_normalize else nraw
+        ep_ret = (ep_ret + rew).astype(F32); ep_cost = (ep_cost + cost).astype(F32); ep_len += 1
+        sl['obs'][t] = obs; sl['act'][t] = act; sl['logp'][t] = logp
+        sl['rew'][t] = rew; sl['cost'][t] = cost; sl['val_r'][t] = v_r; sl['val_c'][t] = v_c
+        sl['flags'][t] = term.astype(np.uint8) * FLAG_TERMINATED + trunc.astype(np.uint8) * FLAG_TRUNCATED
+        obs = nobs
+        epoch_end = t == T - 1
+        need_final = trunc & ~term
+        need_next = (~term) & (~trunc) & epoch_end
+        if need_final.any():
+            br, bc = ac.values(theta, final_norm, O, A)
+            sl['boot_r'][t][need_final] = br[need_final]; sl['boot_c'][t][need_final] = bc[need_final]
+        if np.any(need_next):
+            br, bc = ac.values(theta, obs, O, A)
+            sl['boot_r'][t][need_next] = br[need_next]; sl['boot_c'][t][need_next] = bc[need_next]
+        for i in np.nonzero(fin)[0]:
+            if window is not None:
+                window.append((float(ep_ret[i]), float(ep_cost[i]), float(ep_len[i])))
+        ep_ret[fin] = 0; ep_cost[fin] = 0; ep_len[fin] = 0
+    return sl

@@ -1,0 +1,229 @@
+"""Generate the golden fixtures under tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shim.py) in the build container.
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the CPU oracle (tests/test_oracle_golden.py); the GPU parity tests then compare
+the CUDA path with the oracle.  /root/reference does not exist on the GPU box, so this script is
+never run there -- only its committed outputs travel.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+import omnisafe  # noqa: E402,F401
+from gymnasium.spaces import Box  # noqa: E402  (shim)
+from omnisafe.common.buffer import VectorOnPolicyBuffer  # noqa: E402
+from omnisafe.common.normalizer import Normalizer  # noqa: E402
+from omnisafe.envs.core import CMDP, env_register  # noqa: E402
+from omnisafe.utils.math import conjugate_gradients, discount_cumsum  # noqa: E402
+
+from oracle.synthetic_env import SyntheticBoxEnv as OracleEnv  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def gen_discount_cumsum():
+    rng = np.random.default_rng(1)
+    out = {}
+    for i, (n, d) in enumerate([(5, 0.9), (5, 0.99), (5, 0.999), (1, 0.5), (37, 0.9405), (200, 0.99)]):
+        x = np.arange(1, 6, dtype=np.float64) if n == 5 else rng.standard_normal(n)
+        y = discount_cumsum(torch.as_tensor(x.astype(np.float32)), d).numpy()
+        out[f'x{i}'] = x.astype(np.float32); out[f'd{i}'] = np.float64(d); out[f'y{i}'] = y
+    out['n'] = 6
+    np.savez(os.path.join(OUT, 'discount_cumsum.npz'), **out)
+
+
+def gen_buffer_gae():
+    """Drive the reference VectorOnPolicyBuffer with random data + random path ends."""
+    rng = np.random.default_rng(2)
+    N, T, O, A = 6, 48, 3, 2
+    gamma, lam, lam_c, pen = 0.99, 0.95, 0.9, 0.05
+    buf = VectorOnPolicyBuffer(
+        obs_space=Box(-1, 1, (O,)), act_space=Box(-1, 1, (A,)), size=T, gamma=gamma, lam=lam,
+        lam_c=lam_c, advantage_estimator='gae', penalty_coefficient=pen,
+        standardized_adv_r=True, standardized_adv_c=True, num_envs=N)
+    rew = rng.random((T, N)).astype(np.float32)
+    cost = (rng.random((T, N)) < 0.2).astype(np.float32)
+    val_r = rng.standard_normal((T, N)).astype(np.float32)
+    val_c = rng.standard_normal((T, N)).astype(np.float32)
+    obs = rng.standard_normal((T, N, O)).astype(np.float32)
+    act = rng.standard_normal((T, N, A)).astype(np.float32)
+    logp = rng.standard_normal((T, N)).astype(np.float32)
+    flags = np.zeros((T, N), np.uint8)
+    flags[rng.random((T, N)) < 0.06] |= 1
+    flags[rng.random((T, N)) < 0.06] |= 2
+    boot_r = rng.standard_normal((T, N)).astype(np.float32)
+    boot_c = rng.standard_normal((T, N)).astype(np.float32)
+    for t in range(T):
+        buf.store(obs=torch.as_tensor(obs[t]), act=torch.as_tensor(act[t]),
+                  reward=torch.as_tensor(rew[t]), cost=torch.as_tensor(cost[t]),
+                  value_r=torch.as_tensor(val_r[t]), value_c=torch.as_tensor(val_c[t]),
+                  logp=torch.as_tensor(logp[t]))
+        for i in range(N):
+            if flags[t, i] or t == T - 1:
+                term = bool(flags[t, i] & 1)
+                lr = torch.zeros(1) if term else torch.as_tensor(boot_r[t, i:i + 1])
+                lc = torch.zeros(1) if term else torch.as_tensor(boot_c[t, i:i + 1])
+                buf.finish_path(lr, lc, i)
+    raw = {k: np.stack([b.data[k].numpy().copy() for b in buf.buffers], 1)  # -> [T, N]
+           for k in ('adv_r', 'adv_c', 'target_value_r', 'target_value_c', 'discounted_ret')}
+    data = buf.get()
+    np.savez(os.path.join(OUT, 'buffer_gae.npz'), rew=rew, cost=cost, val_r=val_r, val_c=val_c,
+             obs=obs, act=act, logp=logp, flags=flags, boot_r=boot_r, boot_c=boot_c,
+             gamma=gamma, lam=lam, lam_c=lam_c, pen=pen,
+             **{'raw_' + k: v for k, v in raw.items()},
+             **{'get_' + k: v.numpy() for k, v in data.items()})
+
+
+def gen_normalizer():
+    rng = np.random.default_rng(3)
+    norm = Normalizer((5,), clip=5)
+    batches = [rng.standard_normal((n, 5)).astype(np.float32) * s + m
+               for n, s, m in [(16, 1.0, 0.0), (3, 2.0, 1.0), (16, 0.5, -1.0), (1, 1.0, 0.0), (16, 3.0, 2.0)]]
+    out = {'nb': len(batches)}
+    for i, b in enumerate(batches):
+        y = norm.normalize(torch.as_tensor(b)).numpy()
+        out[f'x{i}'] = b; out[f'y{i}'] = y
+        out[f'mean{i}'] = norm.mean.numpy().copy(); out[f'std{i}'] = norm.std.numpy().copy()
+    np.savez(os.path.join(OUT, 'normalizer.npz'), **out)
+
+
+@env_register
+class RefSyntheticBox(CMDP):
+    """The synthetic Box env as an ordinary reference CMDP (torch-CPU wrapper around the numpy
+    spec in oracle/synthetic_env.py) so the unmodified reference classes can roll it out."""
+
+    _support_envs = ['SyntheticBox-v0']  # noqa: RUF012
+    need_auto_reset_wrapper = False
+    need_time_limit_wrapper = False
+    need_evaluation = False
+
+    def __init__(self, env_id, num_envs=1, device='cpu', **kw):
+        super().__init__(env_id)
+        self._num_envs = num_envs
+        self._kw = dict(kw)
+        self._env = None
+        O, A = kw.get('obs_dim', 60), kw.get('act_dim', 8)
+        self._observation_space = Box(-10.0, 10.0, (O,))
+        self._action_space = Box(-1.0, 1.0, (A,))
+        self._seed = 0
+
+    def set_seed(self, seed):
+        self._seed = seed
+        self._env = OracleEnv(self._num_envs, seed=seed, **self._kw)
+
+    def reset(self, seed=None, options=None):
+        if self._env is None:
+            self.set_seed(self._seed)
+        return torch.as_tensor(self._env.reset()), {}
+
+    def step(self, action):
+        nobs, rew, cost, term, trunc, final, fin = self._env.step(action.numpy())
+        info = {}
+        if fin.any():
+            info['final_observation'] = torch.as_tensor(final.copy())
+            info['_final_observation'] = torch.as_tensor(fin)
+        return (torch.as_tensor(nobs), torch.as_tensor(rew), torch.as_tensor(cost),
+                torch.as_tensor(term), torch.as_tensor(trunc), info)
+
+    def render(self):
+        return None
+
+    def close(self):
+        pass
+
+    @property
+    def max_episode_steps(self):
+        return self._kw.get('max_episode_steps', 64)
+
+
+def _build_algo(algo, N, T, O, A, seed, extra_algo=None, tmax=8, term_prob=0.05, epochs=2):
+    from omnisafe.utils.config import get_default_kwargs_yaml
+    from omnisafe.utils.tools import recursive_check_config
+    from omnisafe.algorithms import registry
+
+    cfgs = get_default_kwargs_yaml(algo, 'SyntheticBox-v0', 'on-policy')
+    custom = {
+        'seed': seed,
+        'train_cfgs': {'vector_env_nums': N, 'total_steps': N * T * epochs, 'torch_threads': 1},
+        'algo_cfgs': {'steps_per_epoch': N * T, 'batch_size': 32, 'update_iters': 2, **(extra_algo or {})},
+        'logger_cfgs': {'use_tensorboard': False, 'use_wandb': False, 'log_dir': '/tmp/osb_golden_runs',
+                        'window_lens': 10},
+        'env_cfgs': {'obs_dim': O, 'act_dim': A, 'max_episode_steps': tmax, 'term_prob': term_prob},
+    }
+    recursive_check_config(custom, cfgs)
+    cfgs.recurisve_update(custom)
+    cfgs.recurisve_update({'exp_name': f'{algo}-golden', 'env_id': 'SyntheticBox-v0', 'algo': algo})
+    cfgs.train_cfgs.recurisve_update({'epochs': epochs})
+    return registry.get(algo)(env_id='SyntheticBox-v0', cfgs=cfgs)
+
+
+def _flat_theta(ac):
+    parts = []
+    for net in (ac.actor, ac.reward_critic, ac.cost_critic):
+        parts += [p.detach().reshape(-1) for p in net.parameters()]
+    return torch.cat(parts).numpy().copy()
+
+
+def gen_rollout():
+    """One epoch of the unmodified OnPolicyAdapter.rollout + buffer on the synthetic env."""
+    import torch.distributions.normal as tdn
+    import torch.distributions.utils as tdu
+
+    N, T, O, A, seed = 8, 24, 12, 3, 5
+    algo = _build_algo('PPOLag', N, T, O, A, seed)
+    theta = _flat_theta(algo._actor_critic)
+    drawn = []
+    orig = tdn._standard_normal
+
+    def rec(shape, dtype, device):
+        e = orig(shape, dtype, device)
+        drawn.append(e.clone())
+        return e
+
+    tdn._standard_normal = rec
+    try:
+        algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf,
+                          logger=algo._logger)
+    finally:
+        tdn._standard_normal = orig
+    eps = np.stack([d.numpy() for d in drawn if tuple(d.shape) == (N, A)])
+    assert eps.shape[0] == T, eps.shape
+    bufs = algo._buf.buffers
+    fields = ('obs', 'act', 'reward', 'cost', 'value_r', 'value_c', 'logp', 'adv_r', 'adv_c',
+              'target_value_r', 'target_value_c', 'discounted_ret')
+    data = {k: np.stack([b.data[k].numpy().copy() for b in bufs], 1) for k in fields}
+    window = {k: np.array(list(algo._logger._data[k]), np.float32)
+              for k in ('Metrics/EpRet', 'Metrics/EpCost', 'Metrics/EpLen')}
+    norm = algo._env._env  # walk the wrapper stack to ObsNormalize
+    while not hasattr(norm, '_obs_normalizer'):
+        norm = norm._env
+    nz = norm._obs_normalizer
+    got = algo._buf.get()
+    np.savez(os.path.join(OUT, 'rollout_ppolag.npz'), N=N, T=T, O=O, A=A, seed=seed, theta=theta,
+             eps=eps, tmax=8, term_prob=0.05, gamma=0.99, lam=0.95, lam_c=0.95,
+             norm_mean=nz.mean.numpy(), norm_std=nz.std.numpy(), norm_count=int(nz._count),
+             win_ret=window['Metrics/EpRet'], win_cost=window['Metrics/EpCost'],
+             win_len=window['Metrics/EpLen'],
+             **{'slab_' + k: v for k, v in data.items()},
+             **{'get_' + k: v.numpy() for k, v in got.items()})
+    return algo
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(1)
+    gen_discount_cumsum()
+    gen_buffer_gae()
+    gen_normalizer()
+    gen_rollout()
+    print('golden fixtures written to', OUT)

@@ -1,0 +1,86 @@
+"""Pin the CPU oracle against (a) the reference's own known-answer tests and (b) golden fixtures
+produced by the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+
+from oracle import gae as ogae
+from oracle import rollout as orollout
+from oracle.normalizer import Normalizer
+from oracle.synthetic_env import SyntheticBoxEnv
+
+
+def test_discount_cumsum_reference_known_answers():
+    # reference tests/test_utils.py:L95-115
+    x = np.array([1, 2, 3, 4, 5], np.float64)
+    np.testing.assert_allclose(ogae.discount_cumsum(x, 0.9), [11.4265, 11.5850, 10.65, 8.5, 5.0], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(ogae.discount_cumsum(x, 0.99), [14.6045, 13.7419, 11.8605, 8.95, 5.0], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(ogae.discount_cumsum(x, 0.999), [14.9600, 13.9740, 11.9860, 8.9950, 5.0], rtol=1e-5, atol=1e-4)
+
+
+def test_discount_cumsum_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'discount_cumsum.npz'))
+    for i in range(int(g['n'])):
+        y = ogae.discount_cumsum(g[f'x{i}'], float(g[f'd{i}']))
+        assert np.array_equal(y, g[f'y{i}']), f'vector {i} not bit-identical to the reference'
+
+
+def test_buffer_gae_golden_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'buffer_gae.npz'))
+    out = ogae.dual_gae_slab(g['rew'], g['cost'], g['val_r'], g['val_c'], g['flags'], g['boot_r'],
+                             g['boot_c'], float(g['gamma']), float(g['lam']), float(g['lam_c']),
+                             float(g['pen']))
+    for ours, ref in (('adv_r', 'raw_adv_r'), ('adv_c', 'raw_adv_c'), ('tv_r', 'raw_target_value_r'),
+                      ('tv_c', 'raw_target_value_c'), ('disc_ret', 'raw_discounted_ret')):
+        assert np.array_equal(out[ours], g[ref]), f'{ours} differs from the reference buffer'
+    # get(): env-major order + standardisation
+    T, N = g['rew'].shape
+    sr, sc = ogae.standardize(out['adv_r'], out['adv_c'])
+    em = lambda x: x.T.reshape(T * N, *x.shape[2:]) if x.ndim == 2 else x.transpose(1, 0, 2).reshape(T * N, -1)
+    np.testing.assert_allclose(em(sr), g['get_adv_r'], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(em(sc), g['get_adv_c'], rtol=2e-6, atol=2e-6)
+    assert np.array_equal(em(out['tv_r']), g['get_target_value_r'])
+    assert np.array_equal(em(g['obs']), g['get_obs'])
+
+
+def test_normalizer_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'normalizer.npz'))
+    norm = Normalizer((5,))
+    for i in range(int(g['nb'])):
+        y = norm.normalize(g[f'x{i}'])
+        np.testing.assert_allclose(norm.mean, g[f'mean{i}'], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(norm.std, g[f'std{i}'], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(y, g[f'y{i}'], rtol=1e-5, atol=1e-5)
+
+
+def test_rollout_golden(golden_dir):
+    """Oracle rollout == unmodified OnPolicyAdapter.rollout + buffer on the synthetic env."""
+    g = np.load(os.path.join(golden_dir, 'rollout_ppolag.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    env = SyntheticBoxEnv(N, O, A, max_episode_steps=int(g['tmax']), seed=int(g['seed']),
+                          term_prob=float(g['term_prob']))
+    norm = Normalizer((O,))
+    window = []
+    sl = orollout.rollout_epoch(env, norm, g['theta'], T, g['eps'], window=window)
+    tol = dict(rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **tol)
+    np.testing.assert_allclose(sl['act'], g['slab_act'], **tol)
+    np.testing.assert_allclose(sl['rew'], g['slab_reward'], **tol)
+    assert np.array_equal(sl['cost'], g['slab_cost'])
+    np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], **tol)
+    np.testing.assert_allclose(sl['val_c'], g['slab_value_c'], **tol)
+    np.testing.assert_allclose(sl['logp'], g['slab_logp'], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(norm.mean, g['norm_mean'], **tol)
+    np.testing.assert_allclose(norm.std, g['norm_std'], **tol)
+    assert norm.count == int(g['norm_count'])
+    out = ogae.dual_gae_slab(sl['rew'], sl['cost'], sl['val_r'], sl['val_c'], sl['flags'],
+                             sl['boot_r'], sl['boot_c'], float(g['gamma']), float(g['lam']), float(g['lam_c']))
+    np.testing.assert_allclose(out['adv_r'], g['slab_adv_r'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out['adv_c'], g['slab_adv_c'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out['tv_r'], g['slab_target_value_r'], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out['disc_ret'], g['slab_discounted_ret'], rtol=1e-4, atol=2e-5)
+    # Logger window (maxlen 10): last finished episodes in (step, env) order
+    w = np.array(window[-10:], np.float32)
+    np.testing.assert_allclose(w[:, 0], g['win_ret'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(w[:, 1], g['win_cost'])
+    np.testing.assert_allclose(w[:, 2], g['win_len'])
