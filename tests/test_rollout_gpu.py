@@ -1,0 +1,147 @@
+"""GPU parity: fused rollout-step kernel (env + ObsNormalize + 3 MLP forwards + sample + append)
+vs the oracle and vs the golden fixture produced by the unmodified reference."""
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor_critic as oac
+from oracle import rollout as orollout
+from oracle.normalizer import Normalizer as ONormalizer
+from oracle.synthetic_env import SyntheticBoxEnv as OEnv
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs(obs_normalize=True, window=100, **env_cfgs):
+    return NS(algo_cfgs=NS(obs_normalize=obs_normalize, reward_normalize=False, cost_normalize=False),
+              logger_cfgs=NS(window_lens=window), env_cfgs=env_cfgs)
+
+
+def _model_cfgs():
+    net = NS(hidden_sizes=[64, 64], activation='tanh', lr=3e-4)
+    return NS(actor=net, critic=net, actor_type='gaussian_learning', linear_lr_decay=True,
+              weight_initialization_mode='kaiming_uniform')
+
+
+def _gpu_rollout(dev, N, T, O, A, seed, theta, eps, tmax, term_prob, obs_normalize=True, window=100, epochs=1):
+    from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
+    from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
+    from omnisafe_b200.models import ConstraintActorCritic
+
+    cfgs = _cfgs(obs_normalize, window, obs_dim=O, act_dim=A, max_episode_steps=tmax, term_prob=term_prob)
+    ad = OnPolicyAdapter('SyntheticBox-v0', N, seed, cfgs, device=dev)
+    agent = ConstraintActorCritic(O, A, _model_cfgs(), epochs=1, device=dev)
+    agent.load_flat(theta)
+    buf = VectorOnPolicyBuffer(O, A, T, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=N, device=dev)
+    outs = []
+    for e in range(epochs):
+        ad.rollout(T, agent, buf, eps=None if eps is None else torch.as_tensor(eps[e]).to(dev))
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy().copy() for k, v in buf.data.items() if v is not None})
+    return ad, buf, outs
+
+
+def _compare(sl_gpu, sl_ref, tol=2e-5):
+    t = dict(rtol=tol, atol=tol)
+    np.testing.assert_allclose(sl_gpu['obs'], sl_ref['obs'], **t)
+    np.testing.assert_allclose(sl_gpu['act'], sl_ref['act'], **t)      # identical eps -> same actions
+    np.testing.assert_allclose(sl_gpu['reward'], sl_ref['rew'], **t)
+    assert (sl_gpu['cost'] != sl_ref['cost']).mean() < 1e-3
+    np.testing.assert_allclose(sl_gpu['value_r'], sl_ref['val_r'], **t)
+    np.testing.assert_allclose(sl_gpu['value_c'], sl_ref['val_c'], **t)
+    np.testing.assert_allclose(sl_gpu['logp'], sl_ref['logp'], rtol=tol, atol=5e-5)
+    assert np.array_equal(sl_gpu['flags'], sl_ref['flags'])
+    ends = (sl_ref['flags'] != 0)
+    ends[-1, :] = True
+    need = ends & ((sl_ref['flags'] & 1) == 0)
+    np.testing.assert_allclose(sl_gpu['boot_r'][need], sl_ref['boot_r'][need], **t)
+    np.testing.assert_allclose(sl_gpu['boot_c'][need], sl_ref['boot_c'][need], **t)
+
+
+def test_rollout_golden_reference(cuda, golden_dir):
+    """Same seed / params / noise as the unmodified reference run -> same slabs."""
+    g = np.load(os.path.join(golden_dir, 'rollout_ppolag.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    ad, buf, outs = _gpu_rollout(cuda, N, T, O, A, int(g['seed']), g['theta'], g['eps'][None],
+                                 int(g['tmax']), float(g['term_prob']), window=10)
+    sl = outs[0]
+    t = dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **t)
+    np.testing.assert_allclose(sl['act'], g['slab_act'], **t)
+    np.testing.assert_allclose(sl['reward'], g['slab_reward'], **t)
+    assert np.array_equal(sl['cost'], g['slab_cost'])
+    np.testing.assert_allclose(sl['value_r'], g['slab_value_r'], **t)
+    np.testing.assert_allclose(sl['logp'], g['slab_logp'], rtol=2e-5, atol=5e-5)
+    nz = ad._obs_normalizer
+    np.testing.assert_allclose(nz.mean.cpu().numpy(), g['norm_mean'], **t)
+    np.testing.assert_allclose(nz.std.cpu().numpy(), g['norm_std'], **t)
+    assert int(nz.count[0]) == int(g['norm_count'])
+    buf.finish_paths()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(buf.data['adv_r'].cpu().numpy(), g['slab_adv_r'], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(buf.data['adv_c'].cpu().numpy(), g['slab_adv_c'], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(buf.data['target_value_r'].cpu().numpy(), g['slab_target_value_r'], rtol=1e-4, atol=5e-5)
+    # Logger window (deque maxlen 10) of finished episodes
+    meta = ad.ep_meta.cpu().numpy()
+    ring = ad.ep_ring.cpu().numpy()
+    cnt, head = int(meta[0]), int(meta[1])
+    assert cnt == len(g['win_ret'])
+    order = [(head - cnt + i) % 10 for i in range(cnt)]
+    np.testing.assert_allclose(ring[0][order], g['win_ret'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ring[1][order], g['win_cost'])
+    np.testing.assert_allclose(ring[2][order], g['win_len'])
+    ws = ad.window_sums.cpu().numpy()
+    np.testing.assert_allclose(ws[1] / ws[3], g['win_cost'].mean(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('N,T,O,A,tmax,term_prob,norm', [
+    (64, 40, 60, 8, 16, 0.0, True),
+    (50, 33, 60, 8, 7, 0.05, True),       # ragged tile (N % 32 != 0), terminations + truncations
+    (32, 20, 17, 6, 5, 0.1, False),       # no ObsNormalize
+    (40, 12, 111, 8, 6, 0.03, True),      # obs dim > 64: two layer-1 chunks
+    (33, 6, 376, 8, 3, 0.0, True),        # Humanoid-like obs dim: six chunks
+])
+def test_rollout_vs_oracle(cuda, N, T, O, A, tmax, term_prob, norm):
+    rng = np.random.default_rng(N * 7 + T)
+    theta = oac.init_theta(O, A, seed=3)
+    epochs = 2
+    eps = rng.standard_normal((epochs, T, N, A)).astype(np.float32)
+    ad, buf, outs = _gpu_rollout(cuda, N, T, O, A, 9, theta, eps, tmax, term_prob, obs_normalize=norm,
+                                 window=16, epochs=epochs)
+    env = OEnv(N, O, A, max_episode_steps=tmax, seed=9, term_prob=term_prob)
+    onorm = ONormalizer((O,))
+    window = []
+    for e in range(epochs):   # state (normaliser, episode counters, window) carries across epochs
+        ref = orollout.rollout_epoch(env, onorm, theta, T, eps[e], obs_normalize=norm, window=window)
+        _compare(outs[e], ref)
+    w = np.array(window[-16:], np.float32)
+    meta = ad.ep_meta.cpu().numpy(); ring = ad.ep_ring.cpu().numpy()
+    cnt, head = int(meta[0]), int(meta[1])
+    assert cnt == len(w)
+    order = [(head - cnt + i) % 16 for i in range(cnt)]
+    np.testing.assert_allclose(ring[0][order], w[:, 0], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(ring[1][order], w[:, 1])
+    np.testing.assert_allclose(ring[2][order], w[:, 2])
+
+
+def test_rollout_philox_fast_mode(cuda):
+    """Fast mode (in-kernel Philox noise): actions are mu + sigma*eps with eps ~ N(0,1) and the
+    stored log-prob is consistent with the stored action; deterministic under a fixed seed."""
+    N, T, O, A = 4096, 8, 60, 8
+    theta = oac.init_theta(O, A, seed=1)
+    _, _, o1 = _gpu_rollout(cuda, N, T, O, A, 4, theta, None, 64, 0.0)
+    _, _, o2 = _gpu_rollout(cuda, N, T, O, A, 4, theta, None, 64, 0.0)
+    assert np.array_equal(o1[0]['act'], o2[0]['act'])
+    sl = o1[0]
+    nets = oac.unflatten(torch.as_tensor(theta), O, A)
+    obs = torch.as_tensor(sl['obs'])
+    with torch.no_grad():
+        dist = oac.actor_dist(nets['actor'], obs)
+        z = ((torch.as_tensor(sl['act']) - dist.loc) / dist.scale).numpy()
+        logp = dist.log_prob(torch.as_tensor(sl['act'])).sum(-1).numpy()
+    np.testing.assert_allclose(sl['logp'], logp, rtol=1e-4, atol=1e-3)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs(np.corrcoef(z[0, :, 0], z[1, :, 0])[0, 1]) < 0.05
