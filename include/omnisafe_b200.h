@@ -106,6 +106,102 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
 int osb_episode_window(const unsigned char* flags, const float* epfin, int T, int N, int W,
                        float* ring, int* meta, double* window_sums, void* stream);
 
+/* ---- learner: fused minibatch forward + loss + backward ------------------------------------
+ * replaces PolicyGradient._update minibatch body  algorithms/on_policy/base/policy_gradient.py:L369-381
+ *          _update_reward_critic/_update_cost_critic/_update_actor                       :L407-524
+ *          PPO._loss_pi  base/ppo.py:L35-87;  PPOLag._compute_adv_surrogate  naive_lagrange/ppo_lag.py:L82-102
+ *          PolicyGradient._loss_pi  base/policy_gradient.py:L551-588;  CPO._loss_pi_cost  second_order/cpo.py:L182-212
+ *          FOCOPS._loss_pi  first_order/focops.py:L62-108
+ * Batch tensors are the slabs ([rows] / [rows][O] / [rows][A], row = t*N + i); advantages are the
+ * RAW GAE outputs and are standardised on the fly with moments[4] (osb_adv_moments).  A minibatch is
+ * the window [mb_start, mb_start+mb_count) of a permutation of [0,total): perm (slab rows, parity
+ * mode) or NULL (in-kernel keyed Feistel bijection).  loss_kind: 0 PPO-clip, 1 plain ratio*adv,
+ * 2 FOCOPS, 3 cost surrogate.  lagrange: device scalar lambda or NULL (0).  net_mask bit0 actor,
+ * bit1 reward critic, bit2 cost critic.  gpart: osb_update_grid_blocks(mb_count) * P floats;
+ * stats_part: that many * 3 * 8 floats.  stop_flag (device int, may be NULL): non-zero = no-op. */
+int osb_update_grid_blocks(int mb_count);
+int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const float* act,
+                       const float* logp, const float* adv_r, const float* adv_c,
+                       const float* tv_r, const float* tv_c, const float* mu_old,
+                       const float* moments, const int* perm, long long total, unsigned perm_seed,
+                       long long mb_start, int mb_count, int loss_kind, float clip,
+                       float entropy_coef, float focops_lam, float focops_eta,
+                       const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                       float* stats_part, const int* stop_flag, void* stream);
+/* Full-batch actor pass (KL early stop policy_gradient.py:L383-397; TRPO/CPO line-search
+ * evaluations trpo.py:L102-138, cpo.py:L114-171).  mu_store != NULL: write mu(theta) per row.
+ * Otherwise out[8] <- {sum_s sum_a KL(old||new), sum ratio*adv, sum ratio*adv_c, sum ratio, count,
+ * sum ratio*adv_r, 0, 0} in fp64; rows 0, stride, 2*stride, ...; workspace: 296*8 doubles. */
+int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, const float* act,
+                   const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
+                   const float* logstd_old, const float* moments, const float* lagrange,
+                   long long total, int stride, float* mu_store, double* workspace, double* out,
+                   void* stream);
+/* Fisher-vector product partials (NaturalPG._fvp, base/natural_pg.py:L74-119, analytic
+ * Gauss-Newton form; damping is added by osb_reduce_partials).  gpart: blocks * P_actor floats. */
+int osb_fvp_grid_blocks(long long total, int stride);
+int osb_fvp_partials(const float* theta_actor, const float* vec, int O, int A, const float* obs,
+                     long long total, int stride, float* gpart, void* stream);
+
+/* ---- optimiser side --------------------------------------------------------------------------
+ * osb_grad_reduce: grad <- sum of CTA partials (+ 2*critic_norm_coef*theta for critics,
+ * policy_gradient.py:L431-433); advances adam_step[net]; accumulates train_stats[3][8]
+ * ({sum of minibatch mean loss, mean ratio, mean kl, #minibatches}).  sumsq_part: 3*osb_optim_blocks.
+ * osb_clip_adam: clip_grad_norm_ per network (do_clip) and torch.optim.Adam step (do_adam);
+ * multi-rank order = clip -> all-reduce SUM -> grad_scale = 1/world -> Adam (policy_gradient.py:L437-443). */
+int osb_optim_blocks(int O, int A);
+int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                    const float* theta, float* grad, float critic_norm_coef, int net_mask,
+                    float* sumsq_part, int* adam_step, float* train_stats, const int* stop_flag,
+                    void* stream);
+int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const int* adam_step,
+                  const float* sumsq_part, int O, int A, float max_grad_norm, float lr_actor,
+                  float lr_critic_r, float lr_critic_c, float grad_scale, int do_clip, int do_adam,
+                  int net_mask, const int* stop_flag, void* stream);
+/* Lagrange.update_lagrange_multiplier (common/lagrange.py:L114-136) on the device: Adam step on
+ * lambda with grad -(Jc - cost_limit), Jc = window_sums[1]/window_sums[3], clamp to
+ * [0, upper_bound] (upper_bound < 0 = none).  state[4] = {lambda, m, v, t}.  nan_flag <- 1 when no
+ * episode has finished yet (the reference asserts, naive_lagrange/ppo_lag.py:L74). */
+int osb_lagrange_update(const double* window_sums, float cost_limit, float lambda_lr,
+                        float upper_bound, float* state, int* nan_flag, void* stream);
+/* kl = eval_out[0]/eval_out[4]; kl_state[4] = {last kl, passes done, stopped, 0}. */
+int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
+                 float* kl_state, void* stream);
+/* out[q] = scale * sum_b gpart[b][q] + add_scale * add[q]  (add may be NULL). */
+int osb_reduce_partials(const float* gpart, int nblocks, int n, float scale, const float* add,
+                        float add_scale, float* out, void* stream);
+/* conjugate_gradients (utils/math.py:L86-132) as device-resident state: x, r, p [n],
+ * cg_scalars[4] = {rdotr, converged, iterations, 0}; the caller computes z = F p between steps. */
+int osb_cg_init(const float* b, int n, float* x, float* r, float* p, float* cg_scalars, void* stream);
+int osb_cg_step(const float* z, int n, float* x, float* r, float* p, float* cg_scalars,
+                float residual_tol, float eps, void* stream);
+int osb_dot(const float* a, const float* b, int n, float* out, void* stream);
+int osb_axpy(const float* x, const float* y, float alpha, int n, float* out, void* stream);
+
+/* ---- epoch driver + NCCL -------------------------------------------------------------------
+ * One epoch of PolicyGradient._update (policy_gradient.py:L345-405) issued from C: old-policy
+ * snapshot, update_iters passes of minibatch steps (grad -> reduce -> clip -> [all-reduce] ->
+ * Adam), full-batch KL after each pass, device-side early stop.  comm = handle from osb_nccl_init
+ * (or NULL for a single rank). */
+int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                         int O, int A, const float* obs, const float* act, const float* logp,
+                         const float* adv_r, const float* adv_c, const float* tv_r,
+                         const float* tv_c, float* mu_old, float* logstd_old, const float* moments,
+                         const int* perm, long long total, unsigned perm_seed, int batch_size,
+                         int update_iters, int loss_kind, float clip, float entropy_coef,
+                         float focops_lam, float focops_eta, const float* lagrange, int net_mask,
+                         float critic_norm_coef, float max_grad_norm, float lr_actor,
+                         float lr_critic, float target_kl, int kl_early_stop, float* gpart,
+                         float* stats_part, float* sumsq_part, float* train_stats, double* eval_ws,
+                         double* eval_out, int* stop_flag, float* kl_state, void* comm,
+                         int world_size, void* stream);
+/* NCCL via dlopen(libpath) of the libnccl.so.2 torch already loaded (distributed.py:L142-228). */
+int osb_nccl_unique_id(const char* libpath, unsigned char* id128);
+int osb_nccl_init(const char* libpath, const unsigned char* id128, int nranks, int rank,
+                  void** comm_out);
+int osb_nccl_allreduce(void* comm, void* buf, long long count, int is_f64, void* stream);
+int osb_nccl_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,328 @@
+// Optimiser-side kernels: partial-gradient reduction, per-network grad-norm clipping, Adam,
+// on-device Lagrange multiplier update, KL early-stop flag, and the block-parallel conjugate
+// gradient vector algebra for CPO / TRPO-Lag.
+//
+// Replaces the reference's
+//   clip_grad_norm_ + optimizer.step()   algorithms/on_policy/base/policy_gradient.py:L436-443,L476-483,L517-524
+//   critic L2 regulariser                base/policy_gradient.py:L431-433
+//   torch.optim.Adam (single-tensor)     (dependency; restated: lerp first moment, addcmul second)
+//   Lagrange.update_lagrange_multiplier  common/lagrange.py:L114-136
+//   KL early stop                        base/policy_gradient.py:L383-397
+//   conjugate_gradients                  utils/math.py:L86-132
+#include "common.cuh"
+#include "mlp.cuh"
+
+namespace osb {
+
+constexpr int OT = 256;
+
+struct ReduceArgs {
+    const float* gpart;       // [nblocks][P]
+    const float* stats_part;  // [nblocks][3][8]
+    int nblocks, P, O, A;
+    const float* theta;
+    float* grad;              // [P]
+    float critic_norm_coef;   // 0 -> off
+    int net_mask;
+    float* sumsq_part;        // [3][NB]
+    int* adam_step;           // [3]
+    float* train_stats;       // [3][8] running sums over minibatch steps
+    const int* stop_flag;
+};
+
+__global__ void __launch_bounds__(OT) grad_reduce_kernel(ReduceArgs p) {
+    if (p.stop_flag && *p.stop_flag) return;
+    const int net = blockIdx.y;
+    if (!((p.net_mask >> net) & 1)) return;
+    __shared__ float red[OT / 32];
+    const NetLayout L = net_layout(net, p.O, p.A);
+    const int noff = net_offset(net, p.O, p.A);
+    const int pl = blockIdx.x * OT + threadIdx.x;
+    float g = 0.f;
+    if (pl < L.size) {
+        const int q = noff + pl;
+        for (int b = 0; b < p.nblocks; ++b) g += p.gpart[(size_t)b * p.P + q];
+        if (net != 0 && p.critic_norm_coef > 0.f) g += 2.f * p.critic_norm_coef * p.theta[q];
+        p.grad[q] = g;
+    }
+    float s = warp_sum(g * g);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < OT / 32; ++w) t += red[w];
+        p.sumsq_part[net * gridDim.x + blockIdx.x] = t;
+        if (blockIdx.x == 0) {
+            p.adam_step[net] += 1;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int b = 0; b < p.nblocks; ++b)
+                for (int i = 0; i < 4; ++i) acc[i] += p.stats_part[((size_t)b * 3 + net) * 8 + i];
+            const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
+            float* ts = p.train_stats + net * 8;
+            ts[0] += acc[0] * inv;   // mean loss of this minibatch
+            ts[1] += acc[1] * inv;   // mean ratio
+            ts[2] += acc[2] * inv;   // mean kl (FOCOPS)
+            ts[3] += 1.f;            // number of minibatch steps
+        }
+    }
+}
+
+struct AdamArgs {
+    float* grad;
+    float* theta;
+    float* m;
+    float* v;
+    const int* adam_step;      // [3]
+    const float* sumsq_part;   // [3][NB]
+    int NB, O, A;
+    float max_grad_norm;       // <= 0 -> no clipping
+    float lr[3];
+    float grad_scale;          // 1 / world_size applied before Adam (avg_grads)
+    int do_clip, do_adam, net_mask;
+    const int* stop_flag;
+};
+
+__global__ void __launch_bounds__(OT) clip_adam_kernel(AdamArgs p) {
+    if (p.stop_flag && *p.stop_flag) return;
+    const int net = blockIdx.y;
+    if (!((p.net_mask >> net) & 1)) return;
+    const NetLayout L = net_layout(net, p.O, p.A);
+    const int pl = blockIdx.x * OT + threadIdx.x;
+    if (pl >= L.size) return;
+    const int q = net_offset(net, p.O, p.A) + pl;
+    float g = p.grad[q];
+    if (p.do_clip && p.max_grad_norm > 0.f) {
+        float tot = 0.f;
+        for (int b = 0; b < p.NB; ++b) tot += p.sumsq_part[net * p.NB + b];
+        const float coef = fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f);
+        g *= coef;
+        p.grad[q] = g;
+    }
+    if (!p.do_adam) return;
+    g *= p.grad_scale;
+    // torch.optim.Adam, single-tensor path (betas 0.9/0.999, eps 1e-8, no weight decay)
+    const int t = p.adam_step[net];
+    const double bc1 = 1.0 - pow(0.9, (double)t);
+    const double bc2 = 1.0 - pow(0.999, (double)t);
+    const float step_size = (float)((double)p.lr[net] / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    float m = p.m[q], v = p.v[q];
+    m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));                       // exp_avg.lerp_(grad, 1-b1)
+    v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
+    p.theta[q] = __fadd_rn(p.theta[q], __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+    p.m[q] = m; p.v[q] = v;
+}
+
+// lambda <- clamp(Adam(lambda, grad = -(Jc - limit)), 0, upper).  state[4] = {lambda, m, v, t}.
+// window_sums[4] = {sum EpRet, sum EpCost, sum EpLen, count} (already all-reduced).
+__global__ void lagrange_update_kernel(const double* __restrict__ window_sums, float cost_limit,
+                                       float lambda_lr, float upper_bound, float* __restrict__ state,
+                                       int* __restrict__ nan_flag) {
+    if (threadIdx.x != 0) return;
+    const double cnt = window_sums[3];
+    if (!(cnt > 0.0)) { *nan_flag = 1; return; }   // reference asserts `Jc` is not NaN (ppo_lag.py:L74)
+    const double jc = window_sums[1] / cnt;
+    const float g = (float)(-(jc - (double)cost_limit));
+    float lam = state[0], m = state[1], v = state[2];
+    const int t = (int)state[3] + 1;
+    const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+    m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));
+    v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), (float)sqrt(bc2)), 1e-8f);
+    lam = __fadd_rn(lam, __fmul_rn(-(float)((double)lambda_lr / bc1), __fdiv_rn(m, denom)));
+    lam = fmaxf(lam, 0.f);
+    if (upper_bound >= 0.f) lam = fminf(lam, upper_bound);
+    state[0] = lam; state[1] = m; state[2] = v; state[3] = (float)t;
+}
+
+// KL early stop: eval_out[0] = sum KL (over samples and action dims), eval_out[4] = sample count.
+// kl_state[4] = {last kl, iterations executed, stopped flag as float, 0}
+__global__ void kl_check_kernel(const double* __restrict__ eval_out, float target_kl, int early_stop,
+                                int* __restrict__ stop_flag, float* __restrict__ kl_state) {
+    if (threadIdx.x != 0) return;
+    if (*stop_flag) return;
+    const float kl = (float)(eval_out[0] / eval_out[4]);
+    kl_state[0] = kl;
+    kl_state[1] += 1.f;
+    if (early_stop && kl > target_kl) { *stop_flag = 1; kl_state[2] = 1.f; }
+}
+
+// out[q] = scale * sum_b gpart[b][q] + add_scale * add[q]
+__global__ void __launch_bounds__(OT) reduce_partials_kernel(const float* __restrict__ gpart, int nblocks,
+                                                             int n, float scale, const float* __restrict__ add,
+                                                             float add_scale, float* __restrict__ out) {
+    const int q = blockIdx.x * OT + threadIdx.x;
+    if (q >= n) return;
+    float g = 0.f;
+    for (int b = 0; b < nblocks; ++b) g += gpart[(size_t)b * n + q];
+    g *= scale;
+    if (add) g += add_scale * add[q];
+    out[q] = g;
+}
+
+// ---- conjugate gradient (utils/math.py:L86-132); single CTA of 1024 threads ---------------------
+__device__ double block_dot(const float* a, const float* b, int n, double* sred) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)a[i] * (double)b[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sred[w];
+    __syncthreads();
+    return t;
+}
+
+// cg_scalars[4] = {rdotr, done flag, iterations run, 0}
+__global__ void __launch_bounds__(1024) cg_init_kernel(const float* __restrict__ b, int n, float* x,
+                                                       float* r, float* pv, float* cg_scalars) {
+    __shared__ double sred[32];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { x[i] = 0.f; r[i] = b[i]; pv[i] = b[i]; }
+    __syncthreads();
+    const double rr = block_dot(r, r, n, sred);
+    if (threadIdx.x == 0) { cg_scalars[0] = (float)rr; cg_scalars[1] = 0.f; cg_scalars[2] = 0.f; cg_scalars[3] = 0.f; }
+}
+
+__global__ void __launch_bounds__(1024) cg_step_kernel(const float* __restrict__ z, int n, float* x,
+                                                       float* r, float* pv, float* cg_scalars,
+                                                       float residual_tol, float eps) {
+    __shared__ double sred[32];
+    if (cg_scalars[1] != 0.f) return;   // converged earlier (uniform)
+    const float rdotr = cg_scalars[0];
+    const float pz = (float)block_dot(pv, z, n, sred);
+    const float alpha = rdotr / (pz + eps);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        x[i] += alpha * pv[i];
+        r[i] -= alpha * z[i];
+    }
+    __syncthreads();
+    const float new_rdotr = (float)block_dot(r, r, n, sred);
+    const bool done = sqrtf(new_rdotr) < residual_tol;
+    if (!done) {
+        const float mu = new_rdotr / (rdotr + eps);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) pv[i] = r[i] + mu * pv[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cg_scalars[2] += 1.f;
+        if (done) cg_scalars[1] = 1.f; else cg_scalars[0] = new_rdotr;
+    }
+}
+
+__global__ void __launch_bounds__(1024) dot_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                   int n, float* __restrict__ out) {
+    __shared__ double sred[32];
+    const double d = block_dot(a, b, n, sred);
+    if (threadIdx.x == 0) out[0] = (float)d;
+}
+
+// out = y + alpha * x
+__global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, int n,
+                            float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = y[i] + alpha * x[i];
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_optim_blocks(int O, int A) {
+    const int sa = actor_layout(O, A).size, sc = critic_layout(O, A).size;
+    const int mx = sa > sc ? sa : sc;
+    return (mx + OT - 1) / OT;
+}
+
+// grad <- sum of the CTA partials (+ 2*coef*theta for the critics); advances adam_step[net] and the
+// running training statistics.  sumsq_part: 3 * osb_optim_blocks floats.
+int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                    const float* theta, float* grad, float critic_norm_coef, int net_mask,
+                    float* sumsq_part, int* adam_step, float* train_stats, const int* stop_flag,
+                    void* stream) {
+    OSB_CHECK_ARG(gpart && stats_part && theta && grad && sumsq_part && adam_step && train_stats, "null pointer");
+    ReduceArgs p;
+    p.gpart = gpart; p.stats_part = stats_part; p.nblocks = nblocks; p.O = O; p.A = A;
+    p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size;
+    p.theta = theta; p.grad = grad; p.critic_norm_coef = critic_norm_coef; p.net_mask = net_mask;
+    p.sumsq_part = sumsq_part; p.adam_step = adam_step; p.train_stats = train_stats; p.stop_flag = stop_flag;
+    grad_reduce_kernel<<<dim3(osb_optim_blocks(O, A), 3), OT, 0, (cudaStream_t)stream>>>(p);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+// Per-network clip_grad_norm_ (do_clip) and/or Adam step (do_adam).  Multi-rank order of the
+// reference: clip locally -> average across ranks (grad_scale = 1/world after the all-reduce SUM) ->
+// optimizer step (policy_gradient.py:L437-443).
+int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const int* adam_step,
+                  const float* sumsq_part, int O, int A, float max_grad_norm, float lr_actor,
+                  float lr_critic_r, float lr_critic_c, float grad_scale, int do_clip, int do_adam,
+                  int net_mask, const int* stop_flag, void* stream) {
+    OSB_CHECK_ARG(grad && theta && adam_m && adam_v && adam_step && sumsq_part, "null pointer");
+    AdamArgs p;
+    p.grad = grad; p.theta = theta; p.m = adam_m; p.v = adam_v; p.adam_step = adam_step;
+    p.sumsq_part = sumsq_part; p.NB = osb_optim_blocks(O, A); p.O = O; p.A = A;
+    p.max_grad_norm = max_grad_norm; p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
+    p.grad_scale = grad_scale; p.do_clip = do_clip; p.do_adam = do_adam; p.net_mask = net_mask;
+    p.stop_flag = stop_flag;
+    clip_adam_kernel<<<dim3(p.NB, 3), OT, 0, (cudaStream_t)stream>>>(p);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_lagrange_update(const double* window_sums, float cost_limit, float lambda_lr,
+                        float upper_bound, float* state, int* nan_flag, void* stream) {
+    OSB_CHECK_ARG(window_sums && state && nan_flag, "null pointer");
+    lagrange_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(window_sums, cost_limit, lambda_lr, upper_bound, state, nan_flag);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
+                 float* kl_state, void* stream) {
+    OSB_CHECK_ARG(eval_out && stop_flag && kl_state, "null pointer");
+    kl_check_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(eval_out, target_kl, early_stop, stop_flag, kl_state);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_reduce_partials(const float* gpart, int nblocks, int n, float scale, const float* add,
+                        float add_scale, float* out, void* stream) {
+    OSB_CHECK_ARG(gpart && out && n > 0 && nblocks > 0, "bad argument");
+    reduce_partials_kernel<<<(n + OT - 1) / OT, OT, 0, (cudaStream_t)stream>>>(gpart, nblocks, n, scale, add, add_scale, out);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_cg_init(const float* b, int n, float* x, float* r, float* p, float* cg_scalars, void* stream) {
+    OSB_CHECK_ARG(b && x && r && p && cg_scalars && n > 0, "bad argument");
+    cg_init_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b, n, x, r, p, cg_scalars);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_cg_step(const float* z, int n, float* x, float* r, float* p, float* cg_scalars,
+                float residual_tol, float eps, void* stream) {
+    OSB_CHECK_ARG(z && x && r && p && cg_scalars && n > 0, "bad argument");
+    cg_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(z, n, x, r, p, cg_scalars, residual_tol, eps);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_dot(const float* a, const float* b, int n, float* out, void* stream) {
+    OSB_CHECK_ARG(a && b && out && n > 0, "bad argument");
+    dot_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_axpy(const float* x, const float* y, float alpha, int n, float* out, void* stream) {
+    OSB_CHECK_ARG(x && y && out && n > 0, "bad argument");
+    axpy_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, y, alpha, n, out);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+}  // extern "C"

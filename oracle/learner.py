@@ -1,0 +1,239 @@
+"""Oracle: the learner side -- Lagrange multiplier, PPO-Lag / FOCOPS minibatch update, KL early
+stop, Fisher-vector product, conjugate gradients and the CPO step logic (torch-CPU autograd).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates
+  common/lagrange.py:L67-136, algorithms/on_policy/base/policy_gradient.py:L308-588,
+  base/ppo.py:L35-87, naive_lagrange/ppo_lag.py:L52-102, first_order/focops.py:L62-230,
+  base/natural_pg.py:L74-230, base/trpo.py:L56-222, second_order/cpo.py:L57-462,
+  utils/math.py:L86-132, utils/tools.py:L35-129.
+torch.optim.Adam / clip_grad_norm_ / autograd are the reference's own (installed) dependencies and
+are called directly.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.distributions import Normal, kl_divergence
+from torch.nn.utils.clip_grad import clip_grad_norm_
+
+from oracle import actor_critic as ac
+
+NETS = ('actor', 'reward_critic', 'cost_critic')
+
+
+class Lagrange:
+    """common/lagrange.py:L67-136 with lambda_optimizer='Adam'."""
+
+    def __init__(self, cost_limit, lagrangian_multiplier_init, lambda_lr, upper_bound=None):
+        self.cost_limit = cost_limit
+        self.upper_bound = upper_bound
+        self.lam = torch.nn.Parameter(torch.as_tensor(max(lagrangian_multiplier_init, 0.0)))
+        self.opt = torch.optim.Adam([self.lam], lr=lambda_lr)
+
+    def update(self, Jc: float) -> float:
+        self.opt.zero_grad()
+        loss = -self.lam * (Jc - self.cost_limit)
+        loss.backward()
+        self.opt.step()
+        self.lam.data.clamp_(0.0, self.upper_bound)
+        return float(self.lam.item())
+
+
+class Learner:
+    """Parameters as per-tensor leaves in the reference's named_parameters order + 3 Adam optimisers."""
+
+    def __init__(self, theta, O, A, lr_actor=3e-4, lr_critic=3e-4):
+        self.O, self.A = O, A
+        lay = ac.layout(O, A)
+        theta = torch.as_tensor(np.asarray(theta, np.float32)).clone()
+        self.params = {}
+        for net in NETS:
+            self.params[net] = {name: theta[o:o + int(np.prod(shape))].view(*shape).clone().requires_grad_(True)
+                                for name, (o, shape) in lay[net]['entries'].items()}
+        self.opt = {
+            'actor': torch.optim.Adam(list(self.params['actor'].values()), lr=lr_actor) if lr_actor is not None else None,
+            'reward_critic': torch.optim.Adam(list(self.params['reward_critic'].values()), lr=lr_critic),
+            'cost_critic': torch.optim.Adam(list(self.params['cost_critic'].values()), lr=lr_critic),
+        }
+
+    # -- flat views (utils/tools.py:L35-129) --------------------------------------------------
+    def flat(self, net=None) -> np.ndarray:
+        nets = NETS if net is None else (net,)
+        return torch.cat([p.detach().reshape(-1) for n in nets for p in self.params[n].values()]).numpy().copy()
+
+    def flat_grad(self, net) -> torch.Tensor:
+        return torch.cat([p.grad.reshape(-1) for p in self.params[net].values()])
+
+    def set_flat(self, net, vec):
+        vec = torch.as_tensor(vec, dtype=torch.float32)
+        i = 0
+        for p in self.params[net].values():
+            n = p.numel()
+            p.data.copy_(vec[i:i + n].view_as(p))
+            i += n
+
+    def zero_grad(self, net):
+        for p in self.params[net].values():
+            p.grad = None
+
+    def dist(self, obs) -> Normal:
+        return ac.actor_dist(self.params['actor'], obs)
+
+    # -- losses -------------------------------------------------------------------------------
+    def loss_pi_ppo(self, obs, act, logp, adv, clip, entropy_coef=0.0):
+        d = self.dist(obs)
+        ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
+        rc = torch.clamp(ratio, 1 - clip, 1 + clip)
+        loss = -torch.min(ratio * adv, rc * adv).mean()
+        loss = loss - entropy_coef * d.entropy().mean()
+        return loss, ratio
+
+    def loss_pi_plain(self, obs, act, logp, adv):
+        d = self.dist(obs)
+        ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
+        return -(ratio * adv).mean()
+
+    def loss_pi_cost(self, obs, act, logp, adv_c):
+        d = self.dist(obs)
+        ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
+        return (ratio * adv_c).mean()
+
+    def loss_pi_focops(self, obs, act, logp, adv, old_mean, old_std, lam_f, eta, entropy_coef=0.0):
+        # NB: as in the reference, kl is [b, 1] while ratio * adv is [b]: the difference broadcasts
+        # to [b, b] before the mean (first_order/focops.py:L85-89).  Kept verbatim for parity.
+        d = self.dist(obs)
+        ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
+        kl = kl_divergence(d, Normal(old_mean, old_std)).sum(-1, keepdim=True)
+        loss = (kl - (1 / lam_f) * ratio * adv) * (kl.detach() <= eta).type(torch.float32)
+        return loss.mean() - entropy_coef * d.entropy().mean(), ratio
+
+    # -- one optimiser step per network (policy_gradient.py:L407-524) --------------------------
+    def _step(self, net, loss, max_grad_norm):
+        self.opt[net].zero_grad()
+        loss.backward()
+        if max_grad_norm is not None:
+            clip_grad_norm_(list(self.params[net].values()), max_grad_norm)
+        self.opt[net].step()
+
+    def critic_step(self, net, obs, target, critic_norm_coef, max_grad_norm):
+        v = ac.critic_value(self.params[net], obs)
+        loss = torch.nn.functional.mse_loss(v, target)
+        if critic_norm_coef:
+            for p in self.params[net].values():
+                loss = loss + p.pow(2).sum() * critic_norm_coef
+        self._step(net, loss, max_grad_norm)
+        return float(loss.item())
+
+    def update_ppo(self, data, perms, lam, *, batch_size, clip=0.2, entropy_coef=0.0, use_cost=True,
+                   critic_norm_coef=0.001, max_grad_norm=40.0, target_kl=0.02, kl_early_stop=True,
+                   focops=None):
+        """PolicyGradient._update / FOCOPS._update.  `data` holds env-major tensors as returned by
+        VectorOnPolicyBuffer.get(); `perms[i]` is the sample order of pass i (DataLoader shuffle)."""
+        t = {k: torch.as_tensor(v) for k, v in data.items()}
+        obs_all = t['obs']
+        with torch.no_grad():
+            old = self.dist(obs_all)
+            old_mean, old_std = old.loc.clone(), old.scale.clone()
+        old = Normal(old_mean, old_std)
+        stats = {'loss_pi': [], 'loss_r': [], 'loss_c': [], 'kl': [], 'iters': 0}
+        for perm in perms:
+            perm = torch.as_tensor(np.asarray(perm, np.int64))
+            for s in range(0, len(perm), batch_size):
+                idx = perm[s:s + batch_size]
+                obs = obs_all[idx]
+                stats['loss_r'].append(self.critic_step('reward_critic', obs, t['target_value_r'][idx], critic_norm_coef, max_grad_norm))
+                if use_cost:
+                    stats['loss_c'].append(self.critic_step('cost_critic', obs, t['target_value_c'][idx], critic_norm_coef, max_grad_norm))
+                adv = (t['adv_r'][idx] - lam * t['adv_c'][idx]) / (1 + lam)
+                if focops is None:
+                    loss, _ = self.loss_pi_ppo(obs, t['act'][idx], t['logp'][idx], adv, clip, entropy_coef)
+                else:
+                    loss, _ = self.loss_pi_focops(obs, t['act'][idx], t['logp'][idx], adv, old_mean[idx],
+                                                  old_std[idx], focops['lam'], focops['eta'], entropy_coef)
+                self._step('actor', loss, max_grad_norm)
+                stats['loss_pi'].append(float(loss.item()))
+            with torch.no_grad():
+                kl = kl_divergence(old, self.dist(obs_all)).sum(-1, keepdim=True).mean().item()
+            stats['kl'].append(kl)
+            stats['iters'] += 1
+            if kl_early_stop and kl > target_kl:
+                break
+        return stats
+
+    # -- natural-gradient machinery ---------------------------------------------------------------
+    def fvp(self, vec, obs, damping):
+        """NaturalPG._fvp: Hessian of mean KL(p || q) at q == p via double backward."""
+        params = list(self.params['actor'].values())
+        q = self.dist(obs)
+        with torch.no_grad():
+            pd = self.dist(obs)
+            pd = Normal(pd.loc.clone(), pd.scale.clone())
+        kl = kl_divergence(pd, q).mean()
+        grads = torch.autograd.grad(kl, params, create_graph=True)
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        kl_p = (flat * torch.as_tensor(vec, dtype=torch.float32)).sum()
+        grads2 = torch.autograd.grad(kl_p, params)
+        out = torch.cat([g.contiguous().reshape(-1) for g in grads2])
+        return out + torch.as_tensor(vec, dtype=torch.float32) * damping
+
+
+def conjugate_gradients(fisher_product, b, num_steps=10, residual_tol=1e-10, eps=1e-6):
+    """utils/math.py:L86-132."""
+    b = torch.as_tensor(b, dtype=torch.float32)
+    x = torch.zeros_like(b)
+    r = b - fisher_product(x)
+    p = r.clone()
+    rdotr = torch.dot(r, r)
+    for _ in range(num_steps):
+        z = fisher_product(p)
+        alpha = rdotr / (torch.dot(p, z) + eps)
+        x = x + alpha * p
+        r = r - alpha * z
+        new_rdotr = torch.dot(r, r)
+        if torch.sqrt(new_rdotr) < residual_tol:
+            break
+        mu = new_rdotr / (rdotr + eps)
+        p = r + mu * p
+        rdotr = new_rdotr
+    return x
+
+
+def cpo_determine_case(b_dot_b, ep_costs, q, r, s, target_kl):
+    """CPO._determine_case (second_order/cpo.py:L215-268) on python floats."""
+    if b_dot_b <= 1e-6 and ep_costs < 0:
+        return 4, 0.0, 0.0
+    A = q - r ** 2 / (s + 1e-8)
+    B = 2 * target_kl - ep_costs ** 2 / (s + 1e-8)
+    if ep_costs < 0 and B < 0:
+        case = 3
+    elif ep_costs < 0 <= B:
+        case = 2
+    elif ep_costs >= 0 and B >= 0:
+        case = 1
+    else:
+        case = 0
+    return case, A, B
+
+
+def cpo_step_direction(case, xHx, x, A, B, q, p, r, s, ep_costs, target_kl):
+    """CPO._step_direction (second_order/cpo.py:L271-337); x, p are torch vectors."""
+    if case in (3, 4):
+        alpha = float(np.sqrt(2 * target_kl / (xHx + 1e-8)))
+        return alpha * x, 1 / (alpha + 1e-8), 0.0
+    if case in (1, 2):
+        lam_a = float(np.sqrt(A / B))
+        lam_b = float(np.sqrt(q / (2 * target_kl)))
+        bound = r / (ep_costs + 1e-8)
+        if ep_costs < 0:
+            lam_a_star = float(np.clip(lam_a, 0.0, bound))
+            lam_b_star = float(np.clip(lam_b, bound, np.inf))
+        else:
+            lam_a_star = float(np.clip(lam_a, bound, np.inf))
+            lam_b_star = float(np.clip(lam_b, 0.0, bound))
+        f_a = lambda lam: -0.5 * (A / (lam + 1e-8) + B * lam) - r * ep_costs / (s + 1e-8)
+        f_b = lambda lam: -0.5 * (q / (lam + 1e-8) + 2 * target_kl * lam)
+        lam_star = lam_a_star if f_a(lam_a_star) >= f_b(lam_b_star) else lam_b_star
+        nu_star = max(lam_star * ep_costs - r, 0.0) / (s + 1e-8)
+        return 1.0 / (lam_star + 1e-8) * (x - nu_star * p), lam_star, nu_star
+    nu_star = float(np.sqrt(2 * target_kl / (s + 1e-8)))
+    return -nu_star * p, 0.0, nu_star

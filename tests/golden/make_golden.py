@@ -161,8 +161,10 @@ def _build_algo(algo, N, T, O, A, seed, extra_algo=None, tmax=8, term_prob=0.05,
                         'window_lens': 10},
         'env_cfgs': {'obs_dim': O, 'act_dim': A, 'max_episode_steps': tmax, 'term_prob': term_prob},
     }
+    env_cfgs = custom.pop('env_cfgs')   # CPO.yaml has no env_cfgs default block: bypass the key check
     recursive_check_config(custom, cfgs)
     cfgs.recurisve_update(custom)
+    cfgs.recurisve_update({'env_cfgs': env_cfgs})
     cfgs.recurisve_update({'exp_name': f'{algo}-golden', 'env_id': 'SyntheticBox-v0', 'algo': algo})
     cfgs.train_cfgs.recurisve_update({'epochs': epochs})
     return registry.get(algo)(env_id='SyntheticBox-v0', cfgs=cfgs)
@@ -220,10 +222,86 @@ def gen_rollout():
     return algo
 
 
+def _record_randperm(fn):
+    perms = []
+    orig = torch.randperm
+
+    def rec(n, *a, **k):
+        out = orig(n, *a, **k)
+        perms.append(out.clone())
+        return out
+
+    torch.randperm = rec
+    try:
+        ret = fn()
+    finally:
+        torch.randperm = orig
+    return ret, perms
+
+
+def _last(logger, key):
+    v = logger._data[key]
+    return np.array(list(v), np.float64)
+
+
+def gen_update_ppolag(algo):
+    """PPOLag._update of the unmodified reference on the rollout above (2 passes x 6 minibatches)."""
+    theta0 = _flat_theta(algo._actor_critic)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    lam0 = float(algo._lagrange.lagrangian_multiplier.item())
+    Jc = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    np.savez(os.path.join(OUT, 'update_ppolag.npz'), theta0=theta0, theta1=_flat_theta(algo._actor_critic),
+             lam0=lam0, lam1=float(algo._lagrange.lagrangian_multiplier.item()), Jc=Jc, perms=perms,
+             batch_size=32, update_iters=2, cost_limit=25.0, lambda_lr=0.035,
+             loss_pi=_last(lg, 'Loss/Loss_pi'), loss_r=_last(lg, 'Loss/Loss_reward_critic'),
+             loss_c=_last(lg, 'Loss/Loss_cost_critic'), kl=_last(lg, 'Train/KL'),
+             stop_iter=_last(lg, 'Train/StopIter'), ratio=_last(lg, 'Train/PolicyRatio'),
+             **{'data_' + k: v for k, v in data.items()})
+
+
+def gen_cpo():
+    """CPO: Fisher-vector product, CG solve and one full actor+critic update of the reference."""
+    from omnisafe.utils.math import conjugate_gradients as ref_cg
+
+    N, T, O, A, seed = 8, 24, 12, 3, 7
+    algo = _build_algo('CPO', N, T, O, A, seed, extra_algo={'cost_limit': 2.0}, tmax=8, term_prob=0.05)
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    obs = torch.as_tensor(data['obs'])
+    algo._fvp_obs = obs[:: algo._cfgs.algo_cfgs.fvp_sample_freq]
+    g = torch.Generator().manual_seed(0)
+    P = sum(p.numel() for p in algo._actor_critic.actor.parameters())
+    vec = torch.randn(P, generator=g) * 0.1
+    fv = algo._fvp(vec).detach().numpy().copy()
+    bvec = torch.randn(P, generator=g) * 0.01
+    xcg = ref_cg(algo._fvp, bvec, algo._cfgs.algo_cfgs.cg_iters).detach().numpy().copy()
+    ep_cost = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    misc = {k.split('/')[1]: _last(lg, k) for k in (
+        'Misc/AcceptanceStep', 'Misc/Alpha', 'Misc/FinalStepNorm', 'Misc/xHx', 'Misc/H_inv_g',
+        'Misc/gradient_norm', 'Misc/cost_gradient_norm', 'Misc/Lambda_star', 'Misc/Nu_star',
+        'Misc/OptimCase', 'Misc/A', 'Misc/B', 'Misc/q', 'Misc/r', 'Misc/s')}
+    np.savez(os.path.join(OUT, 'update_cpo.npz'), N=N, T=T, O=O, A=A, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), vec=vec.numpy(), fvp=fv, bvec=bvec.numpy(), xcg=xcg,
+             ep_cost=ep_cost, cost_limit=2.0, perms=perms, batch_size=32, update_iters=2,
+             cg_damping=0.1, cg_iters=15, target_kl=0.01, kl=_last(lg, 'Train/KL'),
+             **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)
     gen_discount_cumsum()
     gen_buffer_gae()
     gen_normalizer()
-    gen_rollout()
+    algo = gen_rollout()
+    gen_update_ppolag(algo)
+    gen_cpo()
     print('golden fixtures written to', OUT)

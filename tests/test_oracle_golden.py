@@ -84,3 +84,74 @@ def test_rollout_golden(golden_dir):
     np.testing.assert_allclose(w[:, 0], g['win_ret'], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(w[:, 1], g['win_cost'])
     np.testing.assert_allclose(w[:, 2], g['win_len'])
+
+
+def _load_update(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
+    return g, data
+
+
+def test_lagrange_and_ppolag_update_golden(golden_dir):
+    """Oracle PPO-Lag update == unmodified PPOLag._update (same minibatch order)."""
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_ppolag.npz')
+    lag = ol.Lagrange(float(g['cost_limit']), float(g['lam0']), float(g['lambda_lr']))
+    lam1 = lag.update(float(g['Jc']))
+    assert abs(lam1 - float(g['lam1'])) < 1e-7
+    L = ol.Learner(g['theta0'], 12, 3)
+    perms = g['perms'][::2]   # RandomSampler draws a second, unused randperm per pass
+    st = L.update_ppo(data, perms, lam1, batch_size=int(g['batch_size']))
+    np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
+    assert st['iters'] == int(g['stop_iter'][-1])
+    np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(st['loss_pi'], g['loss_pi'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(st['loss_r'], g['loss_r'], rtol=1e-4, atol=1e-6)
+
+
+def test_fvp_and_cg_golden(golden_dir):
+    import torch
+
+    from oracle import actor_critic as oac
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_cpo.npz')
+    O, A = int(g['O']), int(g['A'])
+    L = ol.Learner(g['theta0'], O, A, lr_actor=None, lr_critic=1e-3)
+    obs = torch.as_tensor(data['obs'])
+    fv = L.fvp(g['vec'], obs, float(g['cg_damping'])).numpy()
+    np.testing.assert_allclose(fv, g['fvp'], rtol=1e-4, atol=1e-6)
+    x = ol.conjugate_gradients(lambda v: L.fvp(v, obs, float(g['cg_damping'])), g['bvec'], int(g['cg_iters'])).numpy()
+    np.testing.assert_allclose(x, g['xcg'], rtol=2e-3, atol=1e-5)
+    # analytic Gauss-Newton form used by the CUDA kernel (SURVEY §8a row 13)
+    nets = oac.unflatten(torch.as_tensor(g['theta0']), O, A)
+    pa = {k: v.clone().requires_grad_(True) for k, v in nets['actor'].items()}
+    params = [pa[k] for k in ('log_std', 'w1', 'b1', 'w2', 'b2', 'w3', 'b3')]
+    mu = oac.mlp(pa, obs)
+    vec = torch.as_tensor(g['vec'])
+    vs, i = [], 0
+    for p_ in params:
+        vs.append(vec[i:i + p_.numel()].view_as(p_)); i += p_.numel()
+    # J v via double-backward trick on a dummy cotangent
+    u = torch.zeros_like(mu, requires_grad=True)
+    gr = torch.autograd.grad(mu, params[1:], u, create_graph=True)
+    jv = torch.autograd.grad(gr, u, vs[1:])[0]
+    sig2 = torch.exp(pa['log_std']) ** 2
+    cot = jv / sig2 / (obs.shape[0] * A)
+    gn = torch.autograd.grad(mu, params[1:], cot)
+    flat = torch.cat([(2.0 / A) * vs[0]] + [t.reshape(-1) for t in gn]) + float(g['cg_damping']) * vec
+    np.testing.assert_allclose(flat.detach().numpy(), g['fvp'], rtol=1e-4, atol=1e-6)
+
+
+def test_cpo_case_known_answers():
+    """reference tests/test_policy.py:L57-74: b_grads=[1], q=r=0 and (ep_costs, s) =
+    (-1, 1), (-1, -1), (1, -1), (1, 1) give optim_case 3, 2, 1, 0 (CPO.yaml target_kl = 0.01)."""
+    from oracle.learner import cpo_determine_case
+
+    b_dot_b, q, r, kl = 1.0, 0.0, 0.0, 0.01
+    assert cpo_determine_case(b_dot_b, -1.0, q, r, 1.0, kl)[0] == 3
+    assert cpo_determine_case(b_dot_b, -1.0, q, r, -1.0, kl)[0] == 2
+    assert cpo_determine_case(b_dot_b, 1.0, q, r, -1.0, kl)[0] == 1
+    assert cpo_determine_case(b_dot_b, 1.0, q, r, 1.0, kl)[0] == 0
+    assert cpo_determine_case(1e-8, -1.0, q, r, 1.0, kl)[0] == 4
