@@ -146,7 +146,7 @@ int osb_fvp_partials(const float* theta_actor, const float* vec, int O, int A, c
 /* ---- optimiser side --------------------------------------------------------------------------
  * osb_grad_reduce: grad <- sum of CTA partials (+ 2*critic_norm_coef*theta for critics,
  * policy_gradient.py:L431-433); advances adam_step[net]; accumulates train_stats[3][8]
- * ({sum of minibatch mean loss, mean ratio, mean kl, #minibatches}).  sumsq_part: 3*osb_optim_blocks.
+ * ({sum of minibatch mean loss, mean ratio, mean kl, #minibatches}).  sumsq_part: 6*osb_optim_blocks.
  * osb_clip_adam: clip_grad_norm_ per network (do_clip) and torch.optim.Adam step (do_adam);
  * multi-rank order = clip -> all-reduce SUM -> grad_scale = 1/world -> Adam (policy_gradient.py:L437-443). */
 int osb_optim_blocks(int O, int A);
@@ -156,8 +156,9 @@ int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, in
                     void* stream);
 int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const int* adam_step,
                   const float* sumsq_part, int O, int A, float max_grad_norm, float lr_actor,
-                  float lr_critic_r, float lr_critic_c, float grad_scale, int do_clip, int do_adam,
-                  int net_mask, const int* stop_flag, void* stream);
+                  float lr_critic_r, float lr_critic_c, float grad_scale, float critic_norm_coef,
+                  float* train_stats, int do_clip, int do_adam, int net_mask, const int* stop_flag,
+                  void* stream);
 /* Lagrange.update_lagrange_multiplier (common/lagrange.py:L114-136) on the device: Adam step on
  * lambda with grad -(Jc - cost_limit), Jc = window_sums[1]/window_sums[3], clamp to
  * [0, upper_bound] (upper_bound < 0 = none).  state[4] = {lambda, m, v, t}.  nan_flag <- 1 when no
@@ -167,9 +168,9 @@ int osb_lagrange_update(const double* window_sums, float cost_limit, float lambd
 /* kl = eval_out[0]/eval_out[4]; kl_state[4] = {last kl, passes done, stopped, 0}. */
 int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
                  float* kl_state, void* stream);
-/* out[q] = scale * sum_b gpart[b][q] + add_scale * add[q]  (add may be NULL). */
-int osb_reduce_partials(const float* gpart, int nblocks, int n, float scale, const float* add,
-                        float add_scale, float* out, void* stream);
+/* out[q] = scale * sum_b gpart[b*stride + q] + add_scale * add[q], q < n  (add may be NULL). */
+int osb_reduce_partials(const float* gpart, int nblocks, int stride, int n, float scale,
+                        const float* add, float add_scale, float* out, void* stream);
 /* conjugate_gradients (utils/math.py:L86-132) as device-resident state: x, r, p [n],
  * cg_scalars[4] = {rdotr, converged, iterations, 0}; the caller computes z = F p between steps. */
 int osb_cg_init(const float* b, int n, float* x, float* r, float* p, float* cg_scalars, void* stream);

@@ -71,7 +71,8 @@ class _Lib:
 
     def __getattr__(self, name: str):
         fn = getattr(self._dll, name)
-        if name in ('osb_abi_version', 'osb_gae_workspace_doubles') or name not in self._checked:
+        # size / version queries return their value; everything else returns an error code
+        if name.endswith(('_blocks', '_doubles', '_version')) or name not in self._checked:
             return fn
 
         def checked(*args):

@@ -19,7 +19,8 @@ class OnPolicyAdapter:
                  env_id_offset: int = 0) -> None:
         self._cfgs = cfgs
         self._device = torch.device(device)
-        env_cfgs = dict(getattr(cfgs, 'env_cfgs', {}) or {})
+        env_cfgs = getattr(cfgs, 'env_cfgs', None) or {}
+        env_cfgs = dict(env_cfgs.todict() if hasattr(env_cfgs, 'todict') else env_cfgs)
         env_cfgs.pop('env_id_offset', None)
         self._env = SyntheticBoxEnv(env_id, num_envs=num_envs, device=self._device,
                                     env_id_offset=env_id_offset, **env_cfgs)

@@ -1,0 +1,409 @@
+"""On-policy algorithms on the fused sm_100a path: PolicyGradient / PPO / PPOLag /
+NaturalPG / TRPO / TRPOLag / CPO / FOCOPS.
+
+Each class mirrors the override structure of the reference
+(omnisafe/algorithms/on_policy/base/{policy_gradient,ppo,natural_pg,trpo}.py,
+naive_lagrange/{ppo_lag,trpo_lag}.py, second_order/cpo.py, first_order/focops.py): the same
+`_init_env/_init_model/_init/_init_log/learn/_update/_update_actor` hooks and logger keys, with the
+method bodies handing the work to the C-ABI kernels (rollout, dual GAE, fused update, CG/FVP).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+
+from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
+from omnisafe_b200.algorithms import registry
+from omnisafe_b200.algorithms.base_algo import BaseAlgo
+from omnisafe_b200.algorithms.engine import (LOSS_COST, LOSS_FOCOPS, LOSS_PPO_CLIP, LOSS_RATIO,
+                                             NET_ACTOR, UpdateEngine)
+from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
+from omnisafe_b200.common.lagrange import Lagrange
+from omnisafe_b200.common.logger import Logger
+from omnisafe_b200.models.actor_critic import ConstraintActorCritic
+from omnisafe_b200.utils import distributed
+
+
+@registry.register
+class PolicyGradient(BaseAlgo):
+    """base/policy_gradient.py:L39-588."""
+
+    _loss_kind = LOSS_RATIO
+
+    # ---- construction ------------------------------------------------------------------------
+    def _init_env(self) -> None:
+        t, a = self._cfgs.train_cfgs, self._cfgs.algo_cfgs
+        rank = distributed.get_rank()
+        self._env = OnPolicyAdapter(self._env_id, t.vector_env_nums, self._seed, self._cfgs,
+                                    device=self._device, env_id_offset=rank * t.vector_env_nums)
+        self._steps_per_epoch = distributed.local_steps(a.steps_per_epoch, t.vector_env_nums)
+
+    def _init_model(self) -> None:
+        gen = torch.Generator().manual_seed(int(self._cfgs.seed))   # identical on every rank == sync_params
+        self._actor_critic = ConstraintActorCritic(self._env.obs_dim, self._env.act_dim, self._cfgs.model_cfgs,
+                                                   epochs=self._cfgs.train_cfgs.epochs, device=self._device,
+                                                   generator=gen)
+
+    def _init(self) -> None:
+        a = self._cfgs.algo_cfgs
+        self._buf = VectorOnPolicyBuffer(
+            self._env.obs_dim, self._env.act_dim, self._steps_per_epoch, a.gamma, a.lam, a.lam_c,
+            a.adv_estimation_method, a.penalty_coef, a.standardized_rew_adv, a.standardized_cost_adv,
+            num_envs=self._cfgs.train_cfgs.vector_env_nums, device=self._device, keep_discounted_ret=False)
+        self._engine = UpdateEngine(self._actor_critic, self._buf)
+        self._stats8 = torch.zeros(8, dtype=torch.float64, device=self._device)
+
+    def _init_log(self) -> None:
+        lc = self._cfgs.logger_cfgs
+        self._logger = Logger(lc.log_dir, self._cfgs.exp_name, seed=self._cfgs.seed, config=self._cfgs,
+                              verbose=bool(getattr(lc, 'verbose', False)))
+        what = {'pi': self._actor_critic.actor_state_dict}
+        what.update(self._env.save())
+        self._logger.setup_torch_saver(what)
+        for key in ('Metrics/EpRet', 'Metrics/EpCost', 'Metrics/EpLen', 'Train/Epoch', 'Train/Entropy',
+                    'Train/KL', 'Train/StopIter', 'Train/PolicyRatio', 'Train/LR', 'Train/PolicyStd',
+                    'TotalEnvSteps', 'Loss/Loss_pi', 'Loss/Loss_reward_critic', 'Loss/Loss_cost_critic',
+                    'Time/Total', 'Time/Rollout', 'Time/Update', 'Time/Epoch', 'Time/FPS'):
+            self._logger.register_key(key)
+
+    # ---- training loop (policy_gradient.py:L238-306) -------------------------------------------
+    def learn(self) -> tuple[float, float, float]:
+        self._start_time = time.time()
+        t = self._cfgs.train_cfgs
+        for epoch in range(t.epochs):
+            self.train_epoch(log=True, epoch=epoch)
+            if (epoch + 1) % self._cfgs.logger_cfgs.save_model_freq == 0 or (epoch + 1) == t.epochs:
+                self._logger.torch_save()
+        ep = self._window_means()
+        self._logger.close()
+        self._env.close()
+        return ep
+
+    def train_epoch(self, eps=None, log: bool = False, epoch: int | None = None):
+        """One epoch: rollout -> dual GAE -> statistics exchange -> update.  Asynchronous unless
+        `log` (the logger reads the epoch's metrics back, one synchronisation per epoch).  `eps`
+        optionally supplies the [T, N, A] standard-normal stream (parity mode)."""
+        epoch_time = time.time()
+        self._env.rollout(self._steps_per_epoch, self._actor_critic, self._buf, self._logger, eps=eps)
+        self._buf.finish_paths()
+        self._reduce_epoch_statistics()
+        roll = time.time()
+        self._update()
+        self._actor_critic.actor_scheduler_step()
+        if not log:
+            return None
+        if epoch is None:
+            epoch = self._logger.current_epoch
+        return self._log_epoch(epoch, getattr(self, '_start_time', epoch_time), epoch_time, roll)
+
+    def _reduce_epoch_statistics(self) -> None:
+        """The once-per-epoch exchange: {adv sums, episode-window sums} in one fp64 all-reduce
+        (vector_onpolicy_buffer.py:L131-132 + logger.py:L365-373), then the advantage moments."""
+        if distributed.world_size() > 1:
+            self._stats8[:4] = self._buf.adv_sums
+            self._stats8[4:] = self._env.window_sums
+            distributed.all_reduce_(self._stats8)
+            self._buf.adv_sums.copy_(self._stats8[:4])
+            self._env.window_sums.copy_(self._stats8[4:])
+        self._buf.finalize_statistics()
+
+    def _window_means(self) -> tuple[float, float, float]:
+        ws = self._env.window_sums.tolist()
+        n = ws[3] if ws[3] > 0 else float('nan')
+        return ws[0] / n, ws[1] / n, ws[2] / n
+
+    def _log_epoch(self, epoch, start, epoch_time, roll) -> None:
+        torch.cuda.synchronize()
+        now = time.time()
+        ep_ret, ep_cost, ep_len = self._window_means()
+        ts = self._engine.train_stats.view(3, 8).tolist()
+        kl = self._engine.kl_state.tolist()
+        n_mb = [max(r[3], 1.0) for r in ts]
+        std = float(torch.exp(self._actor_critic.theta[: self._env.act_dim]).mean())
+        logstd = float(self._actor_critic.theta[: self._env.act_dim].mean())
+        gsteps = self._cfgs.algo_cfgs.steps_per_epoch
+        self._logger.store({
+            'Metrics/EpRet': ep_ret, 'Metrics/EpCost': ep_cost, 'Metrics/EpLen': ep_len,
+            'Train/Epoch': epoch, 'Train/Entropy': 0.5 + 0.5 * math.log(2 * math.pi) + logstd,
+            'Train/KL': kl[0], 'Train/StopIter': kl[1], 'Train/PolicyRatio': ts[0][1] / n_mb[0],
+            'Train/LR': self._actor_critic.actor_lr, 'Train/PolicyStd': std,
+            'TotalEnvSteps': (epoch + 1) * gsteps, 'Loss/Loss_pi': ts[0][0] / n_mb[0],
+            'Loss/Loss_reward_critic': ts[1][0] / n_mb[1], 'Loss/Loss_cost_critic': ts[2][0] / n_mb[2],
+            'Time/Total': now - start, 'Time/Rollout': roll - epoch_time, 'Time/Update': now - roll,
+            'Time/Epoch': now - epoch_time, 'Time/FPS': gsteps / (now - epoch_time),
+        })
+        self._log_extra()
+        self._logger.dump_tabular()
+        A = self._env.act_dim
+        return {'d2h_bytes': 4 * 8 + 24 * 4 + 4 * 4 + 2 * A * 4 + 8, 'fps': gsteps / (now - epoch_time)}
+
+    def _log_extra(self) -> None:
+        pass
+
+    # ---- update (policy_gradient.py:L308-405) -----------------------------------------------------
+    def _lagrange_ptr(self):
+        return None
+
+    def _update(self, net_mask: int = 7, perm=None) -> None:
+        a = self._cfgs.algo_cfgs
+        if not a.use_cost:
+            net_mask &= ~4
+        self._engine.ppo_epoch(
+            loss_kind=self._loss_kind, lagrange=self._lagrange_ptr(), net_mask=net_mask,
+            batch_size=a.batch_size, update_iters=a.update_iters, clip=getattr(a, 'clip', 0.2),
+            entropy_coef=a.entropy_coef, focops_lam=getattr(a, 'focops_lam', 1.0),
+            focops_eta=getattr(a, 'focops_eta', 0.0),
+            critic_norm_coef=a.critic_norm_coef if a.use_critic_norm else 0.0,
+            max_grad_norm=a.max_grad_norm if a.use_max_grad_norm else 0.0,
+            lr_actor=self._actor_critic.actor_lr, lr_critic=self._actor_critic.critic_lr,
+            target_kl=a.target_kl, kl_early_stop=a.kl_early_stop, perm=perm)
+
+
+@registry.register
+class PPO(PolicyGradient):
+    """base/ppo.py:L28-87 (clipped surrogate)."""
+
+    _loss_kind = LOSS_PPO_CLIP
+
+
+class _LagrangeMixin:
+    """The `_init / _init_log / _update` additions shared by PPOLag / TRPOLag / FOCOPS
+    (naive_lagrange/ppo_lag.py:L31-80)."""
+
+    def _init(self) -> None:
+        super()._init()
+        self._lagrange = Lagrange(**self._cfgs.lagrange_cfgs.todict(), device=self._device)
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Metrics/LagrangeMultiplier')
+
+    def _lagrange_ptr(self):
+        return self._lagrange.state
+
+    def _update(self, *args, **kwargs) -> None:
+        # Jc = windowed mean EpCost (already all-reduced); first update lambda, then the networks
+        self._lagrange.update_lagrange_multiplier(self._env.window_sums)
+        super()._update(*args, **kwargs)
+
+    def _log_extra(self) -> None:
+        super()._log_extra()
+        assert int(self._lagrange.nan_flag) == 0, 'cost for updating lagrange multiplier is nan'
+        self._logger.store({'Metrics/LagrangeMultiplier': float(self._lagrange.lagrangian_multiplier)})
+
+
+@registry.register
+class PPOLag(_LagrangeMixin, PPO):
+    """naive_lagrange/ppo_lag.py:L26-102."""
+
+
+@registry.register
+class FOCOPS(_LagrangeMixin, PolicyGradient):
+    """first_order/focops.py:L31-230."""
+
+    _loss_kind = LOSS_FOCOPS
+
+
+@registry.register
+class NaturalPG(PolicyGradient):
+    """base/natural_pg.py:L30-230: one full-batch natural-gradient actor step, then critic passes."""
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        for key in ('Misc/Alpha', 'Misc/FinalStepNorm', 'Misc/gradient_norm', 'Misc/xHx', 'Misc/H_inv_g'):
+            self._logger.register_key(key)
+        self._misc: dict[str, float] = {}
+
+    def _log_extra(self) -> None:
+        super()._log_extra()
+        self._logger.store(self._misc)
+
+    def _adv_lagrange(self):
+        return self._lagrange_ptr()
+
+    def _natural_direction(self):
+        """theta_old, g = -grad(loss), x = H^-1 g, xHx, alpha (natural_pg.py:L146-166)."""
+        a, e, ac = self._cfgs.algo_cfgs, self._engine, self._actor_critic
+        Pa = e.Pa
+        e.snapshot_old_policy()
+        theta_old = ac.theta[:Pa].clone()
+        grads = torch.empty(Pa, dtype=torch.float32, device=self._device)
+        loss_before = e.actor_loss_grad(LOSS_RATIO, self._adv_lagrange(), grads, sign=-1.0)
+        x = e.conjugate_gradients(grads, a.cg_iters, a.cg_damping, a.fvp_sample_freq)
+        assert torch.isfinite(x).all(), 'x is not finite'
+        e.fvp(x, e.cg_z, a.cg_damping, a.fvp_sample_freq)
+        xHx = e.dot(x, e.cg_z)
+        assert xHx >= 0, 'xHx is negative'
+        alpha = math.sqrt(2 * a.target_kl / (xHx + 1e-8))
+        return theta_old, grads, x, xHx, alpha, float(loss_before)
+
+    def _update_actor(self) -> None:
+        theta_old, grads, x, xHx, alpha, _ = self._natural_direction()
+        step = alpha * x
+        self._actor_critic.theta[: self._engine.Pa] = theta_old + step
+        self._misc = {'Misc/Alpha': alpha, 'Misc/FinalStepNorm': float(step.norm()), 'Misc/xHx': xHx,
+                      'Misc/gradient_norm': float(grads.norm()), 'Misc/H_inv_g': float(x.norm())}
+
+    def _update(self, perm=None) -> None:
+        self._update_actor()
+        final_kl = self._engine.kl_state[0].clone()
+        super()._update(net_mask=6, perm=perm)   # critics only, update_iters passes (natural_pg.py:L209-223)
+        self._engine.kl_state[0] = final_kl      # Train/KL = KL of the accepted actor step
+
+
+@registry.register
+class TRPO(NaturalPG):
+    """base/trpo.py:L32-222: natural direction + backtracking line search."""
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Misc/AcceptanceStep')
+
+    def _search_step_size(self, step_direction, grads, theta_old, loss_before, total_steps=15, decay=0.8):
+        a, e = self._cfgs.algo_cfgs, self._engine
+        step_frac, final_kl = 1.0, 0.0
+        trial = self._actor_critic.theta.clone()
+        acceptance_step = 0
+        for step in range(total_steps):
+            trial[: e.Pa] = theta_old + step_frac * step_direction
+            ev = e.evaluate(trial, self._adv_lagrange())
+            loss_improve = loss_before - ev['loss']
+            if not math.isfinite(ev['loss']):
+                self._logger.log('WARNING: loss_pi not finite')
+            elif loss_improve < 0:
+                self._logger.log('INFO: did not improve improve <0')
+            elif ev['kl'] > a.target_kl:
+                self._logger.log('INFO: violated KL constraint.')
+            else:
+                acceptance_step, final_kl = step + 1, ev['kl']
+                break
+            step_frac *= decay
+        else:
+            self._logger.log('INFO: no suitable step found...')
+            step_direction = torch.zeros_like(step_direction)
+        self._engine.kl_state[0] = final_kl
+        return step_frac * step_direction, acceptance_step
+
+    def _update_actor(self) -> None:
+        theta_old, grads, x, xHx, alpha, loss_before = self._natural_direction()
+        step, accept = self._search_step_size(alpha * x, grads, theta_old, loss_before)
+        self._actor_critic.theta[: self._engine.Pa] = theta_old + step
+        self._misc = {'Misc/Alpha': alpha, 'Misc/FinalStepNorm': float(step.norm()), 'Misc/xHx': xHx,
+                      'Misc/gradient_norm': float(grads.norm()), 'Misc/H_inv_g': float(x.norm()),
+                      'Misc/AcceptanceStep': accept}
+
+
+@registry.register
+class TRPOLag(_LagrangeMixin, TRPO):
+    """naive_lagrange/trpo_lag.py:L25-103."""
+
+
+@registry.register
+class CPO(TRPO):
+    """second_order/cpo.py:L33-462."""
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        for key in ('Misc/cost_gradient_norm', 'Misc/Lambda_star', 'Misc/Nu_star', 'Misc/OptimCase',
+                    'Misc/A', 'Misc/B', 'Misc/q', 'Misc/r', 'Misc/s'):
+            self._logger.register_key(key)
+
+    def _adv_lagrange(self):
+        return None   # CPO's reward surrogate uses adv_r alone
+
+    def _determine_case(self, b_dot_b, ep_costs, q, r, s):
+        kl = self._cfgs.algo_cfgs.target_kl
+        if b_dot_b <= 1e-6 and ep_costs < 0:
+            return 4, 0.0, 0.0
+        assert math.isfinite(r), 'r is not finite'
+        assert math.isfinite(s), 's is not finite'
+        A = q - r ** 2 / (s + 1e-8)
+        B = 2 * kl - ep_costs ** 2 / (s + 1e-8)
+        if ep_costs < 0 and B < 0:
+            return 3, A, B
+        if ep_costs < 0 <= B:
+            return 2, A, B
+        if ep_costs >= 0 and B >= 0:
+            self._logger.log('Alert! Attempting feasible recovery!')
+            return 1, A, B
+        self._logger.log('Alert! Attempting infeasible recovery!')
+        return 0, A, B
+
+    def _step_direction(self, optim_case, xHx, x, A, B, q, p, r, s, ep_costs):
+        kl = self._cfgs.algo_cfgs.target_kl
+        if optim_case in (3, 4):
+            alpha = math.sqrt(2 * kl / (xHx + 1e-8))
+            return alpha * x, 1 / (alpha + 1e-8), 0.0
+        if optim_case in (1, 2):
+            lambda_a = math.sqrt(A / B)
+            lambda_b = math.sqrt(q / (2 * kl))
+            bound = r / (ep_costs + 1e-8)
+            clampf = lambda v, lo, hi: min(max(v, lo), hi)   # noqa: E731
+            if ep_costs < 0:
+                lambda_a_star, lambda_b_star = clampf(lambda_a, 0.0, bound), clampf(lambda_b, bound, math.inf)
+            else:
+                lambda_a_star, lambda_b_star = clampf(lambda_a, bound, math.inf), clampf(lambda_b, 0.0, bound)
+            f_a = lambda lam: -0.5 * (A / (lam + 1e-8) + B * lam) - r * ep_costs / (s + 1e-8)   # noqa: E731
+            f_b = lambda lam: -0.5 * (q / (lam + 1e-8) + 2 * kl * lam)   # noqa: E731
+            lambda_star = lambda_a_star if f_a(lambda_a_star) >= f_b(lambda_b_star) else lambda_b_star
+            nu_star = max(lambda_star * ep_costs - r, 0.0) / (s + 1e-8)
+            return 1.0 / (lambda_star + 1e-8) * (x - nu_star * p), lambda_star, nu_star
+        nu_star = math.sqrt(2 * kl / (s + 1e-8))
+        return -nu_star * p, 0.0, nu_star
+
+    def _cpo_search_step(self, step_direction, theta_old, loss_reward_before, loss_cost_before,
+                         total_steps=15, decay=0.8, violation_c=0.0, optim_case=0):
+        a, e = self._cfgs.algo_cfgs, self._engine
+        step_frac, kl = 1.0, 0.0
+        trial = self._actor_critic.theta.clone()
+        acceptance_step = 0
+        for step in range(total_steps):
+            trial[: e.Pa] = theta_old + step_frac * step_direction
+            acceptance_step = step + 1
+            ev = e.evaluate(trial, None)
+            kl = ev['kl']
+            loss_reward_improve = loss_reward_before - ev['loss_r']
+            loss_cost_diff = ev['loss_c'] - loss_cost_before
+            if not math.isfinite(kl):
+                self._logger.log('WARNING: KL not finite')
+                continue
+            if optim_case > 1 and loss_reward_improve < 0:
+                self._logger.log('INFO: did not improve improve <0')
+            elif loss_cost_diff > max(-violation_c, 0):
+                self._logger.log(f'INFO: no improve {loss_cost_diff} > {max(-violation_c, 0)}')
+            elif kl > a.target_kl:
+                self._logger.log(f'INFO: violated KL constraint {kl} at step {step + 1}.')
+            else:
+                break
+            step_frac *= decay
+        else:
+            self._logger.log('INFO: no suitable step found...')
+            step_direction = torch.zeros_like(step_direction)
+            acceptance_step = 0
+        self._engine.kl_state[0] = kl
+        return step_frac * step_direction, acceptance_step
+
+    def _update_actor(self) -> None:
+        a, e = self._cfgs.algo_cfgs, self._engine
+        theta_old, grads, x, xHx, alpha, loss_reward_before = self._natural_direction()
+        b_grads = torch.empty(e.Pa, dtype=torch.float32, device=self._device)
+        loss_cost_before = float(e.actor_loss_grad(LOSS_COST, None, b_grads, sign=1.0))
+        ep_costs = self._window_means()[1] - a.cost_limit
+        p = e.conjugate_gradients(b_grads, a.cg_iters, a.cg_damping, a.fvp_sample_freq)
+        q, r, s = xHx, e.dot(grads, p), e.dot(b_grads, p)
+        optim_case, A, B = self._determine_case(e.dot(b_grads, b_grads), ep_costs, q, r, s)
+        step_direction, lambda_star, nu_star = self._step_direction(optim_case, xHx, x, A, B, q, p, r, s, ep_costs)
+        step, accept = self._cpo_search_step(step_direction, theta_old, loss_reward_before, loss_cost_before,
+                                             total_steps=20, violation_c=ep_costs, optim_case=optim_case)
+        self._actor_critic.theta[: e.Pa] = theta_old + step
+        self._misc = {
+            'Misc/AcceptanceStep': accept, 'Misc/Alpha': alpha, 'Misc/FinalStepNorm': float(step.norm()),
+            'Misc/xHx': xHx, 'Misc/H_inv_g': float(x.norm()), 'Misc/gradient_norm': float(grads.norm()),
+            'Misc/cost_gradient_norm': float(b_grads.norm()), 'Misc/Lambda_star': lambda_star,
+            'Misc/Nu_star': nu_star, 'Misc/OptimCase': int(optim_case), 'Misc/A': A, 'Misc/B': B,
+            'Misc/q': q, 'Misc/r': r, 'Misc/s': s}
+
+
+ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'TRPO', 'TRPOLag', 'CPO', 'FOCOPS']

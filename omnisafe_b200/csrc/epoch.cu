@@ -27,8 +27,9 @@ int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, in
                     void* stream);
 int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const int* adam_step,
                   const float* sumsq_part, int O, int A, float max_grad_norm, float lr_actor,
-                  float lr_critic_r, float lr_critic_c, float grad_scale, int do_clip, int do_adam,
-                  int net_mask, const int* stop_flag, void* stream);
+                  float lr_critic_r, float lr_critic_c, float grad_scale, float critic_norm_coef,
+                  float* train_stats, int do_clip, int do_adam, int net_mask, const int* stop_flag,
+                  void* stream);
 int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
                  float* kl_state, void* stream);
 }
@@ -166,17 +167,17 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
             if (rc) return rc;
             if (comm && world_size > 1) {
                 rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
-                                   max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, 1, 0, net_mask,
+                                   max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, critic_norm_coef, train_stats, 1, 0, net_mask,
                                    stop_flag, stream);
                 if (rc) return rc;
                 rc = osb_nccl_allreduce(comm, grad, P, 0, stream);
                 if (rc) return rc;
                 rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
-                                   max_grad_norm, lr_actor, lr_critic, lr_critic, gscale, 0, 1, net_mask,
+                                   max_grad_norm, lr_actor, lr_critic, lr_critic, gscale, critic_norm_coef, train_stats, 0, 1, net_mask,
                                    stop_flag, stream);
             } else {
                 rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
-                                   max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, 1, 1, net_mask,
+                                   max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, critic_norm_coef, train_stats, 1, 1, net_mask,
                                    stop_flag, stream);
             }
             if (rc) return rc;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(OT) grad_reduce_kernel(ReduceArgs p) {
     if (p.stop_flag && *p.stop_flag) return;
     const int net = blockIdx.y;
     if (!((p.net_mask >> net) & 1)) return;
-    __shared__ float red[OT / 32];
+    __shared__ float red[OT / 32], red2[OT / 32];
     const NetLayout L = net_layout(net, p.O, p.A);
     const int noff = net_offset(net, p.O, p.A);
     const int pl = blockIdx.x * OT + threadIdx.x;
@@ -45,15 +45,19 @@ __global__ void __launch_bounds__(OT) grad_reduce_kernel(ReduceArgs p) {
         if (net != 0 && p.critic_norm_coef > 0.f) g += 2.f * p.critic_norm_coef * p.theta[q];
         p.grad[q] = g;
     }
-    float s = warp_sum(g * g);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    float th = 0.f;
+    if (pl < L.size && net != 0) th = p.theta[noff + pl];
+    float s = warp_sum(g * g), s2 = warp_sum(th * th);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red2[threadIdx.x >> 5] = s2; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < OT / 32; ++w) t += red[w];
+        float t = 0.f, t2 = 0.f;
+        for (int w = 0; w < OT / 32; ++w) { t += red[w]; t2 += red2[w]; }
         p.sumsq_part[net * gridDim.x + blockIdx.x] = t;
+        p.sumsq_part[(3 + net) * gridDim.x + blockIdx.x] = t2;   // sum theta^2 (critic regulariser)
         if (blockIdx.x == 0) {
             p.adam_step[net] += 1;
+            // per-minibatch means of the loss statistics; the regulariser is added in clip_adam
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int b = 0; b < p.nblocks; ++b)
                 for (int i = 0; i < 4; ++i) acc[i] += p.stats_part[((size_t)b * 3 + net) * 8 + i];
@@ -78,6 +82,8 @@ struct AdamArgs {
     float max_grad_norm;       // <= 0 -> no clipping
     float lr[3];
     float grad_scale;          // 1 / world_size applied before Adam (avg_grads)
+    float critic_norm_coef;
+    float* train_stats;
     int do_clip, do_adam, net_mask;
     const int* stop_flag;
 };
@@ -88,6 +94,12 @@ __global__ void __launch_bounds__(OT) clip_adam_kernel(AdamArgs p) {
     if (!((p.net_mask >> net) & 1)) return;
     const NetLayout L = net_layout(net, p.O, p.A);
     const int pl = blockIdx.x * OT + threadIdx.x;
+    if (p.do_clip && net != 0 && p.critic_norm_coef > 0.f && blockIdx.x == 0 && threadIdx.x == 0) {
+        // logged critic loss = mse + coef * sum(theta^2) (policy_gradient.py:L429-433)
+        float t2 = 0.f;
+        for (int b = 0; b < p.NB; ++b) t2 += p.sumsq_part[(3 + net) * p.NB + b];
+        p.train_stats[net * 8] += p.critic_norm_coef * t2;
+    }
     if (pl >= L.size) return;
     const int q = net_offset(net, p.O, p.A) + pl;
     float g = p.grad[q];
@@ -150,12 +162,13 @@ __global__ void kl_check_kernel(const double* __restrict__ eval_out, float targe
 
 // out[q] = scale * sum_b gpart[b][q] + add_scale * add[q]
 __global__ void __launch_bounds__(OT) reduce_partials_kernel(const float* __restrict__ gpart, int nblocks,
-                                                             int n, float scale, const float* __restrict__ add,
+                                                             int stride, int n, float scale,
+                                                             const float* __restrict__ add,
                                                              float add_scale, float* __restrict__ out) {
     const int q = blockIdx.x * OT + threadIdx.x;
     if (q >= n) return;
     float g = 0.f;
-    for (int b = 0; b < nblocks; ++b) g += gpart[(size_t)b * n + q];
+    for (int b = 0; b < nblocks; ++b) g += gpart[(size_t)b * stride + q];
     g *= scale;
     if (add) g += add_scale * add[q];
     out[q] = g;
@@ -237,7 +250,7 @@ int osb_optim_blocks(int O, int A) {
 }
 
 // grad <- sum of the CTA partials (+ 2*coef*theta for the critics); advances adam_step[net] and the
-// running training statistics.  sumsq_part: 3 * osb_optim_blocks floats.
+// running training statistics.  sumsq_part: 6 * osb_optim_blocks floats.
 int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, int O, int A,
                     const float* theta, float* grad, float critic_norm_coef, int net_mask,
                     float* sumsq_part, int* adam_step, float* train_stats, const int* stop_flag,
@@ -258,10 +271,12 @@ int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, in
 // optimizer step (policy_gradient.py:L437-443).
 int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const int* adam_step,
                   const float* sumsq_part, int O, int A, float max_grad_norm, float lr_actor,
-                  float lr_critic_r, float lr_critic_c, float grad_scale, int do_clip, int do_adam,
-                  int net_mask, const int* stop_flag, void* stream) {
-    OSB_CHECK_ARG(grad && theta && adam_m && adam_v && adam_step && sumsq_part, "null pointer");
+                  float lr_critic_r, float lr_critic_c, float grad_scale, float critic_norm_coef,
+                  float* train_stats, int do_clip, int do_adam, int net_mask, const int* stop_flag,
+                  void* stream) {
+    OSB_CHECK_ARG(grad && theta && adam_m && adam_v && adam_step && sumsq_part && train_stats, "null pointer");
     AdamArgs p;
+    p.critic_norm_coef = critic_norm_coef; p.train_stats = train_stats;
     p.grad = grad; p.theta = theta; p.m = adam_m; p.v = adam_v; p.adam_step = adam_step;
     p.sumsq_part = sumsq_part; p.NB = osb_optim_blocks(O, A); p.O = O; p.A = A;
     p.max_grad_norm = max_grad_norm; p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
@@ -288,10 +303,10 @@ int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* s
     return OSB_OK;
 }
 
-int osb_reduce_partials(const float* gpart, int nblocks, int n, float scale, const float* add,
-                        float add_scale, float* out, void* stream) {
-    OSB_CHECK_ARG(gpart && out && n > 0 && nblocks > 0, "bad argument");
-    reduce_partials_kernel<<<(n + OT - 1) / OT, OT, 0, (cudaStream_t)stream>>>(gpart, nblocks, n, scale, add, add_scale, out);
+int osb_reduce_partials(const float* gpart, int nblocks, int stride, int n, float scale,
+                        const float* add, float add_scale, float* out, void* stream) {
+    OSB_CHECK_ARG(gpart && out && n > 0 && nblocks > 0 && stride >= n, "bad argument");
+    reduce_partials_kernel<<<(n + OT - 1) / OT, OT, 0, (cudaStream_t)stream>>>(gpart, nblocks, stride, n, scale, add, add_scale, out);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }

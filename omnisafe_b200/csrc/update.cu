@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
         if (net == 0 && threadIdx.x < A) {
             float g = sLs[2 * OUTP + threadIdx.x];
             // entropy bonus: loss -= coef * mean(entropy); d entropy / d log_std_a = 1 (mean over A)
-            if (blockIdx.x == 0) g -= p.lc.entropy_coef / (float)A;
+            // (only PPO._loss_pi / FOCOPS._loss_pi carry the entropy term)
+            if (blockIdx.x == 0 && (p.lc.kind == LOSS_PPO_CLIP || p.lc.kind == LOSS_FOCOPS))
+                g -= p.lc.entropy_coef / (float)A;
             gout[L.off_logstd + threadIdx.x] = g;
         }
         if (threadIdx.x < ST_N)

@@ -1,0 +1,98 @@
+"""CPU tests of the host-side logic: config surface, registry, Agent checks, and the N > 1 path
+(world_size-2 gloo): global steps_per_epoch partitioning, env-id sharding, averaging helpers."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def test_config_merge_and_unknown_keys():
+    from omnisafe_b200.utils.config import get_default_kwargs_yaml, recursive_check_config
+
+    cfg = get_default_kwargs_yaml('PPOLag', 'Some-Other-Env', 'on-policy')
+    assert cfg.algo_cfgs.steps_per_epoch == 20000 and cfg.algo_cfgs.batch_size == 64      # upstream defaults
+    assert cfg.lagrange_cfgs.lambda_lr == 0.035 and cfg.model_cfgs.actor.hidden_sizes == [64, 64]
+    cfg2 = get_default_kwargs_yaml('PPOLag', 'SyntheticBox-v0', 'on-policy')                 # env block merged
+    assert cfg2.train_cfgs.vector_env_nums == 4096 and cfg2.algo_cfgs.batch_size == 16384
+    with pytest.raises(KeyError):
+        recursive_check_config({'algo_cfgs': {'not_a_key': 1}}, cfg)
+    recursive_check_config({'algo_cfgs': {'clip': 0.1}, 'env_cfgs': {'anything': 1}}, cfg)
+    cfg.recurisve_update({'algo_cfgs': {'clip': 0.1}})
+    assert cfg.algo_cfgs.clip == 0.1 and cfg.algo_cfgs.gamma == 0.99
+    for algo in ('TRPOLag', 'CPO', 'FOCOPS'):
+        c = get_default_kwargs_yaml(algo, 'x', 'on-policy')
+        assert c.algo_cfgs.use_cost is True
+    assert get_default_kwargs_yaml('CPO', 'x').algo_cfgs.cg_iters == 15
+
+
+def test_registry_and_agent_checks():
+    import omnisafe_b200
+    from omnisafe_b200.algorithms import ALGORITHM2TYPE, registry
+
+    assert ALGORITHM2TYPE['PPOLag'] == 'on-policy' and registry.get('CPO').__name__ == 'CPO'
+    with pytest.raises(KeyError):
+        registry.get('NoSuchAlgo')
+    with pytest.raises(KeyError):
+        registry.register(registry.get('PPOLag'))          # duplicate names are rejected
+    with pytest.raises(AssertionError):
+        omnisafe_b200.Agent('NoSuchAlgo', 'SyntheticBox-v0')
+    with pytest.raises(AssertionError):
+        omnisafe_b200.Agent('PPOLag', 'NoSuchEnv-v0')
+    with pytest.raises(KeyError):
+        omnisafe_b200.Agent('PPOLag', 'SyntheticBox-v0', custom_cfgs={'algo_cfgs': {'bogus': 1}})
+    # device='cpu' is refused loudly: the path has no CPU fallback
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        omnisafe_b200.Agent('PPOLag', 'SyntheticBox-v0', custom_cfgs={'train_cfgs': {'device': 'cpu'}})
+
+
+def test_param_layout_matches_reference_counts():
+    from omnisafe_b200.models import param_layout
+
+    lay = param_layout(60, 8)    # actor 8 592, each critic 8 129
+    assert lay['actor']['size'] == 8592 and lay['reward_critic']['size'] == 8129 and lay['total'] == 24850
+    assert list(lay['actor']['entries'])[0] == 'log_std'
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    from omnisafe_b200.utils import distributed
+
+    distributed.init_process_group('cpu')      # gloo
+    assert distributed.world_size() == world and distributed.get_rank() == rank
+    # steps_per_epoch is global: local T = steps // world // envs (policy_gradient.py:L70-77)
+    T = distributed.local_steps(2 * 16 * 8, 16)
+    avg = distributed.dist_avg(torch.tensor(float(rank + 1)))
+    sums = torch.tensor([1.0 + rank, 10.0, 2.0 * rank, 5.0], dtype=torch.float64)
+    distributed.all_reduce_(sums)
+    try:
+        distributed.local_steps(2 * 16 * 8 + 1, 16)
+        bad = False
+    except AssertionError:
+        bad = True
+    q.put((rank, T, float(avg), sums.tolist(), rank * 16, bad))
+
+
+def test_two_rank_gloo_host_logic():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, T, avg, sums, env_off, bad in res:
+        assert T == 8 and abs(avg - 1.5) < 1e-6 and bad
+        assert sums == [3.0, 20.0, 2.0, 10.0]          # SUM over ranks of the epoch statistics vector
+        assert env_off == rank * 16                    # rank r owns global envs [r*N, (r+1)*N)
