@@ -191,21 +191,21 @@ def run_b200(args) -> dict:
     total = T * N
 
     def grad_launch():
-        lib().osb_minibatch_grad(ptr(ac.theta), w['obs_dim'], A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
-                                 ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']),
-                                 ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 12345, 0, w['batch_size'], 0,
-                                 0.2, 0.0, 1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7,
-                                 ptr(eng.gpart), ptr(eng.stats_part), 0, current_stream())
+        lib().osb_minibatch_grad_tc(ptr(ac.theta), w['obs_dim'], A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
+                                    ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']),
+                                    ptr(buf.adv_moments), 0, total, 12345, 0, w['batch_size'], 0, 0.2, 0.0,
+                                    ptr(algo._lagrange.state), 7, ptr(eng.gpart), ptr(eng.stats_part), 0,
+                                    current_stream())
 
     ms_grad = timed(grad_launch, 50) / 50
     flop_per_sample = _flops_per_sample(w['obs_dim'], A)
     ach_tf = flop_per_sample * w['batch_size'] / (ms_grad * 1e-3) / 1e12
     ms_gae = timed(buf.finish_paths, 50) / 50
     gae_gbs = 33.0 * total / (ms_gae * 1e-3) / 1e9
-    roofline = {'kernel': 'minibatch_grad_kernel', 'bound': 'tensor', 'achieved': ach_tf,
+    roofline = {'kernel': 'minibatch_grad_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf,
                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': ach_tf / peaks['bf16_tflops_sustained'], 'traffic': None,
-                'peak_source': peaks['source'] + ' (cuBLAS bf16 sustained; this kernel is the fp32-FMA parity path)',
+                'peak_source': peaks['source'] + ' (cuBLAS bf16 sustained; kernel runs tcgen05 kind::tf32, nominal tf32 peak = half of bf16)',
                 'us_per_launch': ms_grad * 1e3,
                 'gae': {'kernel': 'gae_dual_kernel', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
                         'unit': 'GB/s', 'frac': gae_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae * 1e3,
@@ -214,7 +214,7 @@ def run_b200(args) -> dict:
     out = {
         'metric': 'env-steps/sec (rollout+GAE+update) PPO-Lag', 'value': value, 'unit': 'env-steps/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 storage/accumulate; GAE fp64 carry)', 'data': 'synthetic',
         'config': {'workload': 'PPOLag SyntheticBox-v0 obs60/act8, 4096 envs/GPU x T=128, batch 16384, update_iters 8 '
                                '(BASELINE.json configs[1])', 'envs_per_gpu': N, 'steps_per_env': T,
                    'global_samples_per_step': samples_global, 'parallelism': f'dp{world}',

@@ -128,6 +128,17 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
                        float entropy_coef, float focops_lam, float focops_eta,
                        const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                        float* stats_part, const int* stop_flag, void* stream);
+/* Tensor-core variant of osb_minibatch_grad: the tile GEMMs run as tcgen05.mma kind::tf32 with TMEM
+ * accumulators (operands fp32 in 128B-swizzled smem tiles; transposed activations produced by
+ * role-swapped MMAs).  Same outputs; O <= 64, loss kinds 0 / 1 / 3.  This is arithmetic mode
+ * `precision = 1` of osb_ppo_update_epoch; mode 0 is the exact-fp32 FMA parity path. */
+int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
+                          const float* logp, const float* adv_r, const float* adv_c,
+                          const float* tv_r, const float* tv_c, const float* moments,
+                          const int* perm, long long total, unsigned perm_seed, long long mb_start,
+                          int mb_count, int loss_kind, float clip, float entropy_coef,
+                          const float* lagrange, int net_mask, float* gpart, float* stats_part,
+                          const int* stop_flag, void* stream);
 /* Full-batch actor pass (KL early stop policy_gradient.py:L383-397; TRPO/CPO line-search
  * evaluations trpo.py:L102-138, cpo.py:L114-171).  mu_store != NULL: write mu(theta) per row.
  * Otherwise out[8] <- {sum_s sum_a KL(old||new), sum ratio*adv, sum ratio*adv_c, sum ratio, count,
@@ -194,14 +205,21 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                          float critic_norm_coef, float max_grad_norm, float lr_actor,
                          float lr_critic, float target_kl, int kl_early_stop, float* gpart,
                          float* stats_part, float* sumsq_part, float* train_stats, double* eval_ws,
-                         double* eval_out, int* stop_flag, float* kl_state, void* comm,
-                         int world_size, void* stream);
+                         double* eval_out, int* stop_flag, float* kl_state, int precision,
+                         void* comm, int world_size, void* stream);
 /* NCCL via dlopen(libpath) of the libnccl.so.2 torch already loaded (distributed.py:L142-228). */
 int osb_nccl_unique_id(const char* libpath, unsigned char* id128);
 int osb_nccl_init(const char* libpath, const unsigned char* id128, int nranks, int rank,
                   void** comm_out);
 int osb_nccl_allreduce(void* comm, void* buf, long long count, int is_f64, void* stream);
 int osb_nccl_destroy(void* comm);
+
+/* ---- diagnostics ---------------------------------------------------------------------------
+ * One tcgen05 (kind::tf32, TMEM accumulator) GEMM D = A * B^T on a single CTA with every operand
+ * major combination; out[128][N] is the raw TMEM dump.  Pins the descriptor / swizzle conventions
+ * the tensor-core MLP tiles rely on (tests/test_umma_gpu.py). */
+int osb_umma_selftest(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn,
+                      float* out, void* stream);
 
 #ifdef __cplusplus
 }

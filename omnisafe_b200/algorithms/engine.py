@@ -41,6 +41,7 @@ class UpdateEngine:
         self.cg_scalars = torch.zeros(4, **f32)
         self.scalar = torch.zeros(4, **f32)
         self._perm_seed = 0x1234567
+        self.precision = 0   # 0 = exact fp32 FMA tiles (parity), 1 = TF32 tcgen05 tiles (fast)
 
     # ---- helpers ----------------------------------------------------------------------------
     def _batch_ptrs(self):
@@ -56,7 +57,7 @@ class UpdateEngine:
     def ppo_epoch(self, *, loss_kind, lagrange, net_mask, batch_size, update_iters, clip=0.2,
                   entropy_coef=0.0, focops_lam=1.0, focops_eta=0.0, critic_norm_coef=0.0,
                   max_grad_norm=0.0, lr_actor=0.0, lr_critic=0.0, target_kl=0.0, kl_early_stop=False,
-                  perm=None) -> None:
+                  perm=None, precision: int | None = None) -> None:
         a = self.agent
         if perm is not None:
             assert perm.dtype == torch.int32 and perm.shape == (update_iters, self.total)
@@ -69,6 +70,7 @@ class UpdateEngine:
             float(lr_actor), float(lr_critic), float(target_kl), int(kl_early_stop),
             ptr(self.gpart), ptr(self.stats_part), ptr(self.sumsq_part), ptr(self.train_stats),
             ptr(self.eval_ws), ptr(self.eval_out), ptr(self.stop_flag), ptr(self.kl_state),
+            self.precision if precision is None else int(precision),
             distributed.nccl_comm(), distributed.world_size(), current_stream())
 
     # ---- full-batch pieces for the natural-gradient family ---------------------------------

@@ -16,6 +16,13 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
                        float entropy_coef, float focops_lam, float focops_eta,
                        const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                        float* stats_part, const int* stop_flag, void* stream);
+int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
+                          const float* logp, const float* adv_r, const float* adv_c,
+                          const float* tv_r, const float* tv_c, const float* moments,
+                          const int* perm, long long total, unsigned perm_seed, long long mb_start,
+                          int mb_count, int loss_kind, float clip, float entropy_coef,
+                          const float* lagrange, int net_mask, float* gpart, float* stats_part,
+                          const int* stop_flag, void* stream);
 int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, const float* act,
                    const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
                    const float* logstd_old, const float* moments, const float* lagrange,
@@ -132,8 +139,8 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                          float critic_norm_coef, float max_grad_norm, float lr_actor,
                          float lr_critic, float target_kl, int kl_early_stop, float* gpart,
                          float* stats_part, float* sumsq_part, float* train_stats, double* eval_ws,
-                         double* eval_out, int* stop_flag, float* kl_state, void* comm,
-                         int world_size, void* stream) {
+                         double* eval_out, int* stop_flag, float* kl_state, int precision,
+                         void* comm, int world_size, void* stream) {
     OSB_CHECK_ARG(theta && grad && adam_m && adam_v && adam_step && obs && moments, "null pointer");
     OSB_CHECK_ARG(batch_size > 0 && update_iters >= 0 && total > 0 && world_size >= 1, "bad argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -151,15 +158,23 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
         OSB_CUDA(cudaMemcpyAsync(logstd_old, theta, A * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     const float gscale = 1.0f / (float)world_size;
+    // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
+    const bool use_tc = precision == 1 && O <= 64 && loss_kind != 2;
     for (int it = 0; it < update_iters; ++it) {
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
         for (long long start = 0; start < total; start += batch_size) {
             const int count = (int)((total - start < batch_size) ? (total - start) : batch_size);
-            rc = osb_minibatch_grad(theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old,
-                                    moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it,
-                                    start, count, loss_kind, clip, entropy_coef, focops_lam,
-                                    focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part,
-                                    stop_flag, stream);
+            if (use_tc)
+                rc = osb_minibatch_grad_tc(theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c,
+                                           moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it,
+                                           start, count, loss_kind, clip, entropy_coef, lagrange,
+                                           net_mask, gpart, stats_part, stop_flag, stream);
+            else
+                rc = osb_minibatch_grad(theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old,
+                                        moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it,
+                                        start, count, loss_kind, clip, entropy_coef, focops_lam,
+                                        focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part,
+                                        stop_flag, stream);
             if (rc) return rc;
             rc = osb_grad_reduce(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
                                  critic_norm_coef, net_mask, sumsq_part, adam_step, train_stats,

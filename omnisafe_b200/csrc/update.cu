@@ -785,9 +785,10 @@ static size_t fvp_smem_bytes() {
 
 extern "C" {
 
+// CTAs per network: the three networks of a minibatch step share the 148 SMs in one wave
 int osb_update_grid_blocks(int mb_count) {
     int tiles = (mb_count + UT - 1) / UT;
-    return tiles < 148 ? tiles : 148;
+    return tiles < 49 ? tiles : 49;
 }
 
 // One minibatch: fused forward + loss + backward for the networks in `net_mask`.

@@ -1,0 +1,96 @@
+"""GPU: the tcgen05 (TF32) variant of the fused minibatch kernel vs autograd and vs the exact-fp32
+path.  Tolerance: TF32 keeps 10 mantissa bits, so gradients agree to ~1e-2 of their scale (stated
+here; the fp32 FMA path is the 1e-5 parity path)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor_critic as oac
+from oracle import learner as ol
+from test_update_gpu import _rand_data, _rows, _setup
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('O,A,N,T,loss_kind', [(60, 8, 20, 13, 0), (60, 8, 64, 40, 0), (17, 6, 9, 31, 3), (64, 16, 16, 24, 1), (60, 8, 512, 80, 0)])
+def test_tc_grad_vs_autograd(cuda, O, A, N, T, loss_kind):
+    from omnisafe_b200._lib import current_stream, lib, ptr
+
+    rng = np.random.default_rng(O + N)
+    theta = oac.init_theta(O, A, seed=5)
+    data = _rand_data(rng, N, T, O, A, theta)
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+    B = N * T
+    lam = 0.37
+    lag = torch.tensor([lam], dtype=torch.float32, device=cuda)
+    perm_em = rng.permutation(B)
+    start, count = 3, B - 10
+    perm = torch.as_tensor(_rows(perm_em, N, T)).to(cuda)
+    coef = 1e-3
+    d = buf.data
+    lib().osb_minibatch_grad_tc(ptr(agent.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
+                                ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']),
+                                ptr(buf.adv_moments), ptr(perm), B, 0, start, count, loss_kind, 0.2, 0.01,
+                                ptr(lag), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, current_stream())
+    nb = lib().osb_update_grid_blocks(count)
+    lib().osb_grad_reduce(ptr(eng.gpart), ptr(eng.stats_part), nb, O, A, ptr(agent.theta), ptr(agent.grad),
+                          coef, 7, ptr(eng.sumsq_part), ptr(agent.adam_step), ptr(eng.train_stats), 0,
+                          current_stream())
+    torch.cuda.synchronize()
+    got = agent.grad.cpu().numpy()
+    L = ol.Learner(theta, O, A)
+    idx = torch.as_tensor(perm_em[start:start + count])
+    t = {k: torch.as_tensor(v)[idx] for k, v in data.items()}
+    adv = (t['adv_r'] - lam * t['adv_c']) / (1 + lam)
+    if loss_kind == 0:
+        loss, _ = L.loss_pi_ppo(t['obs'], t['act'], t['logp'], adv, 0.2, 0.01)
+    elif loss_kind == 1:
+        loss = L.loss_pi_plain(t['obs'], t['act'], t['logp'], adv)
+    else:
+        loss = L.loss_pi_cost(t['obs'], t['act'], t['logp'], t['adv_c'])
+    loss.backward()
+    for net, tgt in (('reward_critic', 'target_value_r'), ('cost_critic', 'target_value_c')):
+        lv = torch.nn.functional.mse_loss(oac.critic_value(L.params[net], t['obs']), t[tgt])
+        for p_ in L.params[net].values():
+            lv = lv + p_.pow(2).sum() * coef
+        lv.backward()
+    want = torch.cat([L.flat_grad(n) for n in ol.NETS]).numpy()
+    lay = oac.layout(O, A)
+    bad = 0
+    for net in ol.NETS:
+        for name, (off, shape) in lay[net]['entries'].items():
+            n = int(np.prod(shape))
+            w, g = want[off:off + n], got[off:off + n]
+            scale = max(np.abs(w).max(), 1e-6)
+            err = np.abs(g - w).max() / scale
+            cos = float((g * w).sum() / (np.linalg.norm(g) * np.linalg.norm(w) + 1e-30))
+            rel = float(np.linalg.norm(g - w) / (np.linalg.norm(w) + 1e-30))
+            print(f'{net}.{name}: max-err/scale {err:.2e}  l2-rel {rel:.2e}  cos {cos:.6f}')
+            tol = 2e-2 if (net == 'actor' and loss_kind == 0) else 5e-3   # PPO clip flips near the boundary
+            bad += (rel > tol) or (cos < 0.9999)
+    assert bad == 0
+
+
+@pytest.mark.timeout(120)
+def test_tc_epoch_close_to_fp32_epoch(cuda):
+    """A whole PPO-Lag update epoch in TF32 mode lands next to the exact-fp32 epoch."""
+    rng = np.random.default_rng(3)
+    N, T, O, A = 64, 32, 60, 8
+    theta = oac.init_theta(O, A, seed=2)
+    data = _rand_data(rng, N, T, O, A, theta)
+    B = N * T
+    perms = torch.as_tensor(np.stack([_rows(rng.permutation(B), N, T) for _ in range(3)])).to(cuda)
+    out = []
+    for prec in (0, 1):
+        agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+        lag = torch.tensor([0.2, 0, 0, 0], dtype=torch.float32, device=cuda)
+        eng.ppo_epoch(loss_kind=0, lagrange=lag, net_mask=7, batch_size=512, update_iters=3, clip=0.2,
+                      critic_norm_coef=0.001, max_grad_norm=40.0, lr_actor=3e-4, lr_critic=3e-4,
+                      target_kl=10.0, kl_early_stop=False, perm=perms, precision=prec)
+        torch.cuda.synchronize()
+        out.append(agent.theta.cpu().numpy())
+    delta = out[0] - theta
+    diff = out[1] - out[0]
+    assert np.isfinite(out[1]).all()
+    assert np.linalg.norm(diff) < 0.15 * np.linalg.norm(delta), (np.linalg.norm(diff), np.linalg.norm(delta))
