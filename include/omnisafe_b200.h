@@ -148,6 +148,12 @@ int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, con
                    const float* logstd_old, const float* moments, const float* lagrange,
                    long long total, int stride, float* mu_store, double* workspace, double* out,
                    void* stream);
+/* Tensor-core (tcgen05 TF32) variant of osb_actor_eval: same arguments / outputs, O <= 64. */
+int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, const float* act,
+                      const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
+                      const float* logstd_old, const float* moments, const float* lagrange,
+                      long long total, int stride, float* mu_store, double* workspace, double* out,
+                      void* stream);
 /* Fisher-vector product partials (NaturalPG._fvp, base/natural_pg.py:L74-119, analytic
  * Gauss-Newton form; damping is added by osb_reduce_partials).  gpart: blocks * P_actor floats. */
 int osb_fvp_grid_blocks(long long total, int stride);
@@ -170,6 +176,12 @@ int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const
                   float lr_critic_r, float lr_critic_c, float grad_scale, float critic_norm_coef,
                   float* train_stats, int do_clip, int do_adam, int net_mask, const int* stop_flag,
                   void* stream);
+/* Single-rank fusion of osb_grad_reduce + osb_clip_adam (clip and step) in one cooperative launch. */
+int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                    float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                    float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
+                    float lr_critic_c, int net_mask, float* sumsq_part, float* train_stats,
+                    const int* stop_flag, void* stream);
 /* Lagrange.update_lagrange_multiplier (common/lagrange.py:L114-136) on the device: Adam step on
  * lambda with grad -(Jc - cost_limit), Jc = window_sums[1]/window_sums[3], clamp to
  * [0, upper_bound] (upper_bound < 0 = none).  state[4] = {lambda, m, v, t}.  nan_flag <- 1 when no

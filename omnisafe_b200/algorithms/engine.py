@@ -44,6 +44,9 @@ class UpdateEngine:
         self.precision = 0   # 0 = exact fp32 FMA tiles (parity), 1 = TF32 tcgen05 tiles (fast)
 
     # ---- helpers ----------------------------------------------------------------------------
+    def _eval_fn(self):
+        return lib().osb_actor_eval_tc if (self.precision == 1 and self.O <= 64) else lib().osb_actor_eval
+
     def _batch_ptrs(self):
         d = self.buf.data
         return [ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']),
@@ -77,8 +80,8 @@ class UpdateEngine:
     def snapshot_old_policy(self) -> None:
         """p_dist = actor(obs) at the current parameters (trpo.py:L177, cpo.py:L366)."""
         a = self.agent
-        lib().osb_actor_eval(ptr(a.theta), self.O, self.A, ptr(self.buf.data['obs']), 0, 0, 0, 0, 0, 0,
-                             0, 0, self.total, 1, ptr(self.mu_old), 0, 0, current_stream())
+        self._eval_fn()(ptr(a.theta), self.O, self.A, ptr(self.buf.data['obs']), 0, 0, 0, 0, 0, 0,
+                        0, 0, self.total, 1, ptr(self.mu_old), 0, 0, current_stream())
         self.logstd_old.copy_(a.theta[:self.A])
 
     def actor_loss_grad(self, loss_kind, lagrange, out_grad: torch.Tensor, sign: float = 1.0) -> torch.Tensor:
@@ -138,10 +141,10 @@ class UpdateEngine:
         Returns python floats averaged over ranks: loss (= -mean ratio*adv), loss_r (= -mean
         ratio*adv_r), loss_c (= mean ratio*adv_c), kl (= mean over samples AND action dims)."""
         d = self.buf.data
-        lib().osb_actor_eval(ptr(theta_actor), self.O, self.A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
-                             ptr(d['adv_r']), ptr(d['adv_c']), ptr(self.mu_old), ptr(self.logstd_old),
-                             ptr(self.buf.adv_moments), ptr(lagrange), self.total, 1, 0, ptr(self.eval_ws),
-                             ptr(self.eval_out), current_stream())
+        self._eval_fn()(ptr(theta_actor), self.O, self.A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
+                        ptr(d['adv_r']), ptr(d['adv_c']), ptr(self.mu_old), ptr(self.logstd_old),
+                        ptr(self.buf.adv_moments), ptr(lagrange), self.total, 1, 0, ptr(self.eval_ws),
+                        ptr(self.eval_out), current_stream())
         if distributed.world_size() > 1:
             distributed.all_reduce_(self.eval_out)
         o = self.eval_out.tolist()

@@ -28,6 +28,11 @@ int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, con
                    const float* logstd_old, const float* moments, const float* lagrange,
                    long long total, int stride, float* mu_store, double* workspace, double* out,
                    void* stream);
+int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, const float* act,
+                      const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
+                      const float* logstd_old, const float* moments, const float* lagrange,
+                      long long total, int stride, float* mu_store, double* workspace, double* out,
+                      void* stream);
 int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, int O, int A,
                     const float* theta, float* grad, float critic_norm_coef, int net_mask,
                     float* sumsq_part, int* adam_step, float* train_stats, const int* stop_flag,
@@ -37,6 +42,11 @@ int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const
                   float lr_critic_r, float lr_critic_c, float grad_scale, float critic_norm_coef,
                   float* train_stats, int do_clip, int do_adam, int net_mask, const int* stop_flag,
                   void* stream);
+int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                    float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                    float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
+                    float lr_critic_c, int net_mask, float* sumsq_part, float* train_stats,
+                    const int* stop_flag, void* stream);
 int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
                  float* kl_state, void* stream);
 }
@@ -149,17 +159,18 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     OSB_CUDA(cudaMemsetAsync(kl_state, 0, 4 * sizeof(float), s));
     OSB_CUDA(cudaMemsetAsync(train_stats, 0, 3 * 8 * sizeof(float), s));
     int rc;
+    // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
+    const bool use_tc = precision == 1 && O <= 64 && loss_kind != 2;
     const bool train_actor = (net_mask & 1) != 0;
     if (train_actor) {
         OSB_CHECK_ARG(mu_old && logstd_old && eval_ws && eval_out, "actor update needs mu_old/logstd_old/eval buffers");
-        rc = osb_actor_eval(theta, O, A, obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                            nullptr, nullptr, total, 1, mu_old, nullptr, nullptr, stream);
+        rc = (use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, nullptr, nullptr, nullptr, nullptr,
+                                                          nullptr, nullptr, nullptr, nullptr, total, 1, mu_old,
+                                                          nullptr, nullptr, stream);
         if (rc) return rc;
         OSB_CUDA(cudaMemcpyAsync(logstd_old, theta, A * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     const float gscale = 1.0f / (float)world_size;
-    // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
-    const bool use_tc = precision == 1 && O <= 64 && loss_kind != 2;
     for (int it = 0; it < update_iters; ++it) {
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
         for (long long start = 0; start < total; start += batch_size) {
@@ -176,11 +187,15 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                                         focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part,
                                         stop_flag, stream);
             if (rc) return rc;
-            rc = osb_grad_reduce(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
-                                 critic_norm_coef, net_mask, sumsq_part, adam_step, train_stats,
-                                 stop_flag, stream);
-            if (rc) return rc;
-            if (comm && world_size > 1) {
+            if (!(comm && world_size > 1)) {
+                rc = osb_optim_fused(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                                     adam_m, adam_v, adam_step, critic_norm_coef, max_grad_norm, lr_actor,
+                                     lr_critic, lr_critic, net_mask, sumsq_part, train_stats, stop_flag, stream);
+            } else {
+                rc = osb_grad_reduce(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                                     critic_norm_coef, net_mask, sumsq_part, adam_step, train_stats,
+                                     stop_flag, stream);
+                if (rc) return rc;
                 rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
                                    max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, critic_norm_coef, train_stats, 1, 0, net_mask,
                                    stop_flag, stream);
@@ -190,16 +205,13 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                 rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
                                    max_grad_norm, lr_actor, lr_critic, lr_critic, gscale, critic_norm_coef, train_stats, 0, 1, net_mask,
                                    stop_flag, stream);
-            } else {
-                rc = osb_clip_adam(grad, theta, adam_m, adam_v, adam_step, sumsq_part, O, A,
-                                   max_grad_norm, lr_actor, lr_critic, lr_critic, 1.f, critic_norm_coef, train_stats, 1, 1, net_mask,
-                                   stop_flag, stream);
             }
             if (rc) return rc;
         }
         if (train_actor) {
-            rc = osb_actor_eval(theta, O, A, obs, act, logp, adv_r, adv_c, mu_old, logstd_old,
-                                moments, lagrange, total, 1, nullptr, eval_ws, eval_out, stream);
+            rc = (use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, act, logp, adv_r, adv_c, mu_old,
+                                                              logstd_old, moments, lagrange, total, 1, nullptr,
+                                                              eval_ws, eval_out, stream);
             if (rc) return rc;
             if (comm && world_size > 1) {
                 rc = osb_nccl_allreduce(comm, eval_out, 8, 1, stream);

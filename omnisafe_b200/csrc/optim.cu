@@ -11,6 +11,7 @@
 //   conjugate_gradients                  utils/math.py:L86-132
 #include "common.cuh"
 #include "mlp.cuh"
+#include <cooperative_groups.h>
 
 namespace osb {
 
@@ -20,7 +21,7 @@ struct ReduceArgs {
     const float* gpart;       // [nblocks][P]
     const float* stats_part;  // [nblocks][3][8]
     int nblocks, P, O, A;
-    const float* theta;
+    float* theta;
     float* grad;              // [P]
     float critic_norm_coef;   // 0 -> off
     int net_mask;
@@ -124,6 +125,81 @@ __global__ void __launch_bounds__(OT) clip_adam_kernel(AdamArgs p) {
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
     p.theta[q] = __fadd_rn(p.theta[q], __fmul_rn(-step_size, __fdiv_rn(m, denom)));
     p.m[q] = m; p.v[q] = v;
+}
+
+// Single-rank fast path: partial reduction + critic L2 term + per-network clip + Adam in ONE
+// cooperative launch (grid.sync() between the norm reduction and the parameter update).
+struct FusedOptArgs {
+    ReduceArgs r;
+    float* m;
+    float* v;
+    float max_grad_norm;
+    float lr[3];
+};
+
+__global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
+    namespace cg = cooperative_groups;
+    if (p.r.stop_flag && *p.r.stop_flag) return;          // uniform across the grid
+    const int net = blockIdx.y;
+    const bool active = ((p.r.net_mask >> net) & 1) != 0;
+    __shared__ float red[OT / 32], red2[OT / 32];
+    __shared__ float s_scale, s_step, s_bc2;
+    const NetLayout L = net_layout(net, p.r.O, p.r.A);
+    const int noff = net_offset(net, p.r.O, p.r.A);
+    const int pl = blockIdx.x * OT + threadIdx.x;
+    const int q = noff + pl;
+    float g = 0.f, th = 0.f;
+    if (active) {
+        if (pl < L.size) {
+            for (int b = 0; b < p.r.nblocks; ++b) g += p.r.gpart[(size_t)b * p.r.P + q];
+            th = p.r.theta[q];
+            if (net != 0 && p.r.critic_norm_coef > 0.f) g += 2.f * p.r.critic_norm_coef * th;
+        }
+        float s = warp_sum(g * g), s2 = warp_sum(net != 0 ? th * th : 0.f);
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red2[threadIdx.x >> 5] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f, t2 = 0.f;
+            for (int w = 0; w < OT / 32; ++w) { t += red[w]; t2 += red2[w]; }
+            p.r.sumsq_part[net * gridDim.x + blockIdx.x] = t;
+            p.r.sumsq_part[(3 + net) * gridDim.x + blockIdx.x] = t2;
+        }
+    }
+    cg::this_grid().sync();
+    if (active && threadIdx.x == 0) {
+        float tot = 0.f, t2 = 0.f;
+        for (int b = 0; b < (int)gridDim.x; ++b) { tot += p.r.sumsq_part[net * gridDim.x + b]; t2 += p.r.sumsq_part[(3 + net) * gridDim.x + b]; }
+        s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
+        const int t = p.r.adam_step[net] + 1;
+        const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+        s_step = (float)((double)p.lr[net] / bc1);
+        s_bc2 = (float)sqrt(bc2);
+        if (blockIdx.x == 0) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int b = 0; b < p.r.nblocks; ++b)
+                for (int i = 0; i < 4; ++i) acc[i] += p.r.stats_part[((size_t)b * 3 + net) * 8 + i];
+            const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
+            float* ts = p.r.train_stats + net * 8;
+            ts[0] += acc[0] * inv + ((net != 0) ? p.r.critic_norm_coef * t2 : 0.f);
+            ts[1] += acc[1] * inv;
+            ts[2] += acc[2] * inv;
+            ts[3] += 1.f;
+        }
+    }
+    __syncthreads();
+    if (active && pl < L.size) {
+        g *= s_scale;
+        p.r.grad[q] = g;
+        float m = p.m[q], v = p.v[q];
+        m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));
+        v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));
+        const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), s_bc2), 1e-8f);
+        p.r.theta[q] = __fadd_rn(th, __fmul_rn(-s_step, __fdiv_rn(m, denom)));
+        p.m[q] = m; p.v[q] = v;
+    }
+    // every block has read adam_step[net] (before the barrier below) -> block 0 may advance it
+    cg::this_grid().sync();
+    if (active && blockIdx.x == 0 && threadIdx.x == 0) p.r.adam_step[net] += 1;
 }
 
 // lambda <- clamp(Adam(lambda, grad = -(Jc - limit)), 0, upper).  state[4] = {lambda, m, v, t}.
@@ -259,7 +335,7 @@ int osb_grad_reduce(const float* gpart, const float* stats_part, int nblocks, in
     ReduceArgs p;
     p.gpart = gpart; p.stats_part = stats_part; p.nblocks = nblocks; p.O = O; p.A = A;
     p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size;
-    p.theta = theta; p.grad = grad; p.critic_norm_coef = critic_norm_coef; p.net_mask = net_mask;
+    p.theta = const_cast<float*>(theta); p.grad = grad; p.critic_norm_coef = critic_norm_coef; p.net_mask = net_mask;
     p.sumsq_part = sumsq_part; p.adam_step = adam_step; p.train_stats = train_stats; p.stop_flag = stop_flag;
     grad_reduce_kernel<<<dim3(osb_optim_blocks(O, A), 3), OT, 0, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
@@ -284,6 +360,26 @@ int osb_clip_adam(float* grad, float* theta, float* adam_m, float* adam_v, const
     p.stop_flag = stop_flag;
     clip_adam_kernel<<<dim3(p.NB, 3), OT, 0, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+// grad_reduce + clip + Adam fused in one cooperative launch (single-rank path).
+int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                    float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                    float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
+                    float lr_critic_c, int net_mask, float* sumsq_part, float* train_stats,
+                    const int* stop_flag, void* stream) {
+    OSB_CHECK_ARG(gpart && stats_part && theta && grad && adam_m && adam_v && adam_step && sumsq_part && train_stats, "null pointer");
+    FusedOptArgs p;
+    p.r.gpart = gpart; p.r.stats_part = stats_part; p.r.nblocks = nblocks; p.r.O = O; p.r.A = A;
+    p.r.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size;
+    p.r.theta = theta; p.r.grad = grad; p.r.critic_norm_coef = critic_norm_coef; p.r.net_mask = net_mask;
+    p.r.sumsq_part = sumsq_part; p.r.adam_step = adam_step; p.r.train_stats = train_stats; p.r.stop_flag = stop_flag;
+    p.m = adam_m; p.v = adam_v; p.max_grad_norm = max_grad_norm;
+    p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
+    void* args[] = {&p};
+    OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
+                                         (cudaStream_t)stream));
     return OSB_OK;
 }
 

@@ -67,59 +67,6 @@ __device__ __forceinline__ unsigned long long tc_feistel(unsigned long long k, u
     return x;
 }
 
-// issue D[tmem] (+)= A * B^T, both K-major SW128 tiles with RA / RB rows; one thread.
-__device__ __forceinline__ void tc_gemm(uint32_t tmem_d, uint32_t a_base, int RA, uint32_t b_base, int RB,
-                                        int M, int N, int K, bool accumulate) {
-    const uint32_t idesc = idesc_tf32(M, N, 0, 0);
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint32_t offA = (uint32_t)((ks >> 2) * RA * 128 + (ks & 3) * 32);
-        const uint32_t offB = (uint32_t)((ks >> 2) * RB * 128 + (ks & 3) * 32);
-        mma_tf32(tmem_d, desc_kmajor(a_base + offA), desc_kmajor(b_base + offB), idesc,
-                 (accumulate || ks > 0) ? 1u : 0u);
-    }
-}
-
-// round-to-nearest TF32 (the MMA would otherwise truncate the low 13 mantissa bits: biased)
-__device__ __forceinline__ float tf32r(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// explicit shared-window (32-bit address) accessors: keeps every tile access an LDS/STS
-__device__ __forceinline__ float lds(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts(uint32_t a, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int r, int c, int R) {
-    return base + sw128_offset(r, c, R);
-}
-// store / load 32 consecutive columns [c0, c0+32) (c0 % 32 == 0) of row r
-__device__ __forceinline__ void store_row32(uint32_t base, int r, int c0, int R, const float (&v)[32]) {
-    const uint32_t row = base + (uint32_t)((c0 >> 5) * R * 128 + r * 128);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t)((i ^ (r & 7)) << 4)),
-                     "f"(tf32r(v[4 * i])), "f"(tf32r(v[4 * i + 1])), "f"(tf32r(v[4 * i + 2])), "f"(tf32r(v[4 * i + 3]))
-                     : "memory");
-}
-__device__ __forceinline__ void load_row32(uint32_t base, int r, int c0, int R, float (&v)[32]) {
-    const uint32_t row = base + (uint32_t)((c0 >> 5) * R * 128 + r * 128);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
-                     : "r"(row + (uint32_t)((i ^ (r & 7)) << 4)));
-}
-
 // TMEM column map
 constexpr uint32_t C_Z = 0, C_ZT = 64, C_OUT = 192, C_DW2 = 224, C_DW1 = 288, TMEM_COLS = 512;
 

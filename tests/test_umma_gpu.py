@@ -12,9 +12,12 @@ def _tf32(x):
     return u.view(np.float32)
 
 
+# K-major operands only: for kind::tf32 an MN-major operand needs the SWIZZLE_128B_BASE32B layout
+# (32-byte swizzle base), i.e. it cannot share a physical tile with the K-major view -- which is why
+# the kernels produce transposed activations with role-swapped MMAs instead (csrc/update_tc.cu).
 @pytest.mark.parametrize('M,N,K,a_mn,b_mn', [
-    (128, 64, 64, 0, 0), (128, 64, 64, 0, 1), (128, 64, 128, 1, 1), (128, 16, 64, 0, 0), (128, 64, 16, 0, 1),
-    (128, 64, 128, 1, 0), (128, 192, 64, 0, 0), (64, 64, 128, 1, 1), (64, 64, 64, 0, 0),
+    (128, 64, 64, 0, 0), (128, 16, 64, 0, 0), (128, 64, 16, 0, 0), (128, 192, 64, 0, 0), (128, 64, 128, 0, 0),
+    (64, 64, 64, 0, 0), (64, 128, 64, 0, 0), (64, 64, 128, 0, 0), (64, 128, 16, 0, 0),
 ])
 def test_umma_gemm(cuda, M, N, K, a_mn, b_mn):
     from omnisafe_b200._lib import current_stream, lib, ptr
@@ -33,6 +36,5 @@ def test_umma_gemm(cuda, M, N, K, a_mn, b_mn):
         np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-3)
     else:
         # M = 64: report where the 64 rows land in TMEM (lane mapping), then check values
-        rows = [int(np.argmin(np.abs(got - want[r]).sum(1))) for r in range(64)]
-        print('M=64 row -> TMEM lane:', rows)
+        rows = [32 * (r // 16) + r % 16 for r in range(64)]   # M = 64: row r -> TMEM lane 32*(r/16) + r%16
         np.testing.assert_allclose(got[rows], want, rtol=2e-3, atol=2e-3)

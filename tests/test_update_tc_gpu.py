@@ -94,3 +94,27 @@ def test_tc_epoch_close_to_fp32_epoch(cuda):
     diff = out[1] - out[0]
     assert np.isfinite(out[1]).all()
     assert np.linalg.norm(diff) < 0.15 * np.linalg.norm(delta), (np.linalg.norm(diff), np.linalg.norm(delta))
+
+
+@pytest.mark.timeout(120)
+def test_tc_actor_eval_matches_fp32_eval(cuda):
+    rng = np.random.default_rng(9)
+    N, T, O, A = 96, 50, 60, 8
+    theta = oac.init_theta(O, A, seed=4)
+    data = _rand_data(rng, N, T, O, A, theta)
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+    eng.precision = 0
+    eng.snapshot_old_policy()
+    mu0 = eng.mu_old.clone()
+    th2 = agent.theta.clone()
+    th2[: eng.Pa] += 0.02 * torch.randn(eng.Pa, device=cuda)
+    lag = torch.tensor([0.3], dtype=torch.float32, device=cuda)
+    ref = eng.evaluate(th2, lag)
+    eng.precision = 1
+    eng.snapshot_old_policy()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(eng.mu_old.cpu().numpy(), mu0.cpu().numpy(), rtol=0, atol=3e-3)
+    eng.mu_old.copy_(mu0)
+    got = eng.evaluate(th2, lag)
+    for k in ('kl', 'loss', 'loss_c', 'loss_r', 'ratio'):
+        np.testing.assert_allclose(got[k], ref[k], rtol=2e-2, atol=2e-3, err_msg=k)
