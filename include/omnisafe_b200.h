@@ -66,7 +66,8 @@ int osb_discount_cumsum(const void* x, int x_is_f64, int rows, int len, double d
  * (all zero-initialised by the caller).  osb_env_reset = OnPolicyAdapter.reset() at epoch start
  * (onpolicy_adapter.py:L80).  osb_rollout_step with t in [0, T) performs step t; t == T is the
  * epoch-end bootstrap launch (critics only).  eps = [N][A] standard-normal draws of this step
- * (parity mode) or NULL (in-kernel Philox keyed by noise_seed / global_step). */
+ * (parity mode) or NULL (in-kernel Philox keyed by noise_seed / global_step).  precision: 0 = exact
+ * fp32 FMA tiles (parity), 1 = tcgen05 TF32 tiles of 128 envs (O <= 64; falls back to 0 otherwise). */
 int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned term_threshold,
                   unsigned env_id_offset, float cost_threshold, int obs_normalize, int N,
                   float* s_raw, float* final_raw, int* ep_step, unsigned* episode, unsigned* gstep,
@@ -84,7 +85,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
                      float* obs, float* act, float* logp, float* rew, float* cost, float* val_r,
                      float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
                      const float* theta, const float* eps, unsigned noise_seed,
-                     unsigned global_step, void* stream);
+                     unsigned global_step, int precision, void* stream);
 /* Whole-epoch rollout in one call: reset, T step launches (eps_all = [T][N][A] or NULL), the
  * epoch-end bootstrap launch and the episode window (= OnPolicyAdapter.rollout,
  * adapter/onpolicy_adapter.py:L58-136).  Philox counter = epoch_index * T + t. */
@@ -99,7 +100,7 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
                       float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
                       const float* theta, const float* eps_all, unsigned noise_seed,
                       unsigned epoch_index, int W, float* ring, int* meta, double* window_sums,
-                      void* stream);
+                      int precision, void* stream);
 /* Logger window of the last <= W finished episodes in (step, env) order
  * (common/logger.py:L253-282, adapter/onpolicy_adapter.py:L159-175).  ring[3][W], meta[2] persist
  * across epochs; window_sums[4] <- {sum EpRet, sum EpCost, sum EpLen, count} (fp64). */

@@ -36,6 +36,7 @@ class OnPolicyAdapter:
         self.ep_meta = torch.zeros(2, dtype=torch.int32, device=self._device)
         self.window_sums = torch.zeros(4, dtype=torch.float64, device=self._device)
         self._epoch_index = 0
+        self.precision = 1 if str(getattr(cfgs.train_cfgs, 'matmul_precision', 'fp32') if hasattr(cfgs, 'train_cfgs') else 'fp32') == 'tf32' else 0
         self.noise_seed = (int(seed) * 2654435761 + 12345) & 0xFFFFFFFF
 
     @property
@@ -71,7 +72,7 @@ class OnPolicyAdapter:
                 + self._obs_normalizer.ptrs() + buffer.slab_ptrs()
                 + [ptr(agent.theta), ptr(eps), self.noise_seed, self._epoch_index & 0xFFFFFFFF,
                    self.window_lens, ptr(self.ep_ring), ptr(self.ep_meta), ptr(self.window_sums),
-                   current_stream()])
+                   int(self.precision), current_stream()])
         lib().osb_rollout_epoch(*args)
         self._epoch_index += 1
 

@@ -15,6 +15,7 @@
 // last actor CTA of the launch; the next launch (= kernel boundary = grid sync) consumes it.
 #include "common.cuh"
 #include "mlp.cuh"
+#include "umma.cuh"
 
 namespace osb {
 
@@ -229,6 +230,7 @@ struct StepArgs {
     uint32_t global_step; // epoch * T + t, Philox counter
     int t, T, N;
     int is_tail;          // t == T: critics only (epoch-end bootstrap)
+    int precision;        // 0 = fp32 FMA tiles of 32 envs, 1 = tcgen05 TF32 tiles of 128 envs (O <= 64)
 };
 
 // normalise (or copy) a tile of raw observations into sX (chunk kc), zero padded.
@@ -488,6 +490,329 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the step kernel (train_cfgs.matmul_precision = tf32, O <= 64): tiles of 128
+// envs, the three layer GEMMs of a network as tcgen05.mma kind::tf32 with TMEM accumulators, operands
+// staged as 128B-swizzled K-major smem tiles.  Everything around the GEMMs (ObsNormalize, sampling,
+// env transition, slab append, normaliser sums, ticket) is the arithmetic of rollout_step_kernel.
+constexpr int RTC = 128;
+
+__global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p) {
+    using namespace umma;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    const uint32_t B0 = smem_u32(smem_raw) + pad;       // X -> H2
+    const uint32_t B2 = B0 + RTC * 256;                 // H1
+    const uint32_t sW1 = B2 + RTC * 256, sW2 = sW1 + 16384, sW3 = sW2 + 16384;
+    float* fbase = reinterpret_cast<float*>(smem_raw + pad + 2 * RTC * 256 + 2 * 16384 + 4096);
+    float* sB1 = fbase;            // [64]
+    float* sB2 = sB1 + 64;         // [64]
+    float* sB3 = sB2 + 64;         // [16]
+    float* sMean = sB3 + 16;       // [64]
+    float* sStd = sMean + 64;      // [64]
+    float* sAct = sStd + 64;       // [128][16]
+    float* sNew = sAct + RTC * OUTP;          // [32][65]
+    float* sFin = sNew + 32 * (KC + 1);       // [32][65]
+    int* sFlag = reinterpret_cast<int*>(sFin + 32 * (KC + 1));   // [128]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int s_last, s_anyfin;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int net = p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y;
+    const int env0 = blockIdx.x * RTC;
+    const int O = p.es.O, A = p.es.A, N = p.N, T = p.T, t = p.t;
+    const NetLayout L = net_layout(net, O, A);
+    const float* theta = p.theta + net_offset(net, O, A);
+    const bool normalize = p.es.obs_normalize && p.ns.count[0] > 1;
+    const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
+    float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
+
+    {   // weights (batched loads)
+        float w1v[16], w2v[16], w3v[4];
+        const int k = tid & 63;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = (tid >> 6) + 4 * j;
+            w1v[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
+            w2v[j] = __ldg(theta + L.off_w2 + n * 64 + k);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = (tid >> 6) + 4 * j;
+            w3v[j] = (o < L.out) ? __ldg(theta + L.off_w3 + o * 64 + k) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = (tid >> 6) + 4 * j;
+            sts(tile_addr(sW1, n, k, 64), tf32r(w1v[j]));
+            sts(tile_addr(sW2, n, k, 64), tf32r(w2v[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts(tile_addr(sW3, (tid >> 6) + 4 * j, k, 16), tf32r(w3v[j]));
+    }
+    if (tid < 64) { sB1[tid] = __ldg(theta + L.off_b1 + tid); sB2[tid] = __ldg(theta + L.off_b2 + tid); }
+    if (tid < 16) sB3[tid] = (tid < L.out) ? __ldg(theta + L.off_b3 + tid) : 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    constexpr uint32_t C_Z = 0, C_OUT = 64;
+    uint32_t phase = 0;
+
+    // normalise `raw` rows of this tile into the X tile (and optionally the obs slab), then run the MLP
+    auto forward = [&](const float* __restrict__ raw, const float* gmean, const float* gstd, bool norm_on,
+                       float* obs_out) {
+        if (tid < 64) { sMean[tid] = (tid < O) ? gmean[tid] : 0.f; sStd[tid] = (tid < O) ? gstd[tid] : 1.f; }
+        __syncthreads();
+        const int k = tid & 63;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float xv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int e = (tid >> 6) + 4 * (16 * half + j);
+                const int env = env0 + e;
+                xv[j] = (env < N && k < O) ? raw[(size_t)env * O + k] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int e = (tid >> 6) + 4 * (16 * half + j);
+                const int env = env0 + e;
+                float v = xv[j];
+                if (env < N && k < O) {
+                    if (norm_on) {
+                        v = __fdiv_rn(__fadd_rn(v, -sMean[k]), sStd[k]);
+                        v = fminf(fmaxf(v, -5.f), 5.f);
+                    }
+                    if (obs_out) obs_out[(size_t)env * O + k] = v;
+                }
+                sts(tile_addr(B0, e, k, RTC), tf32r(v));
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B0, RTC, sW1, 64, 128, 64, 64, false); mma_commit(&bar); }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] + sB1[32 * h + i]);
+            store_row32(B2, 32 * q + lane, 32 * h, RTC, v);
+        }
+        fence_async_smem(); tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B2, RTC, sW2, 64, 128, 64, 64, false); mma_commit(&bar); }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] + sB2[32 * h + i]);
+            store_row32(B0, 32 * q + lane, 32 * h, RTC, v);
+        }
+        fence_async_smem(); tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_OUT, B0, RTC, sW3, 16, 128, 16, 64, false); mma_commit(&bar); }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+    };
+
+    // ---- bootstrap values of paths that ended in the previous step (critic CTAs only) ---------
+    if (net != 0 && t > 0) {
+        if (tid == 0) s_anyfin = 0;
+        __syncthreads();
+        if (tid < RTC && env0 + tid < N) {
+            const unsigned f = p.sl.flags[(size_t)(t - 1) * N + env0 + tid];
+            if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED)) s_anyfin = 1;
+        }
+        __syncthreads();
+        if (s_anyfin) {
+            const bool norm1 = p.es.obs_normalize && p.ns.count[1] > 1;
+            forward(p.st.final_raw + (size_t)((t - 1) & 1) * N * O, p.ns.mean1, p.ns.std1, norm1, nullptr);
+            if (h == 0) {
+                float o16[16];
+                tmem_ld16(tmem + lane_base + C_OUT, o16);
+                const int env = env0 + 32 * q + lane;
+                if (env < N) {
+                    const size_t idx = (size_t)(t - 1) * N + env;
+                    const unsigned f = p.sl.flags[idx];
+                    if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED))
+                        (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = o16[0] + sB3[0];
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+
+    // ---- forward on the current observation -----------------------------------------------------
+    forward(s_cur, p.ns.mean, p.ns.std, normalize, (net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr);
+    if (h == 0) {
+        float o16[16];
+        tmem_ld16(tmem + lane_base + C_OUT, o16);
+        const int e = 32 * q + lane;
+        const int env = env0 + e;
+        if (net != 0) {
+            if (env < N) {
+                const float v = o16[0] + sB3[0];
+                if (!p.is_tail) {
+                    (net == 1 ? p.sl.val_r : p.sl.val_c)[(size_t)t * N + env] = v;
+                } else {
+                    const size_t idx = (size_t)(T - 1) * N + env;
+                    if (p.sl.flags[idx] == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 16; ++a) sAct[e * OUTP + a] = o16[a] + sB3[a];   // mu
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    if (net == 0) {
+        // ---- sample + log-prob: thread -> (env e = 32*g + tid/8, lane qq = tid%8) -------------------
+        const int qq = tid & 7;
+        for (int g = 0; g < RTC / 32; ++g) {
+            const int e = 32 * g + (tid >> 3);
+            const int env = env0 + e;
+            const bool ok = env < N;
+            float lp = 0.f;
+            for (int a = qq; a < A; a += 8) {
+                const float mu = sAct[e * OUTP + a];
+                const float sd = expf(__ldg(theta + L.off_logstd + a));
+                float eps = 0.f;
+                if (ok)
+                    eps = p.eps ? p.eps[(size_t)env * A + a]
+                                : philox_normal(p.noise_seed, p.es.env_id_offset + env, p.global_step, a);
+                const float act = __fadd_rn(mu, __fmul_rn(sd, eps));
+                const float d = __fadd_rn(act, -mu);
+                const float var = __fmul_rn(sd, sd);
+                float term = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
+                term = __fadd_rn(__fadd_rn(term, -logf(sd)), -0.9189385332046727f);
+                lp += term;
+                sAct[e * OUTP + a] = act;
+                if (ok) p.sl.act[((size_t)t * N + env) * A + a] = act;
+            }
+            lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+            lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+            lp += __shfl_xor_sync(0xffffffffu, lp, 4);
+            if (ok && qq == 0) p.sl.logp[(size_t)t * N + env] = lp;
+        }
+        __syncthreads();
+        // ---- env transition, 32 envs at a time (arithmetic identical to rollout_step_kernel) --------
+        for (int g = 0; g < RTC / 32; ++g) {
+            const int er = tid >> 3;            // env within the group
+            const int e = 32 * g + er;
+            const int env = env0 + e;
+            const bool ok = env < N;
+            const uint32_t gid = p.es.env_id_offset + env;
+            int ep_step = 0; uint32_t epi = 0, gstep = 0;
+            if (ok) { ep_step = p.st.ep_step[env]; epi = p.st.episode[env]; gstep = p.st.gstep[env]; }
+            const bool trunc = ok && (ep_step + 1 >= p.es.max_episode_steps);
+            const bool term = ok && p.es.term_threshold != 0u &&
+                              hash4(p.es.seed ^ 0xA5A5A5A5u, gid, gstep, 0xFFFFu) < p.es.term_threshold;
+            const bool fin = term || trunc;
+            float part = 0.f, s0n = 0.f;
+            float* finrow = p.st.final_raw + ((size_t)(t & 1) * N + (ok ? env : 0)) * O;
+            for (int j = qq; j < O; j += 8) {
+                float nv = 0.f, fv = 0.f;
+                if (ok) {
+                    float a = sAct[e * OUTP + (j % A)];
+                    a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
+                    a = fminf(fmaxf(a, -1.f), 1.f);
+                    const float s = s_cur[(size_t)env * O + j];
+                    const float sn = env_next_value(s, a, __ldg(p.st.bias + j));
+                    part = __fadd_rn(part, __fmul_rn(sn, sn));
+                    if (j == 0) s0n = sn;
+                    fv = sn;
+                    nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
+                    s_nxt[(size_t)env * O + j] = nv;
+                    if (fin) finrow[j] = sn;
+                }
+                sNew[er * (KC + 1) + j] = nv;
+                sFin[er * (KC + 1) + j] = fin ? fv : 0.f;
+            }
+            if (qq == 0) sFlag[e] = fin ? 1 : 0;
+            __syncthreads();
+            if (p.es.obs_normalize && tid < O) {
+                long long sx = 0, sxx = 0, fx = 0, fxx = 0;
+                for (int r = 0; r < 32; ++r)
+                    if (env0 + 32 * g + r < N) {
+                        const float v = sNew[r * (KC + 1) + tid];
+                        sx += to_fix(v); sxx += to_fix(__fmul_rn(v, v));
+                        if (sFlag[32 * g + r]) {
+                            const float w = sFin[r * (KC + 1) + tid];
+                            fx += to_fix(w); fxx += to_fix(__fmul_rn(w, w));
+                        }
+                    }
+                atomicAdd((unsigned long long*)(p.ns.acc_all + tid), (unsigned long long)sx);
+                atomicAdd((unsigned long long*)(p.ns.acc_all + O + tid), (unsigned long long)sxx);
+                if (fx != 0 || fxx != 0) {
+                    atomicAdd((unsigned long long*)(p.ns.acc_fin + tid), (unsigned long long)fx);
+                    atomicAdd((unsigned long long*)(p.ns.acc_fin + O + tid), (unsigned long long)fxx);
+                }
+            }
+            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 1));
+            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 2));
+            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 4));
+            if (ok && qq == 0) {
+                const float rew = __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
+                const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
+                const size_t idx = (size_t)t * N + env;
+                p.sl.rew[idx] = rew;
+                p.sl.cost[idx] = cst;
+                p.sl.flags[idx] = (uint8_t)((term ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
+                const float erv = __fadd_rn(p.st.ep_ret[env], rew);
+                const float ecv = __fadd_rn(p.st.ep_cost[env], cst);
+                const int el = p.st.ep_len[env] + 1;
+                if (fin) {
+                    const size_t TN = (size_t)T * N;
+                    p.sl.epfin[idx] = erv;
+                    p.sl.epfin[TN + idx] = ecv;
+                    p.sl.epfin[2 * TN + idx] = (float)el;
+                    p.st.ep_ret[env] = 0.f; p.st.ep_cost[env] = 0.f; p.st.ep_len[env] = 0;
+                    p.st.episode[env] = epi + 1u;
+                    p.st.ep_step[env] = 0;
+                } else {
+                    p.st.ep_ret[env] = erv; p.st.ep_cost[env] = ecv; p.st.ep_len[env] = el;
+                    p.st.ep_step[env] = ep_step + 1;
+                }
+                p.st.gstep[env] = gstep + 1u;
+            }
+            __syncthreads();
+        }
+        if (p.es.obs_normalize && tid == 0) {
+            int nf = 0;
+            for (int r = 0; r < RTC; ++r) nf += (env0 + r < N) ? sFlag[r] : 0;
+            if (nf) atomicAdd(p.ns.fin_count, nf);
+        }
+    }
+    if (p.es.obs_normalize && !p.is_tail) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.ns.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) norm_finalize(p.ns, O, (long long)N);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+static size_t rollout_tc_smem_bytes() {
+    return 1024 + 2 * RTC * 256 + 2 * 16384 + 4096 +
+           (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * 32 * (KC + 1)) * sizeof(float) + RTC * sizeof(int) + 64;
+}
+
 // Window of the last <= W finished episodes in (step, env) append order: Logger deque semantics
 // (common/logger.py:L253-282 with window_lens; adapter/onpolicy_adapter.py:L159-175).
 // ring[3][W] holds (EpRet, EpCost, EpLen); meta[0] = number of valid entries, meta[1] = head.
@@ -617,6 +942,18 @@ int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned t
 }
 
 static int launch_step(StepArgs& p, cudaStream_t stream) {
+    if (p.precision == 1 && p.es.O <= 64) {
+        const size_t smem_tc = rollout_tc_smem_bytes();
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+            attr_tc = true;
+        }
+        dim3 grid_tc((p.N + RTC - 1) / RTC, p.is_tail ? 2 : 3);
+        rollout_step_tc_kernel<<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
+        OSB_LAUNCH_CHECK();
+        return OSB_OK;
+    }
     const size_t smem = rollout_smem_bytes(p.es.O);
     static size_t attr = 0;
     if (smem > attr) {
@@ -639,7 +976,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
                      float* obs, float* act, float* logp, float* rew, float* cost, float* val_r,
                      float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
                      const float* theta, const float* eps, unsigned noise_seed,
-                     unsigned global_step, void* stream) {
+                     unsigned global_step, int precision, void* stream) {
     OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && N > 0 && T > 0, "bad dims (need 0 < A <= 16)");
     OSB_CHECK_ARG(t >= 0 && t <= T, "step index out of range");
     StepArgs p;
@@ -649,7 +986,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
     p.theta = theta; p.eps = eps; p.noise_seed = noise_seed; p.global_step = global_step;
-    p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0;
+    p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0; p.precision = precision;
     return launch_step(p, (cudaStream_t)stream);
 }
 
@@ -664,7 +1001,7 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
                       float* val_c, float* boot_r, float* boot_c, unsigned char* flags, float* epfin,
                       const float* theta, const float* eps_all, unsigned noise_seed,
                       unsigned epoch_index, int W, float* ring, int* meta, double* window_sums,
-                      void* stream) {
+                      int precision, void* stream) {
     OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && N > 0 && T > 0, "bad dims (need 0 < A <= 16)");
     cudaStream_t s = (cudaStream_t)stream;
     int rc = osb_env_reset(O, A, max_episode_steps, seed, term_threshold, env_id_offset,
@@ -679,7 +1016,7 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
     p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
-    p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N;
+    p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N; p.precision = precision;
     for (int t = 0; t <= T; ++t) {
         p.t = t; p.is_tail = (t == T) ? 1 : 0;
         p.eps = (eps_all && t < T) ? eps_all + (size_t)t * N * A : nullptr;

@@ -145,3 +145,41 @@ def test_rollout_philox_fast_mode(cuda):
     np.testing.assert_allclose(sl['logp'], logp, rtol=1e-4, atol=1e-3)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
     assert abs(np.corrcoef(z[0, :, 0], z[1, :, 0])[0, 1]) < 0.05
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('N,T,tmax,term_prob', [(256, 24, 8, 0.0), (200, 20, 6, 0.05)])
+def test_rollout_tensor_core_mode(cuda, N, T, tmax, term_prob):
+    """matmul_precision = tf32 (tcgen05 tiles of 128 envs): same trajectory as the oracle up to the
+    TF32 rounding of the three layer GEMMs (tolerance 5e-3 on values / actions, stated here); the
+    env / normaliser / bookkeeping arithmetic is unchanged."""
+    from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
+    from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
+    from omnisafe_b200.models import ConstraintActorCritic
+
+    O, A = 60, 8
+    rng = np.random.default_rng(N + T)
+    theta = oac.init_theta(O, A, seed=3)
+    eps = rng.standard_normal((T, N, A)).astype(np.float32)
+    cfgs = _cfgs(True, 16, obs_dim=O, act_dim=A, max_episode_steps=tmax, term_prob=term_prob)
+    ad = OnPolicyAdapter('SyntheticBox-v0', N, 9, cfgs, device=cuda)
+    ad.precision = 1
+    agent = ConstraintActorCritic(O, A, _model_cfgs(), epochs=1, device=cuda)
+    agent.load_flat(theta)
+    buf = VectorOnPolicyBuffer(O, A, T, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=N, device=cuda)
+    ad.rollout(T, agent, buf, eps=torch.as_tensor(eps).to(cuda))
+    torch.cuda.synchronize()
+    sl = {k: v.cpu().numpy() for k, v in buf.data.items() if v is not None}
+    ref = orollout.rollout_epoch(OEnv(N, O, A, max_episode_steps=tmax, seed=9, term_prob=term_prob),
+                                 ONormalizer((O,)), theta, T, eps)
+    assert np.array_equal(sl['flags'], ref['flags'])
+    tol = dict(rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(sl['obs'], ref['obs'], **tol)
+    np.testing.assert_allclose(sl['act'], ref['act'], **tol)
+    np.testing.assert_allclose(sl['value_r'], ref['val_r'], **tol)
+    np.testing.assert_allclose(sl['value_c'], ref['val_c'], **tol)
+    np.testing.assert_allclose(sl['reward'], ref['rew'], **tol)
+    np.testing.assert_allclose(sl['logp'], ref['logp'], rtol=5e-3, atol=2e-2)
+    assert (sl['cost'] != ref['cost']).mean() < 5e-3
+    need = ((ref['flags'] != 0) | (np.arange(T)[:, None] == T - 1)) & ((ref['flags'] & 1) == 0)
+    np.testing.assert_allclose(sl['boot_r'][need], ref['boot_r'][need], **tol)
