@@ -231,6 +231,8 @@ int osb_nccl_destroy(void* comm);
  * One tcgen05 (kind::tf32, TMEM accumulator) GEMM D = A * B^T on a single CTA with every operand
  * major combination; out[128][N] is the raw TMEM dump.  Pins the descriptor / swizzle conventions
  * the tensor-core MLP tiles rely on (tests/test_umma_gpu.py). */
+/* cycles for `reps` back-to-back M x N x 8 tf32 MMAs: out[0] issue->completion, out[1] issue loop. */
+int osb_umma_timing(int M, int N, int reps, long long* out, void* stream);
 int osb_umma_selftest(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn,
                       float* out, void* stream);
 

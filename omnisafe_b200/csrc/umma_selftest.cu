@@ -71,7 +71,48 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
+// timing probe: `reps` back-to-back MMAs of shape M x N x 8 (tf32) issued by one thread, then commit +
+// mbarrier wait; out[0] = cycles from first issue to completion, out[1] = cycles of the issue loop.
+__global__ void __launch_bounds__(128, 1) umma_timing_kernel(int M, int N, int reps, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t pad = (1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u;
+    const uint32_t sA = umma::smem_u32(smem_raw) + pad, sB = sA + 32768;
+    for (int i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<float*>(smem_raw + pad)[i] = 1.0f;
+    if (threadIdx.x == 0) { umma::mbar_init(&bar, 1); umma::mbar_init_fence(); }
+    if (threadIdx.x < 32) umma::tmem_alloc(&tmem_slot, 256);
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t id = umma::idesc_tf32(M, N, 0, 0);
+        t0 = clock64();
+        for (int r = 0; r < reps; ++r)
+            umma::mma_tf32(tmem, umma::desc_kmajor(sA + (uint32_t)(r & 3) * 32u), umma::desc_kmajor(sB + (uint32_t)(r & 3) * 32u), id, r > 0);
+        umma::mma_commit(&bar);
+        t1 = clock64();
+    }
+    umma::mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) { t2 = clock64(); out[0] = t2 - t0; out[1] = t1 - t0; }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace osb
+
+extern "C" int osb_umma_timing(int M, int N, int reps, long long* out, void* stream) {
+    OSB_CHECK_ARG(out && (M == 64 || M == 128) && N % 16 == 0 && N <= 256 && reps > 0, "bad argument");
+    const size_t smem = 1024 + 65536;
+    OSB_CUDA(cudaFuncSetAttribute(osb::umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    osb::umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(M, N, reps, out);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
 
 extern "C" int osb_umma_selftest(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn,
                                  float* out, void* stream) {

@@ -68,9 +68,30 @@ __device__ __forceinline__ unsigned long long tc_feistel(unsigned long long k, u
 }
 
 // TMEM column map
-constexpr uint32_t C_Z = 0, C_ZT = 64, C_OUT = 192, C_DW2 = 224, C_DW1 = 288, TMEM_COLS = 512;
+constexpr uint32_t C_Z = 0, C_ZT = 64, C_OUT = 192, C_DW2 = 224, C_DW1 = 288, C_DW3 = 352, TMEM_COLS = 512;
+constexpr int NTC = 512;   // 16 warps: lane quarter q = warp % 4, column group h = warp / 4 (0..3)
 
-__global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p) {
+// 16-column variants of the row accessors (c0 % 16 == 0)
+__device__ __forceinline__ void store_row16(uint32_t base, int r, int c0, int R, const float (&v)[16]) {
+    const uint32_t row = base + (uint32_t)((c0 >> 5) * R * 128 + r * 128);
+    const int ch0 = (c0 & 31) >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t)(((ch0 + i) ^ (r & 7)) << 4)),
+                     "f"(tf32r(v[4 * i])), "f"(tf32r(v[4 * i + 1])), "f"(tf32r(v[4 * i + 2])), "f"(tf32r(v[4 * i + 3]))
+                     : "memory");
+}
+__device__ __forceinline__ void load_row16(uint32_t base, int r, int c0, int R, float (&v)[16]) {
+    const uint32_t row = base + (uint32_t)((c0 >> 5) * R * 128 + r * 128);
+    const int ch0 = (c0 & 31) >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                     : "r"(row + (uint32_t)(((ch0 + i) ^ (r & 7)) << 4)));
+}
+
+__global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     if (p.stop_flag && *p.stop_flag) return;
     const int net = blockIdx.y;
     if (!((p.net_mask >> net) & 1)) return;
@@ -92,13 +113,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
     float* sB3 = sB2 + 64;            // [16]
     float* sLs = sB3 + 16;            // logstd[16], sigma[16], dlogstd acc[16]
     float* sStat = sLs + 48;          // [8]
-    float* sRed = sStat + 8;          // [16 + 4 * 16]
-    long long* sRow = reinterpret_cast<long long*>(sRed + 80);   // [128]
+    float* sRed = sStat + 8;          // [16 + 4 * 16 + 4 * 16]
+    float* sB3acc = sRed + 144;       // [16]
+    long long* sRow = reinterpret_cast<long long*>(sB3acc + 16);   // [128]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, h = warp >> 2;           // h in [0, 4)
     const int O = p.O, A = p.A;
     const NetLayout L = net_layout(net, O, A);
     const int noff = net_offset(net, O, A);
@@ -109,36 +131,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
 
     // ---- weights -> swizzled K-major tiles (loads batched so they are all in flight together) ----
     {
-        float w1v[16], w2v[16], w3v[4];
+        float w1v[8], w2v[8], w3v[2];
         const int k = tid & 63;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = (tid >> 6) + 4 * j;
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
             w1v[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
             w2v[j] = __ldg(theta + L.off_w2 + n * 64 + k);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = (tid >> 6) + 4 * j;
+        for (int j = 0; j < 2; ++j) {
+            const int o = (tid >> 6) + 8 * j;
             w3v[j] = (o < L.out) ? __ldg(theta + L.off_w3 + o * 64 + k) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = (tid >> 6) + 4 * j;
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
             sts(tile_addr(sW1, n, k, 64), tf32r(w1v[j]));
             const float w2 = tf32r(w2v[j]);
             sts(tile_addr(sW2, n, k, 64), w2);
             sts(tile_addr(sW2T, k, n, 64), w2);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = (tid >> 6) + 4 * j;
+        for (int j = 0; j < 2; ++j) {
+            const int o = (tid >> 6) + 8 * j;
             const float w = tf32r(w3v[j]);
             sts(tile_addr(sW3, o, k, 16), w);
             sts(tile_addr(sW3T, k, o, 64), w);
         }
     }
-    for (int i = tid; i < 64 * 16; i += NTHREADS) sts(tile_addr(sW3T, i >> 4, 16 + (i & 15), 64), 0.f);
+    for (int i = tid; i < 64 * 16; i += NTC) sts(tile_addr(sW3T, i >> 4, 16 + (i & 15), 64), 0.f);
     if (tid < 64) { sB1[tid] = __ldg(theta + L.off_b1 + tid); sB2[tid] = __ldg(theta + L.off_b2 + tid); }
     if (tid < 16) {
         sB3[tid] = (tid < L.out) ? __ldg(theta + L.off_b3 + tid) : 0.f;
@@ -146,6 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         sLs[tid] = ls; sLs[16 + tid] = expf(ls); sLs[32 + tid] = 0.f;
     }
     if (tid < 8) sStat[tid] = 0.f;
+    if (tid < 16) sB3acc[tid] = 0.f;
     if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
     if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
@@ -157,12 +180,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
 
     const float lam = (p.lagrange != nullptr) ? __ldg(p.lagrange) : 0.f;
     const float m_r = __ldg(p.b.moments + 0), s_r = __ldg(p.b.moments + 1), m_c = __ldg(p.b.moments + 2);
-    float aw3[4] = {0.f, 0.f, 0.f, 0.f};
-    float ab1 = 0.f, ab2 = 0.f, ab3 = 0.f;
+    float ab1 = 0.f, ab2 = 0.f;
     bool first_tile = true;
-
-    const uint32_t aB0 = B0, aB1 = B1, aB2 = B2, aB3 = B3, aB4 = B4;
-    const uint32_t aW1 = sW1, aW2 = sW2, aW2T = sW2T, aW3 = sW3, aW3T = sW3T;
+    const int s_row = 32 * q + lane;       // sample row of this thread in [s][.] accumulators
+    const int t_row = 16 * q + lane;       // row (valid for lane < 16) in [64][.] accumulators
+    const int c16 = 16 * h;                // 16-column group of the plain epilogues
+    const int c32 = 32 * h;                // 32-column group of the transposed epilogues
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- P0: gather X and X^T --------------------------------------------------------------
@@ -176,24 +199,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
             sRow[tid] = row;
         }
         __syncthreads();
-        {
+        if ((O & 3) == 0) {   // rows are 16 B aligned: 128-bit gathers, one swizzled 16 B chunk per load
+            const int kq = tid & 15, k4 = kq << 2;
+            float4 xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long row = sRow[(tid >> 4) + 32 * j];
+                xv[j] = (row >= 0 && k4 < O) ? __ldg(reinterpret_cast<const float4*>(p.b.obs + row * O + k4))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = (tid >> 4) + 32 * j;
+                const float4 v = make_float4(tf32r(xv[j].x), tf32r(xv[j].y), tf32r(xv[j].z), tf32r(xv[j].w));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, m, k4, TT)), "f"(v.x),
+                             "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+                sts(tile_addr(B1, k4 + 0, m, 64), v.x);
+                sts(tile_addr(B1, k4 + 1, m, 64), v.y);
+                sts(tile_addr(B1, k4 + 2, m, 64), v.z);
+                sts(tile_addr(B1, k4 + 3, m, 64), v.w);
+            }
+        } else {
             const int k = tid & 63;
+            float xv[16];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float xv[16];
+            for (int j = 0; j < 16; ++j) {
+                const long long row = sRow[(tid >> 6) + 8 * j];
+                xv[j] = (row >= 0 && k < O) ? __ldg(p.b.obs + row * O + k) : 0.f;
+            }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int m = (tid >> 6) + 4 * (16 * half + j);
-                    const long long row = sRow[m];
-                    xv[j] = (row >= 0 && k < O) ? __ldg(p.b.obs + row * O + k) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int m = (tid >> 6) + 4 * (16 * half + j);
-                    const float v = tf32r(xv[j]);
-                    sts(tile_addr(B0, m, k, TT), v);
-                    sts(tile_addr(B1, k, m, 64), v);
-                }
+            for (int j = 0; j < 16; ++j) {
+                const int m = (tid >> 6) + 8 * j;
+                const float v = tf32r(xv[j]);
+                sts(tile_addr(B0, m, k, TT), v);
+                sts(tile_addr(B1, k, m, 64), v);
             }
         }
         fence_async_smem();
@@ -201,50 +241,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         // ---- P1: Z1 and Z1^T ---------------------------------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_Z, aB0, TT, aW1, 64, 128, 64, 64, false);
-            tc_gemm(tmem + C_ZT, aW1, 64, aB0, TT, 64, 128, 64, false);
+            tc_gemm(tmem + C_Z, B0, TT, sW1, 64, 128, 64, 64, false);
+            tc_gemm(tmem + C_ZT, sW1, 64, B0, TT, 64, 128, 64, false);
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);        // row s = 32q+lane, cols 32h..
-            const int s = 32 * q + lane;
+            float v[16];
+            tmem_ld16(tmem + lane_base + C_Z + c16, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] + sB1[32 * h + i]);
-            store_row32(B2, s, 32 * h, TT, v);
-            // transposed: row n = 16q + lane (lane < 16), cols s in [64h, 64h+64)
-            const int n = 16 * q + lane;
+            for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] + sB1[c16 + i]);
+            store_row16(B2, s_row, c16, TT, v);
+            float w[32];
+            tmem_ld32(tmem + lane_base + C_ZT + c32, w);
+            if (lane < 16) {
+                const float bb = sB1[t_row];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem + lane_base + C_ZT + 64 * h + 32 * half, v);
-                if (lane < 16) {
-                    const float bb = sB1[n];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] + bb);
-                    store_row32(B3, n, 64 * h + 32 * half, 64, v);
-                }
+                for (int i = 0; i < 32; ++i) w[i] = tanh_fast(w[i] + bb);
+                store_row32(B3, t_row, c32, 64, w);
             }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        // ---- P2: Z2 -> H2 (into B0; X is dead) ---------------------------------------------------
+        // ---- P2: Z2 -> H2 (into B0; X is dead) and Z2^T -> H2^T (into B2; H1 is dead afterwards) ----
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_Z, aB2, TT, aW2, 64, 128, 64, 64, false);
+            tc_gemm(tmem + C_Z, B2, TT, sW2, 64, 128, 64, 64, false);
+            tc_gemm(tmem + C_ZT, sW2, 64, B2, TT, 64, 128, 64, false);
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);
-            const int s = 32 * q + lane;
+            float v[16];
+            tmem_ld16(tmem + lane_base + C_Z + c16, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i] + sB2[32 * h + i]);
-            store_row32(B0, s, 32 * h, TT, v);
+            for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] + sB2[c16 + i]);
+            store_row16(B0, s_row, c16, TT, v);
+            float w[32];
+            tmem_ld32(tmem + lane_base + C_ZT + c32, w);
+            if (lane < 16) {
+                const float bb = sB2[t_row];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) w[i] = tanh_fast(w[i] + bb);
+                store_row32(B2, t_row, c32, 64, w);              // H2^T [k][s]
+            }
         }
         fence_async_smem();
         tc_fence_before();
@@ -252,13 +295,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         // ---- P3: OUT -> loss -> dOUT (B4, cols 0..31) --------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_OUT, aB0, TT, aW3, 16, 128, 16, 64, false);
+            tc_gemm(tmem + C_OUT, B0, TT, sW3, 16, 128, 16, 64, false);
             mma_commit(&bar);
         }
         // per-sample scalars: issue the global loads before blocking on the MMA
         float pf_act[16], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
+        const long long prow = (h == 0) ? sRow[s_row] : -1;
         {
-            const long long prow = (h == 0) ? sRow[32 * q + lane] : -1;
 #pragma unroll
             for (int a = 0; a < 16; ++a) pf_act[a] = 0.f;
             if (prow >= 0) {
@@ -276,76 +319,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        {
+        if (h == 0) {
             float st[4] = {0.f, 0.f, 0.f, 0.f};
             float dls[16];
 #pragma unroll
             for (int a = 0; a < 16; ++a) dls[a] = 0.f;
-            if (h == 0) {
-                float o16[16];
-                tmem_ld16(tmem + lane_base + C_OUT, o16);
-                const int s = 32 * q + lane;
-                const long long row = sRow[s];
-                float d32[32];
+            float o16[16], d32[32];
+            tmem_ld16(tmem + lane_base + C_OUT, o16);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) d32[i] = 0.f;
-                if (row >= 0) {
-                    if (net != 0) {
-                        const float v = o16[0] + sB3[0];
-                        const float d = v - pf_tv;
-                        st[0] = d * d; st[3] = 1.f;
-                        d32[0] = 2.f * d * inv_b;
-                    } else {
-                        float logp_new = 0.f, diff[16];
+            for (int i = 0; i < 32; ++i) d32[i] = 0.f;
+            if (prow >= 0) {
+                if (net != 0) {
+                    const float d = o16[0] + sB3[0] - pf_tv;
+                    st[0] = d * d; st[3] = 1.f;
+                    d32[0] = 2.f * d * inv_b;
+                } else {
+                    float logp_new = 0.f, diff[16];
 #pragma unroll
-                        for (int a = 0; a < 16; ++a) {
-                            diff[a] = 0.f;
-                            if (a < A) {
-                                const float mu = o16[a] + sB3[a];
-                                const float sd = sLs[16 + a];
-                                const float d = pf_act[a] - mu;
-                                diff[a] = d;
-                                logp_new += -(d * d) / (2.f * sd * sd) - sLs[a] - 0.9189385332046727f;
-                            }
+                    for (int a = 0; a < 16; ++a) {
+                        diff[a] = 0.f;
+                        if (a < A) {
+                            const float sd = sLs[16 + a];
+                            const float d = pf_act[a] - (o16[a] + sB3[a]);
+                            diff[a] = d;
+                            logp_new += -(d * d) / (2.f * sd * sd) - sLs[a] - 0.9189385332046727f;
                         }
-                        const float ratio = expf(logp_new - pf_logp);
-                        const float adv_r = (pf_advr - m_r) / s_r;
-                        const float adv_c = pf_advc - m_c;
-                        const float adv = (adv_r - lam * adv_c) / (1.f + lam);
-                        float dlogp, loss;
-                        if (p.kind == TC_PPO_CLIP) {
-                            const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
-                            const float s1 = ratio * adv, s2 = rc * adv;
-                            loss = -fminf(s1, s2);
-                            dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
-                        } else if (p.kind == TC_RATIO) {
-                            loss = -ratio * adv; dlogp = -adv * ratio * inv_b;
-                        } else {
-                            loss = ratio * adv_c; dlogp = adv_c * ratio * inv_b;
-                        }
-                        st[0] = loss; st[1] = ratio; st[3] = 1.f;
-#pragma unroll
-                        for (int a = 0; a < 16; ++a)
-                            if (a < A) {
-                                const float sd = sLs[16 + a];
-                                const float iv = 1.f / (sd * sd);
-                                d32[a] = dlogp * diff[a] * iv;
-                                dls[a] = dlogp * (diff[a] * diff[a] * iv - 1.f);
-                            }
                     }
+                    const float ratio = expf(logp_new - pf_logp);
+                    const float adv_r = (pf_advr - m_r) / s_r;
+                    const float adv_c = pf_advc - m_c;
+                    const float adv = (adv_r - lam * adv_c) / (1.f + lam);
+                    float dlogp, loss;
+                    if (p.kind == TC_PPO_CLIP) {
+                        const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
+                        const float s1 = ratio * adv, s2 = rc * adv;
+                        loss = -fminf(s1, s2);
+                        dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
+                    } else if (p.kind == TC_RATIO) {
+                        loss = -ratio * adv; dlogp = -adv * ratio * inv_b;
+                    } else {
+                        loss = ratio * adv_c; dlogp = adv_c * ratio * inv_b;
+                    }
+                    st[0] = loss; st[1] = ratio; st[3] = 1.f;
+#pragma unroll
+                    for (int a = 0; a < 16; ++a)
+                        if (a < A) {
+                            const float sd = sLs[16 + a];
+                            const float iv = 1.f / (sd * sd);
+                            d32[a] = dlogp * diff[a] * iv;
+                            dls[a] = dlogp * (diff[a] * diff[a] * iv - 1.f);
+                        }
                 }
-                store_row32(B4, s, 0, TT, d32);
             }
-            // deterministic reductions over the 128 sample threads (warps 0..3)
+            store_row32(B4, s_row, 0, TT, d32);
+#pragma unroll
+            for (int o = 0; o < 16; ++o) sts(tile_addr(B4 + 16384u, o, s_row, 16), tf32r(d32[o]));   // dOUT^T [o][s]
+            // deterministic reductions over the 128 sample threads (warps with h == 0)
 #pragma unroll
             for (int i = 0; i < 4; ++i) st[i] = warp_sum(st[i]);
+            if (net == 0) {
 #pragma unroll
-            for (int a = 0; a < 16; ++a) dls[a] = warp_sum(dls[a]);
-            if (h == 0 && lane == 0) {
+                for (int a = 0; a < 16; ++a) dls[a] = warp_sum(dls[a]);
+            }
+            float db[16];   // db3[o] = sum_s dOUT[s][o]
+#pragma unroll
+            for (int a = 0; a < 16; ++a) db[a] = (a < L.out) ? warp_sum(d32[a]) : 0.f;
+            if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sRed[q * 4 + i] = st[i];
 #pragma unroll
-                for (int a = 0; a < 16; ++a) sRed[16 + q * 16 + a] = dls[a];
+                for (int a = 0; a < 16; ++a) { sRed[16 + q * 16 + a] = dls[a]; sRed[80 + q * 16 + a] = db[a]; }
             }
         }
         fence_async_smem();
@@ -356,66 +399,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
             const int a = tid - 32;
             sLs[32 + a] += sRed[16 + a] + sRed[32 + a] + sRed[48 + a] + sRed[64 + a];
         }
-        // ---- P4: dZ2 and dZ2^T -------------------------------------------------------------------
+        if (tid >= 64 && tid < 64 + L.out) {
+            const int a = tid - 64;
+            sB3acc[a] += sRed[80 + a] + sRed[96 + a] + sRed[112 + a] + sRed[128 + a];
+        }
+        // ---- P4: dZ2, dZ2^T and dW3^T += H2^T dOUT ------------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_Z, aB4, TT, aW3T, 64, 128, 64, 16, false);
-            tc_gemm(tmem + C_ZT, aW3T, 64, aB4, TT, 64, 128, 16, false);
+            tc_gemm(tmem + C_Z, B4, TT, sW3T, 64, 128, 64, 16, false);
+            tc_gemm(tmem + C_ZT, sW3T, 64, B4, TT, 64, 128, 16, false);
+            tc_gemm(tmem + C_DW3, B2, 64, B4 + 16384u, 16, 64, 16, 128, !first_tile);
             mma_commit(&bar);
         }
-        {   // CUDA cores meanwhile: dW3[o][k] += sum_s dOUT[s][o] H2[s][k]; db3
-            const int k = tid & 63, og = tid >> 6;
-            const uint32_t hb = B0 + (uint32_t)((k >> 5) * TT * 128 + ((k & 3) << 2));
-            const uint32_t hc = (uint32_t)((k >> 2) & 7);
-            for (int s0 = 0; s0 < TT; s0 += 8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t rowoff = (uint32_t)((s0 + j) * 128);
-                    const float hv = lds(hb + rowoff + ((hc ^ (uint32_t)j) << 4));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int o = og + 4 * i;
-                        if (o < L.out)
-                            aw3[i] = fmaf(lds(B4 + rowoff + ((((uint32_t)o >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)o & 3) << 2)), hv, aw3[i]);
-                    }
-                }
-            }
-            if (tid < L.out) {
-                float c = 0.f;
-                for (int s0 = 0; s0 < TT; s0 += 8)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        c += lds(B4 + (uint32_t)((s0 + j) * 128) + ((((uint32_t)tid >> 2) ^ (uint32_t)j) << 4) + (((uint32_t)tid & 3) << 2));
-                ab3 += c;
-            }
-        }
-        __syncthreads();           // all CUDA-core reads of dOUT (B4) done before the epilogue overwrites it
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            float v[32], hh[32];
-            tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);
-            const int s = 32 * q + lane;
-            load_row32(B0, s, 32 * h, TT, hh);
+            float w[32], hh[32];
+            tmem_ld32(tmem + lane_base + C_ZT + c32, w);
+            if (lane < 16) {
+                load_row32(B2, t_row, c32, 64, hh);              // H2^T
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= (1.f - hh[i] * hh[i]);
-            store_row32(B2, s, 32 * h, TT, v);                   // dZ2 [s][k]
-            const int k = 16 * q + lane;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem + lane_base + C_ZT + 64 * h + 32 * half, v);
-                if (lane < 16) {
-                    const int s0 = 64 * h + 32 * half;
-                    const uint32_t hb = B0 + (uint32_t)((k >> 5) * TT * 128 + ((k & 3) << 2) + s0 * 128);
-                    const uint32_t hc = (uint32_t)((k >> 2) & 7);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float hv = lds(hb + (uint32_t)(i * 128) + ((hc ^ (uint32_t)(i & 7)) << 4));
-                        v[i] *= (1.f - hv * hv);
-                    }
-                    store_row32(B4, k, s0, 64, v);               // dZ2^T [k][s]
-                }
+                for (int i = 0; i < 32; ++i) w[i] *= (1.f - hh[i] * hh[i]);
+                store_row32(B4, t_row, c32, 64, w);              // dZ2^T [k][s]
             }
+        }
+        __syncthreads();           // every read of H2^T (B2) is done before dZ2 overwrites it
+        {
+            float v[16], hh[16];
+            tmem_ld16(tmem + lane_base + C_Z + c16, v);
+            load_row16(B0, s_row, c16, TT, hh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= (1.f - hh[i] * hh[i]);
+            store_row16(B2, s_row, c16, TT, v);                  // dZ2 [s][k]
         }
         fence_async_smem();
         tc_fence_before();
@@ -423,13 +438,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         // ---- P5: dW2 += dZ2^T H1 ; dZ1^T = W2^T dZ2^T --------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_DW2, aB4, 64, aB3, 64, 64, 64, 128, !first_tile);
-            tc_gemm(tmem + C_ZT, aW2T, 64, aB2, TT, 64, 128, 64, false);
+            tc_gemm(tmem + C_DW2, B4, 64, B3, 64, 64, 64, 128, !first_tile);
+            tc_gemm(tmem + C_ZT, sW2T, 64, B2, TT, 64, 128, 64, false);
             mma_commit(&bar);
         }
         if (tid < 64) {   // db2[j] = sum_s dZ2^T[j][s]
             float c = 0.f, v[32];
-#pragma unroll
+#pragma unroll 1
             for (int a4 = 0; a4 < 4; ++a4) {
                 load_row32(B4, tid, 32 * a4, 64, v);
 #pragma unroll
@@ -440,18 +455,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            float v[32], hh[32];
-            const int k = 16 * q + lane;
+            float w[32], hh[32];
+            tmem_ld32(tmem + lane_base + C_ZT + c32, w);
+            if (lane < 16) {
+                load_row32(B3, t_row, c32, 64, hh);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(tmem + lane_base + C_ZT + 64 * h + 32 * half, v);
-                if (lane < 16) {
-                    const int s0 = 64 * h + 32 * half;
-                    load_row32(B3, k, s0, 64, hh);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= (1.f - hh[i] * hh[i]);
-                    store_row32(B0, k, s0, 64, v);               // dZ1^T [k][s] (H2 is dead)
-                }
+                for (int i = 0; i < 32; ++i) w[i] *= (1.f - hh[i] * hh[i]);
+                store_row32(B0, t_row, c32, 64, w);              // dZ1^T [k][s] (H2 is dead)
             }
         }
         fence_async_smem();
@@ -460,12 +470,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         // ---- P6: dW1 += dZ1^T X --------------------------------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            tc_gemm(tmem + C_DW1, aB0, 64, aB1, 64, 64, 64, 128, !first_tile);
+            tc_gemm(tmem + C_DW1, B0, 64, B1, 64, 64, 64, 128, !first_tile);
             mma_commit(&bar);
         }
         if (tid < 64) {   // db1[j] = sum_s dZ1^T[j][s]
             float c = 0.f, v[32];
-#pragma unroll
+#pragma unroll 1
             for (int a4 = 0; a4 < 4; ++a4) {
                 load_row32(B0, tid, 32 * a4, 64, v);
 #pragma unroll
@@ -479,30 +489,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
         __syncthreads();
     }
 
-    // ---- write this CTA's partial gradient segment ----------------------------------------------
+    // ---- write this CTA's partial gradient segment (staged through smem so that stores coalesce) ----
     {
-        float v[32];
-        const int j = 16 * q + lane;
-        tmem_ld32(tmem + lane_base + C_DW2 + 32 * h, v);
+        float v[16];
+        float* stage = reinterpret_cast<float*>(smem_raw + pad);            // B0 region: [2][64][65]
+        tmem_ld16(tmem + lane_base + C_DW2 + c16, v);
         if (lane < 16)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gout[L.off_w2 + j * 64 + 32 * h + i] = v[i];
-        tmem_ld32(tmem + lane_base + C_DW1 + 32 * h, v);
+            for (int i = 0; i < 16; ++i) stage[t_row * 65 + c16 + i] = v[i];
+        tmem_ld16(tmem + lane_base + C_DW1 + c16, v);
         if (lane < 16)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int o = 32 * h + i;
-                if (o < O) gout[L.off_w1 + j * O + o] = v[i];
-            }
-        const int k = tid & 63, og = tid >> 6;
+            for (int i = 0; i < 16; ++i) stage[64 * 65 + t_row * 65 + c16 + i] = v[i];
+        if (h == 0) {   // dW3^T [k][o] accumulator (M = 64 layout)
+            tmem_ld16(tmem + lane_base + C_DW3, v);
+            if (lane < 16)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int o = og + 4 * i;
-            if (o < L.out) gout[L.off_w3 + o * 64 + k] = aw3[i];
+                for (int o = 0; o < 16; ++o) stage[2 * 64 * 65 + o * 65 + t_row] = v[o];
         }
-        if (tid < 64) { gout[L.off_b1 + tid] = ab1; gout[L.off_b2 + tid] = ab2; }
-        if (tid < L.out) gout[L.off_b3 + tid] = ab3;
         __syncthreads();
+        for (int i = tid; i < 64 * 64; i += NTC) gout[L.off_w2 + i] = stage[(i >> 6) * 65 + (i & 63)];
+        for (int i = tid; i < 64 * O; i += NTC) gout[L.off_w1 + i] = stage[64 * 65 + (i / O) * 65 + (i % O)];
+        for (int i = tid; i < L.out * 64; i += NTC) gout[L.off_w3 + i] = stage[2 * 64 * 65 + (i >> 6) * 65 + (i & 63)];
+        if (tid < 64) { gout[L.off_b1 + tid] = ab1; gout[L.off_b2 + tid] = ab2; }
+        if (tid < L.out) gout[L.off_b3 + tid] = sB3acc[tid];
         if (net == 0 && tid < A) {
             float g = sLs[32 + tid];
             if (blockIdx.x == 0 && p.kind == TC_PPO_CLIP) g -= p.entropy_coef / (float)A;
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_tc_kernel(TcArgs p
 using namespace osb;
 
 static size_t tc_smem_bytes() {
-    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 80) * 4 + 128 * 8 + 64;
+    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 160) * 4 + 128 * 8 + 64;
 }
 
 extern "C" {
@@ -551,7 +561,7 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
         attr = true;
     }
     dim3 grid(osb_update_grid_blocks(mb_count), 3);
-    minibatch_grad_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
+    minibatch_grad_tc_kernel<<<grid, NTC, smem, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
