@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
 // staged as 128B-swizzled K-major smem tiles.  Everything around the GEMMs (ObsNormalize, sampling,
 // env transition, slab append, normaliser sums, ticket) is the arithmetic of rollout_step_kernel.
 constexpr int RTC = 128;
+constexpr int SNW = KC + 1;   // row stride of the next-state staging tiles
 
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p) {
     using namespace umma;
@@ -509,11 +510,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     float* sB2 = sB1 + 64;         // [64]
     float* sB3 = sB2 + 64;         // [16]
     float* sMean = sB3 + 16;       // [64]
-    float* sStd = sMean + 64;      // [64]
-    float* sAct = sStd + 64;       // [128][16]
-    float* sNew = sAct + RTC * OUTP;          // [32][65]
-    float* sFin = sNew + 32 * (KC + 1);       // [32][65]
-    int* sFlag = reinterpret_cast<int*>(sFin + 32 * (KC + 1));   // [128]
+    float* sRstd = sMean + 64;     // [64]  1 / std
+    float* sAct = sRstd + 64;      // [128][16]
+    float* sNew = sAct + RTC * OUTP;           // [128][65] next observation (post reset)
+    float* sFin = sNew + RTC * SNW;            // [128][65] final observation of finished envs
+    long long* sAcc = reinterpret_cast<long long*>(sFin + RTC * SNW);   // [4][4][64] partial fixed-point sums
+    int* sFlag = reinterpret_cast<int*>(sAcc + 4 * 4 * 64);             // [128]
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ int s_last, s_anyfin;
@@ -528,6 +530,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     const bool normalize = p.es.obs_normalize && p.ns.count[0] > 1;
     const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
     float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
+
+    // env bookkeeping scalars of "my" env (actor CTAs: 2 threads per env), prefetched early
+    const int e_env = tid >> 1, e_half = tid & 1;
+    const int my_env = env0 + e_env;
+    const bool my_ok = (net == 0) && my_env < N;
+    int ep_step = 0; uint32_t epi = 0, gstep = 0;
+    if (my_ok) { ep_step = p.st.ep_step[my_env]; epi = p.st.episode[my_env]; gstep = p.st.gstep[my_env]; }
 
     {   // weights (batched loads)
         float w1v[16], w2v[16], w3v[4];
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     }
     if (tid < 64) { sB1[tid] = __ldg(theta + L.off_b1 + tid); sB2[tid] = __ldg(theta + L.off_b2 + tid); }
     if (tid < 16) sB3[tid] = (tid < L.out) ? __ldg(theta + L.off_b3 + tid) : 0.f;
-    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); s_anyfin = 0; }
     if (warp == 0) tmem_alloc(&tmem_slot, 128);
     tc_fence_before();
     __syncthreads();
@@ -564,31 +573,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     constexpr uint32_t C_Z = 0, C_OUT = 64;
     uint32_t phase = 0;
 
-    // normalise `raw` rows of this tile into the X tile (and optionally the obs slab), then run the MLP
-    auto forward = [&](const float* __restrict__ raw, const float* gmean, const float* gstd, bool norm_on,
-                       float* obs_out) {
-        if (tid < 64) { sMean[tid] = (tid < O) ? gmean[tid] : 0.f; sStd[tid] = (tid < O) ? gstd[tid] : 1.f; }
+    // does this critic tile need bootstrap values for paths cut in the previous step?
+    if (net != 0 && t > 0 && tid < RTC && env0 + tid < N) {
+        const unsigned f = p.sl.flags[(size_t)(t - 1) * N + env0 + tid];
+        if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED)) s_anyfin = 1;
+    }
+    __syncthreads();
+    const int first_pass = (net != 0 && t > 0 && s_anyfin) ? 0 : 1;
+
+    // pass 0: final observations of the previous step (critics, rare); pass 1: current observation
+#pragma unroll 1
+    for (int pass = first_pass; pass < 2; ++pass) {
+        const float* raw = pass ? s_cur : p.st.final_raw + (size_t)((t - 1) & 1) * N * O;
+        const float* gmean = pass ? p.ns.mean : p.ns.mean1;
+        const float* gstd = pass ? p.ns.std : p.ns.std1;
+        const bool norm_on = pass ? normalize : (p.es.obs_normalize && p.ns.count[1] > 1);
+        float* obs_out = (pass && net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr;
+        if (tid < 64) { sMean[tid] = (tid < O) ? gmean[tid] : 0.f; sRstd[tid] = (tid < O) ? gstd[tid] : 1.f; }
         __syncthreads();
-        const int k = tid & 63;
+        if ((O & 3) == 0) {   // 128-bit row loads, all 8 in flight per thread
+            const int kq = tid & 15, k4 = kq << 2;
+            float4 xv[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float xv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int e = (tid >> 6) + 4 * (16 * half + j);
-                const int env = env0 + e;
-                xv[j] = (env < N && k < O) ? raw[(size_t)env * O + k] : 0.f;
+            for (int j = 0; j < 8; ++j) {
+                const int env = env0 + (tid >> 4) + 16 * j;
+                xv[j] = (env < N && k4 < O) ? *reinterpret_cast<const float4*>(raw + (size_t)env * O + k4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const float m0 = sMean[k4], m1 = sMean[k4 + 1], m2 = sMean[k4 + 2], m3 = sMean[k4 + 3];
+            const float r0 = sRstd[k4], r1 = sRstd[k4 + 1], r2 = sRstd[k4 + 2], r3 = sRstd[k4 + 3];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int e = (tid >> 6) + 4 * (16 * half + j);
+            for (int j = 0; j < 8; ++j) {
+                const int e = (tid >> 4) + 16 * j;
                 const int env = env0 + e;
-                float v = xv[j];
-                if (env < N && k < O) {
+                float4 v = xv[j];
+                if (env < N && k4 < O) {
                     if (norm_on) {
-                        v = __fdiv_rn(__fadd_rn(v, -sMean[k]), sStd[k]);
-                        v = fminf(fmaxf(v, -5.f), 5.f);
+                        v.x = fminf(fmaxf(__fdiv_rn(__fadd_rn(v.x, -m0), r0), -5.f), 5.f);
+                        v.y = fminf(fmaxf(__fdiv_rn(__fadd_rn(v.y, -m1), r1), -5.f), 5.f);
+                        v.z = fminf(fmaxf(__fdiv_rn(__fadd_rn(v.z, -m2), r2), -5.f), 5.f);
+                        v.w = fminf(fmaxf(__fdiv_rn(__fadd_rn(v.w, -m3), r3), -5.f), 5.f);
                     }
+                    if (obs_out) *reinterpret_cast<float4*>(obs_out + (size_t)env * O + k4) = v;
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, e, k4, RTC)),
+                             "f"(tf32r(v.x)), "f"(tf32r(v.y)), "f"(tf32r(v.z)), "f"(tf32r(v.w))
+                             : "memory");
+            }
+        } else {
+            const int k = tid & 63;
+            const float mk = sMean[k], sk = sRstd[k];
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int e = (tid >> 6) + 4 * j;
+                const int env = env0 + e;
+                float v = 0.f;
+                if (env < N && k < O) {
+                    v = raw[(size_t)env * O + k];
+                    if (norm_on) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v, -mk), sk), -5.f), 5.f);
                     if (obs_out) obs_out[(size_t)env * O + k] = v;
                 }
                 sts(tile_addr(B0, e, k, RTC), tf32r(v));
@@ -623,64 +665,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_OUT, B0, RTC, sW3, 16, 128, 16, 64, false); mma_commit(&bar); }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-    };
-
-    // ---- bootstrap values of paths that ended in the previous step (critic CTAs only) ---------
-    if (net != 0 && t > 0) {
-        if (tid == 0) s_anyfin = 0;
-        __syncthreads();
-        if (tid < RTC && env0 + tid < N) {
-            const unsigned f = p.sl.flags[(size_t)(t - 1) * N + env0 + tid];
-            if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED)) s_anyfin = 1;
-        }
-        __syncthreads();
-        if (s_anyfin) {
-            const bool norm1 = p.es.obs_normalize && p.ns.count[1] > 1;
-            forward(p.st.final_raw + (size_t)((t - 1) & 1) * N * O, p.ns.mean1, p.ns.std1, norm1, nullptr);
-            if (h == 0) {
-                float o16[16];
-                tmem_ld16(tmem + lane_base + C_OUT, o16);
-                const int env = env0 + 32 * q + lane;
+        if (h == 0) {
+            float o16[16];
+            tmem_ld16(tmem + lane_base + C_OUT, o16);
+            const int e = 32 * q + lane;
+            const int env = env0 + e;
+            if (net != 0) {
                 if (env < N) {
-                    const size_t idx = (size_t)(t - 1) * N + env;
-                    const unsigned f = p.sl.flags[idx];
-                    if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED))
-                        (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = o16[0] + sB3[0];
+                    const float v = o16[0] + sB3[0];
+                    if (pass == 0) {
+                        const size_t idx = (size_t)(t - 1) * N + env;
+                        const unsigned f = p.sl.flags[idx];
+                        if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED))
+                            (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
+                    } else if (!p.is_tail) {
+                        (net == 1 ? p.sl.val_r : p.sl.val_c)[(size_t)t * N + env] = v;
+                    } else {
+                        const size_t idx = (size_t)(T - 1) * N + env;
+                        if (p.sl.flags[idx] == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
+                    }
                 }
-            }
-            tc_fence_before();
-            __syncthreads();
-        }
-    }
-
-    // ---- forward on the current observation -----------------------------------------------------
-    forward(s_cur, p.ns.mean, p.ns.std, normalize, (net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr);
-    if (h == 0) {
-        float o16[16];
-        tmem_ld16(tmem + lane_base + C_OUT, o16);
-        const int e = 32 * q + lane;
-        const int env = env0 + e;
-        if (net != 0) {
-            if (env < N) {
-                const float v = o16[0] + sB3[0];
-                if (!p.is_tail) {
-                    (net == 1 ? p.sl.val_r : p.sl.val_c)[(size_t)t * N + env] = v;
-                } else {
-                    const size_t idx = (size_t)(T - 1) * N + env;
-                    if (p.sl.flags[idx] == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
-                }
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int a = 0; a < 16; ++a) sAct[e * OUTP + a] = o16[a] + sB3[a];   // mu
+                for (int a = 0; a < 16; ++a) sAct[e * OUTP + a] = o16[a] + sB3[a];   // mu
+            }
         }
+        tc_fence_before();
+        __syncthreads();
     }
-    tc_fence_before();
-    __syncthreads();
 
     if (net == 0) {
         // ---- sample + log-prob: thread -> (env e = 32*g + tid/8, lane qq = tid%8) -------------------
         const int qq = tid & 7;
+#pragma unroll 1
         for (int g = 0; g < RTC / 32; ++g) {
             const int e = 32 * g + (tid >> 3);
             const int env = env0 + e;
@@ -708,64 +725,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
             if (ok && qq == 0) p.sl.logp[(size_t)t * N + env] = lp;
         }
         __syncthreads();
-        // ---- env transition, 32 envs at a time (arithmetic identical to rollout_step_kernel) --------
-        for (int g = 0; g < RTC / 32; ++g) {
-            const int er = tid >> 3;            // env within the group
-            const int e = 32 * g + er;
-            const int env = env0 + e;
-            const bool ok = env < N;
+        // ---- env transition: all 128 envs at once, 2 threads per env.  Thread `e_half` owns the
+        //      partial sums p_q, q = 4*e_half .. 4*e_half+3 (dims j = q mod 8): the summation tree is the
+        //      one of the spec ((p0+p1)+(p2+p3)) + ((p4+p5)+(p6+p7)). --------------------------------
+        {
+            const int env = my_env;
+            const bool ok = my_ok;
             const uint32_t gid = p.es.env_id_offset + env;
-            int ep_step = 0; uint32_t epi = 0, gstep = 0;
-            if (ok) { ep_step = p.st.ep_step[env]; epi = p.st.episode[env]; gstep = p.st.gstep[env]; }
             const bool trunc = ok && (ep_step + 1 >= p.es.max_episode_steps);
             const bool term = ok && p.es.term_threshold != 0u &&
                               hash4(p.es.seed ^ 0xA5A5A5A5u, gid, gstep, 0xFFFFu) < p.es.term_threshold;
             const bool fin = term || trunc;
-            float part = 0.f, s0n = 0.f;
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            float s0n = 0.f;
             float* finrow = p.st.final_raw + ((size_t)(t & 1) * N + (ok ? env : 0)) * O;
-            for (int j = qq; j < O; j += 8) {
-                float nv = 0.f, fv = 0.f;
-                if (ok) {
-                    float a = sAct[e * OUTP + (j % A)];
-                    a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
-                    a = fminf(fmaxf(a, -1.f), 1.f);
-                    const float s = s_cur[(size_t)env * O + j];
-                    const float sn = env_next_value(s, a, __ldg(p.st.bias + j));
-                    part = __fadd_rn(part, __fmul_rn(sn, sn));
-                    if (j == 0) s0n = sn;
-                    fv = sn;
-                    nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
-                    s_nxt[(size_t)env * O + j] = nv;
-                    if (fin) finrow[j] = sn;
-                }
-                sNew[er * (KC + 1) + j] = nv;
-                sFin[er * (KC + 1) + j] = fin ? fv : 0.f;
-            }
-            if (qq == 0) sFlag[e] = fin ? 1 : 0;
-            __syncthreads();
-            if (p.es.obs_normalize && tid < O) {
-                long long sx = 0, sxx = 0, fx = 0, fxx = 0;
-                for (int r = 0; r < 32; ++r)
-                    if (env0 + 32 * g + r < N) {
-                        const float v = sNew[r * (KC + 1) + tid];
-                        sx += to_fix(v); sxx += to_fix(__fmul_rn(v, v));
-                        if (sFlag[32 * g + r]) {
-                            const float w = sFin[r * (KC + 1) + tid];
-                            fx += to_fix(w); fxx += to_fix(__fmul_rn(w, w));
+#pragma unroll 1
+            for (int jb = 4 * e_half; jb < O; jb += 8) {
+#pragma unroll
+                for (int qi = 0; qi < 4; ++qi) {
+                    const int j = jb + qi;
+                    if (j < O) {
+                        float nv = 0.f, fv = 0.f;
+                        if (ok) {
+                            float a = sAct[e_env * OUTP + (j % A)];
+                            a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
+                            a = fminf(fmaxf(a, -1.f), 1.f);
+                            const float s = s_cur[(size_t)env * O + j];
+                            const float sn = env_next_value(s, a, __ldg(p.st.bias + j));
+                            part[qi] = __fadd_rn(part[qi], __fmul_rn(sn, sn));
+                            if (j == 0) s0n = sn;
+                            fv = sn;
+                            nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
+                            s_nxt[(size_t)env * O + j] = nv;
+                            if (fin) finrow[j] = sn;
                         }
+                        sNew[e_env * SNW + j] = nv;
+                        sFin[e_env * SNW + j] = fin ? fv : 0.f;
                     }
-                atomicAdd((unsigned long long*)(p.ns.acc_all + tid), (unsigned long long)sx);
-                atomicAdd((unsigned long long*)(p.ns.acc_all + O + tid), (unsigned long long)sxx);
-                if (fx != 0 || fxx != 0) {
-                    atomicAdd((unsigned long long*)(p.ns.acc_fin + tid), (unsigned long long)fx);
-                    atomicAdd((unsigned long long*)(p.ns.acc_fin + O + tid), (unsigned long long)fxx);
                 }
             }
-            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 1));
-            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 2));
-            part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 4));
-            if (ok && qq == 0) {
-                const float rew = __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
+            if (e_half == 0) sFlag[e_env] = fin ? 1 : 0;
+            float tot = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
+            tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, 1));
+            if (ok && e_half == 0) {
+                const float rew = __fadd_rn(1.f, -__fdiv_rn(tot, (float)O));
                 const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
                 const size_t idx = (size_t)t * N + env;
                 p.sl.rew[idx] = rew;
@@ -788,12 +791,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 }
                 p.st.gstep[env] = gstep + 1u;
             }
-            __syncthreads();
         }
-        if (p.es.obs_normalize && tid == 0) {
+        __syncthreads();
+        if (p.es.obs_normalize) {
+            // fixed-point column sums over the tile: thread (dim j = tid % 64, env quarter g = tid / 64)
+            const int j = tid & 63, g = tid >> 6;
+            long long sx = 0, sxx = 0, fx = 0, fxx = 0;
             int nf = 0;
-            for (int r = 0; r < RTC; ++r) nf += (env0 + r < N) ? sFlag[r] : 0;
-            if (nf) atomicAdd(p.ns.fin_count, nf);
+            if (j < O) {
+#pragma unroll 4
+                for (int r = 32 * g; r < 32 * g + 32; ++r)
+                    if (env0 + r < N) {
+                        const float v = sNew[r * SNW + j];
+                        sx += to_fix(v); sxx += to_fix(__fmul_rn(v, v));
+                        if (sFlag[r]) {
+                            const float w = sFin[r * SNW + j];
+                            fx += to_fix(w); fxx += to_fix(__fmul_rn(w, w));
+                            ++nf;
+                        }
+                    }
+            }
+            sAcc[(g * 4 + 0) * 64 + j] = sx; sAcc[(g * 4 + 1) * 64 + j] = sxx;
+            sAcc[(g * 4 + 2) * 64 + j] = fx; sAcc[(g * 4 + 3) * 64 + j] = fxx;
+            __syncthreads();
+            if (tid < O) {
+                long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                for (int gg = 0; gg < 4; ++gg) {
+                    a0 += sAcc[(gg * 4 + 0) * 64 + tid]; a1 += sAcc[(gg * 4 + 1) * 64 + tid];
+                    a2 += sAcc[(gg * 4 + 2) * 64 + tid]; a3 += sAcc[(gg * 4 + 3) * 64 + tid];
+                }
+                atomicAdd((unsigned long long*)(p.ns.acc_all + tid), (unsigned long long)a0);
+                atomicAdd((unsigned long long*)(p.ns.acc_all + O + tid), (unsigned long long)a1);
+                if (a2 != 0 || a3 != 0) {
+                    atomicAdd((unsigned long long*)(p.ns.acc_fin + tid), (unsigned long long)a2);
+                    atomicAdd((unsigned long long*)(p.ns.acc_fin + O + tid), (unsigned long long)a3);
+                }
+            }
+            if (tid == 0) {
+                int nfin = 0;
+                for (int r = 0; r < RTC; ++r) nfin += (env0 + r < N) ? sFlag[r] : 0;
+                if (nfin) atomicAdd(p.ns.fin_count, nfin);
+            }
         }
     }
     if (p.es.obs_normalize && !p.is_tail) {
@@ -810,7 +848,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 
 static size_t rollout_tc_smem_bytes() {
     return 1024 + 2 * RTC * 256 + 2 * 16384 + 4096 +
-           (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * 32 * (KC + 1)) * sizeof(float) + RTC * sizeof(int) + 64;
+           (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * RTC * SNW) * sizeof(float) + 4 * 4 * 64 * sizeof(long long) +
+           RTC * sizeof(int) + 64;
 }
 
 // Window of the last <= W finished episodes in (step, env) append order: Logger deque semantics
