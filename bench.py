@@ -112,7 +112,7 @@ def _launches_per_epoch() -> int:
     n_mb = -(-(w['envs_per_gpu'] * T) // w['batch_size'])
     rollout = 1 + (T + 1) + 2            # reset, T steps + bootstrap launch, episode window + sums
     gae = 2 + 1                          # scan + stats reduce, moments
-    update = 1 + 1 + w['update_iters'] * (n_mb * 3 + 3)   # lagrange, old-policy snapshot, (grad, reduce, clip+adam)*mb + (eval, reduce, kl)
+    update = 1 + 1 + w['update_iters'] * (n_mb * 2 + 3)   # lagrange, old-policy snapshot, (fused fwd+bwd, fused reduce+clip+adam)*mb + (eval, reduce, kl)
     return rollout + gae + update
 
 
@@ -223,6 +223,9 @@ def run_b200(args) -> dict:
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(budget_s=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return out if rank == 0 else {}
 
 

@@ -10,21 +10,23 @@
 // Layout: time-major SoA slabs [T][N] (env index contiguous) so that the rollout kernel appends a
 // step with coalesced stores and this kernel reads rows with coalesced 128 B requests.
 //
-// Parallelisation: block = 32 envs (x) x 32 time-chunks (y) x 4 steps per thread.  Every thread
+// Parallelisation: block = 16 envs (x) x 32 time-chunks (y) x 4 steps per thread (512 threads).  Every thread
 // folds its 4 steps into an affine map  A_in -> b + a*A_in  (fp64), the 32 chunk maps of one env are
 // combined with a warp-shuffle suffix scan (after a shared-memory transpose so that lanes run along
 // time), and a second local pass replays the reference's sequential arithmetic
 // (separately rounded fp64 mul/add) from the exact carry-in.  Tiles of 128 steps are walked from
 // the end of the horizon to its start with a per-env carry.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace osb {
 
-constexpr int GE = 32;         // envs per block
+constexpr int GE = 16;         // envs per block
 constexpr int GC = 32;         // chunks per tile
 constexpr int GL = 4;          // steps per chunk
 constexpr int GT = GC * GL;    // steps per tile
 constexpr int GPAD = GE + 1;
+constexpr int GTHREADS = GE * GC;   // 512
 
 struct GaeArgs {
     const float* rew;
@@ -40,6 +42,8 @@ struct GaeArgs {
     float* tv_c;
     float* disc_ret;  // may be null
     double* partials; // [gridDim.x][4]
+    double* sums;     // [4] written by the last block
+    unsigned int* ticket;
     int T, N;
     float gamma_f;    // (float)gamma : fp32 delta arithmetic (onpolicy_buffer.py:L301)
     float pen;        // penalty_coefficient (onpolicy_buffer.py:L185)
@@ -48,66 +52,81 @@ struct GaeArgs {
     double gl_c;      // gamma * lam_c
 };
 
-__global__ void __launch_bounds__(GE* GC, 1) gae_dual_kernel(GaeArgs p) {
-    extern __shared__ double sm[];
-    double* sa = sm;                         // [3][GC][GPAD]
-    double* sb = sm + 3 * GC * GPAD;         // [3][GC][GPAD]
-    double* carry = sm + 6 * GC * GPAD;      // [3][GE]
-    double* red = carry + 3 * GE;            // [3][32]
+struct GaeTile {      // one thread's 4 steps (+ the value after them) of one env
+    float r[GL], c[GL], vr[GL + 1], vc[GL + 1];
+    unsigned f[GL];
+};
 
-    const int x = threadIdx.x, y = threadIdx.y;
+__device__ __forceinline__ void gae_load_tile(const GaeArgs& p, int env, bool env_ok, int t0, GaeTile& d) {
+    const int N = p.N, T = p.T;
+#pragma unroll
+    for (int i = 0; i < GL; ++i) {
+        const int t = t0 + i;
+        const bool ok = env_ok && t >= 0;
+        const size_t idx = (size_t)(ok ? t : 0) * N + (env_ok ? env : 0);
+        d.r[i] = ok ? __ldg(p.rew + idx) : 0.f;
+        d.c[i] = ok ? __ldg(p.cost + idx) : 0.f;
+        d.vr[i] = ok ? __ldg(p.val_r + idx) : 0.f;
+        d.vc[i] = ok ? __ldg(p.val_c + idx) : 0.f;
+        d.f[i] = ok ? (unsigned)__ldg(p.flags + idx) : 0u;
+    }
+    const int t = t0 + GL;
+    const bool ok = env_ok && t >= 0 && t < T;
+    const size_t idx = (size_t)(ok ? t : 0) * N + (env_ok ? env : 0);
+    d.vr[GL] = ok ? __ldg(p.val_r + idx) : 0.f;
+    d.vc[GL] = ok ? __ldg(p.val_c + idx) : 0.f;
+}
+
+// MULTI = more than one 128-step tile: prefetches the next tile (more registers, 1 CTA per SM);
+// the single-tile instantiation fits 64 registers so that two CTAs share an SM.
+template <bool MULTI>
+__global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeArgs p) {
+    __shared__ double sa[3 * GC * GPAD];
+    __shared__ double sb[3 * GC * GPAD];
+    __shared__ double carry[3 * GE];
+    __shared__ double red[3 * (GTHREADS / 32)];
+    __shared__ int s_last;
+
+    const int x = threadIdx.x, y = threadIdx.y;     // env lane (16), time chunk (32)
+    const int lin = y * GE + x;
+    const int tw = lin >> 5, tl = lin & 31;          // transposed role: warp tw <-> env tw, lane tl <-> chunk
     const int env = blockIdx.x * GE + x;
     const bool env_ok = env < p.N;
     const int N = p.N, T = p.T;
     const int ntiles = (T + GT - 1) / GT;
 
-    if (y < 3) carry[y * GE + x] = 0.0;
-    __syncthreads();
+    if (lin < 3 * GE) carry[lin] = 0.0;
 
     double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
+    GaeTile cur;
+    gae_load_tile(p, env, env_ok, T - GT + y * GL, cur);
+    __syncthreads();
 
     for (int k = 0; k < ntiles; ++k) {
         const int t0 = T - (k + 1) * GT + y * GL;  // first step of my chunk (may be < 0)
-        float r[GL], c[GL], vr[GL + 1], vc[GL + 1];
-        unsigned f[GL];
-#pragma unroll
-        for (int i = 0; i < GL; ++i) {
-            const int t = t0 + i;
-            const bool ok = env_ok && t >= 0;
-            const size_t idx = (size_t)(ok ? t : 0) * N + (env_ok ? env : 0);
-            r[i] = ok ? __ldg(p.rew + idx) : 0.f;
-            c[i] = ok ? __ldg(p.cost + idx) : 0.f;
-            vr[i] = ok ? __ldg(p.val_r + idx) : 0.f;
-            vc[i] = ok ? __ldg(p.val_c + idx) : 0.f;
-            f[i] = ok ? (unsigned)__ldg(p.flags + idx) : 0u;
-        }
-        {
-            const int t = t0 + GL;
-            const bool ok = env_ok && t >= 0 && t < T;
-            const size_t idx = (size_t)(ok ? t : 0) * N + (env_ok ? env : 0);
-            vr[GL] = ok ? __ldg(p.val_r + idx) : 0.f;
-            vc[GL] = ok ? __ldg(p.val_c + idx) : 0.f;
-        }
         // fp32 deltas with the reference's three separately rounded ops; bootstrap at path ends.
-        float dr[GL], dc[GL], bootr[GL];
+        float dr[GL], dc[GL], bootr[GL], r[GL], vr[GL], vc[GL];
         bool end[GL], valid[GL];
 #pragma unroll
         for (int i = 0; i < GL; ++i) {
             const int t = t0 + i;
             valid[i] = env_ok && t >= 0;
-            end[i] = valid[i] && (f[i] != 0u || t == T - 1);
-            float nr = vr[i + 1], nc = vc[i + 1];
+            end[i] = valid[i] && (cur.f[i] != 0u || t == T - 1);
+            float nr = cur.vr[i + 1], nc = cur.vc[i + 1];
             if (end[i]) {
-                const bool term = (f[i] & OSB_FLAG_TERMINATED) != 0u;
+                const bool term = (cur.f[i] & OSB_FLAG_TERMINATED) != 0u;
                 const size_t idx = (size_t)t * N + env;
                 nr = term ? 0.f : __ldg(p.boot_r + idx);
                 nc = term ? 0.f : __ldg(p.boot_c + idx);
             }
             bootr[i] = nr;
-            const float rp = __fadd_rn(r[i], -__fmul_rn(p.pen, c[i]));
-            dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -vr[i]);
-            dc[i] = __fadd_rn(__fadd_rn(c[i], __fmul_rn(p.gamma_f, nc)), -vc[i]);
+            const float rp = __fadd_rn(cur.r[i], -__fmul_rn(p.pen, cur.c[i]));
+            dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -cur.vr[i]);
+            dc[i] = __fadd_rn(__fadd_rn(cur.c[i], __fmul_rn(p.gamma_f, nc)), -cur.vc[i]);
+            r[i] = cur.r[i]; vr[i] = cur.vr[i]; vc[i] = cur.vc[i];
         }
+        // prefetch the next (earlier) tile while this one is scanned
+        if (MULTI && k + 1 < ntiles) gae_load_tile(p, env, env_ok, t0 - GT, cur);
         // pass 1: fold the chunk into affine maps (a, b) per quantity.
         double ar = 1.0, br = 0.0, ac = 1.0, bc = 0.0, ag = 1.0, bg = 0.0;
 #pragma unroll
@@ -128,24 +147,24 @@ __global__ void __launch_bounds__(GE* GC, 1) gae_dual_kernel(GaeArgs p) {
         sa[(1 * GC + y) * GPAD + x] = ac; sb[(1 * GC + y) * GPAD + x] = bc;
         sa[(2 * GC + y) * GPAD + x] = ag; sb[(2 * GC + y) * GPAD + x] = bg;
         __syncthreads();
-        // transposed role: this warp owns env y of the block, lane x = chunk index.
+        // transposed role: warp tw owns env tw of the block, lane tl = chunk index.
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            double a = sa[(q * GC + x) * GPAD + y];
-            double b = sb[(q * GC + x) * GPAD + y];
+            double a = sa[(q * GC + tl) * GPAD + tw];
+            double b = sb[(q * GC + tl) * GPAD + tw];
 #pragma unroll
             for (int off = 1; off < GC; off <<= 1) {
                 const double a2 = __shfl_down_sync(0xffffffffu, a, off);
                 const double b2 = __shfl_down_sync(0xffffffffu, b, off);
-                if (x + off < GC) { b = b + a * b2; a = a * a2; }
+                if (tl + off < GC) { b = b + a * b2; a = a * a2; }
             }
-            const double cin = carry[q * GE + y];
-            const double full = b + a * cin;              // value at the first step of chunk x
+            const double cin = carry[q * GE + tw];
+            const double full = b + a * cin;              // value at the first step of chunk tl
             double ain = __shfl_down_sync(0xffffffffu, full, 1);
-            if (x == GC - 1) ain = cin;                   // last chunk takes the tile carry
+            if (tl == GC - 1) ain = cin;                  // last chunk takes the tile carry
             __syncwarp();
-            sb[(q * GC + x) * GPAD + y] = ain;
-            if (x == 0) carry[q * GE + y] = full;
+            sb[(q * GC + tl) * GPAD + tw] = ain;
+            if (tl == 0) carry[q * GE + tw] = full;
         }
         __syncthreads();
         // pass 2: replay sequentially from the exact carry-in with the reference's roundings.
@@ -178,19 +197,33 @@ __global__ void __launch_bounds__(GE* GC, 1) gae_dual_kernel(GaeArgs p) {
         }
         __syncthreads();
     }
-    // epilogue: block partial sums for the advantage statistics (fixed order -> deterministic).
+    // epilogue: block partial sums for the advantage statistics (fixed order -> deterministic);
+    // the last block to finish folds all partials into sums[4].
     st_r = warp_sum(st_r); st_r2 = warp_sum(st_r2); st_c = warp_sum(st_c);
-    if (x == 0) { red[0 * 32 + y] = st_r; red[1 * 32 + y] = st_r2; red[2 * 32 + y] = st_c; }
+    if (tl == 0) { red[0 * 16 + tw] = st_r; red[1 * 16 + tw] = st_r2; red[2 * 16 + tw] = st_c; }
     __syncthreads();
-    if (y == 0) {
-        double a = warp_sum(red[0 * 32 + x]);
-        double b = warp_sum(red[1 * 32 + x]);
-        double c = warp_sum(red[2 * 32 + x]);
-        if (x == 0) {
-            double* o = p.partials + (size_t)blockIdx.x * 4;
-            o[0] = a; o[1] = b; o[2] = c;
-            const int nenv = min(GE, N - blockIdx.x * GE);
-            o[3] = (double)nenv * (double)T;
+    if (lin == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < GTHREADS / 32; ++w) { a += red[w]; b += red[16 + w]; c += red[32 + w]; }
+        double* o = p.partials + (size_t)blockIdx.x * 4;
+        o[0] = a; o[1] = b; o[2] = c;
+        const int nenv = min(GE, N - (int)blockIdx.x * GE);
+        o[3] = (double)nenv * (double)T;
+        __threadfence();
+        s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && lin < 32) {
+        __threadfence();
+        double acc[4] = {0, 0, 0, 0};
+        for (int bb = lin; bb < (int)gridDim.x; bb += 32)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += __ldcg(p.partials + (size_t)bb * 4 + q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+        if (lin == 0) {
+            for (int q = 0; q < 4; ++q) p.sums[q] = acc[q];
+            *p.ticket = 0u;
         }
     }
 }
@@ -275,7 +308,8 @@ using namespace osb;
 
 extern "C" {
 
-int osb_gae_workspace_doubles(int n_envs) { return ((n_envs + GE - 1) / GE) * 4 + 4; }
+// partials [blocks][4] + one 8-byte ticket slot (zero-initialised by the caller, self-resetting)
+int osb_gae_workspace_doubles(int n_envs) { return ((n_envs + GE - 1) / GE) * 4 + 8; }
 
 int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const float* val_c,
                  const uint8_t* flags, const float* boot_r, const float* boot_c, int T, int N,
@@ -294,17 +328,16 @@ int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const 
     a.gamma_f = (float)gamma; a.pen = (float)penalty_coef;
     a.g = gamma; a.gl_r = gamma * lam; a.gl_c = gamma * lam_c;
     const int nblocks = (N + GE - 1) / GE;
-    const size_t smem = (size_t)(6 * GC * GPAD + 3 * GE + 3 * 32) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        OSB_CUDA(cudaFuncSetAttribute(gae_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        attr_set = true;
-    }
+    a.sums = sums;
+    a.ticket = reinterpret_cast<unsigned int*>(workspace + (size_t)nblocks * 4 + 1);
     cudaStream_t s = (cudaStream_t)stream;
-    gae_dual_kernel<<<nblocks, dim3(GE, GC), smem, s>>>(a);
-    OSB_LAUNCH_CHECK();
-    gae_stats_reduce_kernel<<<1, 32, 0, s>>>(workspace, nblocks, sums);
+    // the 64-register instantiation (two CTAs per SM) wins at every T measured on B200: occupancy beats
+    // the register-hungry prefetching variant, which is kept for experiments (OSB_GAE_PREFETCH=1)
+    static const bool prefetch = getenv("OSB_GAE_PREFETCH") != nullptr;
+    if (prefetch && T > GT)
+        gae_dual_kernel<true><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    else
+        gae_dual_kernel<false><<<nblocks, dim3(GE, GC), 0, s>>>(a);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
