@@ -149,9 +149,18 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
     const int pl = blockIdx.x * OT + threadIdx.x;
     const int q = noff + pl;
     float g = 0.f, th = 0.f;
+    int step_t = 0;
     if (active) {
+        step_t = p.r.adam_step[net] + 1;                   // read before the grid barrier, bumped after it
         if (pl < L.size) {
-            for (int b = 0; b < p.r.nblocks; ++b) g += p.r.gpart[(size_t)b * p.r.P + q];
+            // fixed-order reduction with 7 independent accumulators (loads in flight together)
+            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int b = 0;
+            for (; b + 7 <= p.r.nblocks; b += 7)
+#pragma unroll
+                for (int u = 0; u < 7; ++u) acc[u] += p.r.gpart[(size_t)(b + u) * p.r.P + q];
+            for (; b < p.r.nblocks; ++b) acc[0] += p.r.gpart[(size_t)b * p.r.P + q];
+            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + acc[6]);
             th = p.r.theta[q];
             if (net != 0 && p.r.critic_norm_coef > 0.f) g += 2.f * p.r.critic_norm_coef * th;
         }
@@ -170,11 +179,11 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
         float tot = 0.f, t2 = 0.f;
         for (int b = 0; b < (int)gridDim.x; ++b) { tot += p.r.sumsq_part[net * gridDim.x + b]; t2 += p.r.sumsq_part[(3 + net) * gridDim.x + b]; }
         s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
-        const int t = p.r.adam_step[net] + 1;
-        const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+        const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
         s_step = (float)((double)p.lr[net] / bc1);
         s_bc2 = (float)sqrt(bc2);
         if (blockIdx.x == 0) {
+            p.r.adam_step[net] = step_t;                   // every CTA read it before the grid barrier
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int b = 0; b < p.r.nblocks; ++b)
                 for (int i = 0; i < 4; ++i) acc[i] += p.r.stats_part[((size_t)b * 3 + net) * 8 + i];
@@ -197,9 +206,6 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
         p.r.theta[q] = __fadd_rn(th, __fmul_rn(-s_step, __fdiv_rn(m, denom)));
         p.m[q] = m; p.v[q] = v;
     }
-    // every block has read adam_step[net] (before the barrier below) -> block 0 may advance it
-    cg::this_grid().sync();
-    if (active && blockIdx.x == 0 && threadIdx.x == 0) p.r.adam_step[net] += 1;
 }
 
 // lambda <- clamp(Adam(lambda, grad = -(Jc - limit)), 0, upper).  state[4] = {lambda, m, v, t}.
