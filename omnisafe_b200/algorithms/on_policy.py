@@ -257,6 +257,11 @@ class NaturalPG(PolicyGradient):
 
 
 @registry.register
+class RCPO(_LagrangeMixin, NaturalPG):
+    """naive_lagrange/rcpo.py:L25-103 (natural gradient step on the Lagrangian surrogate)."""
+
+
+@registry.register
 class TRPO(NaturalPG):
     """base/trpo.py:L32-222: natural direction + backtracking line search."""
 
@@ -409,4 +414,4 @@ class CPO(TRPO):
             'Misc/q': q, 'Misc/r': r, 'Misc/s': s}
 
 
-ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'TRPO', 'TRPOLag', 'CPO', 'FOCOPS']
+ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'FOCOPS']

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
 
     for (int k = 0; k < ntiles; ++k) {
         const int t0 = T - (k + 1) * GT + y * GL;  // first step of my chunk (may be < 0)
+        if (!MULTI && k > 0) gae_load_tile(p, env, env_ok, t0, cur);   // no prefetch in the 2-CTA/SM variant
         // fp32 deltas with the reference's three separately rounded ops; bootstrap at path ends.
         float dr[GL], dc[GL], bootr[GL], r[GL], vr[GL], vc[GL];
         bool end[GL], valid[GL];

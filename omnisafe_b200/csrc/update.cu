@@ -72,6 +72,7 @@ struct LossCfg {
     float focops_lam, focops_eta;
     const float* lagrange;   // device scalar lambda or null (-> 0): adv = (adv_r - l*adv_c)/(1+l)
     const float* logstd_old; // [A] (FOCOPS), may be null
+    const float* focops_mask_mean;  // device scalar mean_i 1{KL_i <= eta} of this minibatch (FOCOPS pass 2)
 };
 
 // stats slots (per launch, summed over CTAs in fixed order)
@@ -86,6 +87,7 @@ struct GradArgs {
     const int* stop_flag;  // device flag: non-zero -> kernel is a no-op (KL early stop)
     int O, A, P;
     int net_mask;          // bit n set -> process network n
+    int forward_only;      // FOCOPS pass 1: actor forward + statistics only (no gradients written)
 };
 
 __device__ __forceinline__ long long sample_row(const Batch& b, long long k) {
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
 
         // ---- per-sample loss and dL/dOUT (threads < UT), dOUT overwrites sO ---------------------
         {
-            float st[4] = {0.f, 0.f, 0.f, 0.f};        // loss, ratio, kl, count
+            float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // loss, ratio, kl, count, focops mask
             float dls[OUTP];
 #pragma unroll
             for (int a = 0; a < OUTP; ++a) dls[a] = 0.f;
@@ -234,15 +236,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
                     } else if (p.lc.kind == LOSS_COST) {
                         loss = ratio * adv_c;
                         dlogp = adv_c * ratio * inv_b;
-                    } else {  // FOCOPS: (KL(new||old) - ratio*adv/lam) * 1{KL <= eta}
+                    } else {
+                        // FOCOPS.  The reference forms (kl[b,1] - ratio[b]*adv[b]/lam) * mask[b,1] and takes
+                        // the mean of the resulting [b,b] matrix (first_order/focops.py:L85-89), i.e.
+                        //   loss = mean_i(mask_i kl_i) - mean_i(mask_i) * mean_j(ratio_j adv_j) / lam ;
+                        // mean_i(mask_i) of this minibatch comes from the forward-only pass 1.
                         for (int a = 0; a < A; ++a) {
                             const float so = expf(__ldg(p.lc.logstd_old + a)), sn = sLs[OUTP + a];
                             const float dm = sO[m * LDO + a] - __ldg(p.b.mu_old + row * A + a);
                             kl += (__ldg(p.lc.logstd_old + a) - sLs[a]) + (sn * sn + dm * dm) / (2.f * so * so) - 0.5f;
                         }
                         dmask = (kl <= p.lc.focops_eta) ? 1.f : 0.f;
-                        loss = (kl - ratio * adv / p.lc.focops_lam) * dmask;
-                        dlogp = -dmask * adv * ratio / p.lc.focops_lam * inv_b;
+                        const float mbar = p.lc.focops_mask_mean ? __ldg(p.lc.focops_mask_mean) : dmask;
+                        loss = kl * dmask - mbar * ratio * adv / p.lc.focops_lam;
+                        dlogp = -mbar * adv * ratio / p.lc.focops_lam * inv_b;
+                        st[4] = dmask;
                     }
                     st[0] = loss; st[1] = ratio; st[2] = kl; st[3] = 1.f;
 #pragma unroll
@@ -266,10 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
                     for (int a = 0; a < OUTP; ++a) sO[m * LDO + a] = diff[a];
                 }
             }
-            block_reduce_store<4>(st, sRed, sStat, true);
+            block_reduce_store<5>(st, sRed, sStat, true);
             if (net == 0) block_reduce_store<OUTP>(dls, sRed, sLs + 2 * OUTP, true);
         }
         __syncthreads();
+        if (p.forward_only) { first_tile = false; continue; }
 
         // ---- backward ---------------------------------------------------------------------------
         {   // dW3[o][k] += sum_s dOUT[s][o] * H2[s][k];  db3[o] += sum_s dOUT[s][o]
@@ -368,6 +377,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
     }
 
     // ---- write this CTA's partial gradient segment ----------------------------------------------
+    if (p.forward_only) {
+        __syncthreads();
+        if (threadIdx.x < ST_N)
+            p.stats_part[((size_t)blockIdx.x * 3 + net) * ST_N + threadIdx.x] = sStat[threadIdx.x];
+        return;
+    }
     {
         const int j0 = (threadIdx.x >> 4) * 4, k0 = (threadIdx.x & 15) * 4;
 #pragma unroll
@@ -766,6 +781,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fvp_kernel(FvpArgs p) {
     }
 }
 
+// FOCOPS pass 1 -> mean_i mask_i of the minibatch: stats slot 4 / slot 3 of the actor, fixed order.
+__global__ void focops_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
+                                        const int* __restrict__ stop_flag) {
+    if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    float m = 0.f, n = 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * ST_N + 4]; n += stats_part[((size_t)b * 3) * ST_N + 3]; }
+    out[0] = n > 0.f ? m / n : 0.f;
+}
+
 }  // namespace osb
 
 using namespace osb;
@@ -801,13 +825,15 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
                        float entropy_coef, float focops_lam, float focops_eta,
                        const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                        float* stats_part, const int* stop_flag, void* stream) {
+    static float* d_mask_mean = nullptr;   // FOCOPS scratch scalar
     OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
     OSB_CHECK_ARG(O > 0 && A > 0 && A <= OUTP && mb_count > 0 && total > 0, "bad dims");
     OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
     OSB_CHECK_ARG(loss_kind != LOSS_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old/logstd_old");
     GradArgs p;
     p.b = Batch{obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old, moments, perm, total, perm_seed, mb_start, mb_count};
-    p.lc = LossCfg{loss_kind, clip, entropy_coef, focops_lam, focops_eta, lagrange, logstd_old};
+    p.lc = LossCfg{loss_kind, clip, entropy_coef, focops_lam, focops_eta, lagrange, logstd_old, nullptr};
+    p.forward_only = 0;
     p.theta = theta; p.gpart = gpart; p.stats_part = stats_part; p.stop_flag = stop_flag;
     p.O = O; p.A = A;
     p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size;
@@ -819,6 +845,17 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
         attr = true;
     }
     dim3 grid(osb_update_grid_blocks(mb_count), 3);
+    if (loss_kind == LOSS_FOCOPS && (net_mask & 1)) {
+        // pass 1: actor forward only -> mean mask of the minibatch (the reference's [b,1] x [b] broadcast)
+        if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
+        GradArgs q = p;
+        q.forward_only = 1; q.net_mask = 1;
+        minibatch_grad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(q);
+        OSB_LAUNCH_CHECK();
+        focops_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, (int)grid.x, d_mask_mean, stop_flag);
+        OSB_LAUNCH_CHECK();
+        p.lc.focops_mask_mean = d_mask_mean;
+    }
     minibatch_grad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;

@@ -263,6 +263,27 @@ def gen_update_ppolag(algo):
              **{'data_' + k: v for k, v in data.items()})
 
 
+def gen_update_focops():
+    """FOCOPS._update of the unmodified reference (incl. its [b,1] x [b] broadcast in the loss)."""
+    N, T, O, A, seed = 8, 24, 12, 3, 11
+    algo = _build_algo('FOCOPS', N, T, O, A, seed, tmax=8, term_prob=0.05)
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    lam0 = float(algo._lagrange.lagrangian_multiplier.item())
+    Jc = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    np.savez(os.path.join(OUT, 'update_focops.npz'), N=N, T=T, O=O, A=A, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), lam0=lam0,
+             lam1=float(algo._lagrange.lagrangian_multiplier.item()), Jc=Jc, perms=perms, batch_size=32,
+             update_iters=2, cost_limit=25.0, lambda_lr=0.035, upper_bound=2.0, focops_lam=1.5, focops_eta=0.02,
+             kl=_last(lg, 'Train/KL'), stop_iter=_last(lg, 'Train/StopIter'), loss_pi=_last(lg, 'Loss/Loss_pi'),
+             **{'data_' + k: v for k, v in data.items()})
+
+
 def gen_cpo():
     """CPO: Fisher-vector product, CG solve and one full actor+critic update of the reference."""
     from omnisafe.utils.math import conjugate_gradients as ref_cg
@@ -303,5 +324,6 @@ if __name__ == '__main__':
     gen_normalizer()
     algo = gen_rollout()
     gen_update_ppolag(algo)
+    gen_update_focops()
     gen_cpo()
     print('golden fixtures written to', OUT)

@@ -155,3 +155,17 @@ def test_cpo_case_known_answers():
     assert cpo_determine_case(b_dot_b, 1.0, q, r, -1.0, kl)[0] == 1
     assert cpo_determine_case(b_dot_b, 1.0, q, r, 1.0, kl)[0] == 0
     assert cpo_determine_case(1e-8, -1.0, q, r, 1.0, kl)[0] == 4
+
+
+def test_focops_update_golden(golden_dir):
+    """Oracle FOCOPS update (with the reference's [b,1] x [b] broadcast) == unmodified FOCOPS._update."""
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_focops.npz')
+    O, A = int(g['O']), int(g['A'])
+    L = ol.Learner(g['theta0'], O, A)
+    st = L.update_ppo(data, g['perms'][::2], float(g['lam1']), batch_size=int(g['batch_size']),
+                      focops={'lam': float(g['focops_lam']), 'eta': float(g['focops_eta'])})
+    np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(st['loss_pi'], g['loss_pi'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7)

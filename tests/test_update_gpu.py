@@ -211,3 +211,25 @@ def test_fvp_cg_eval_golden(cuda, golden_dir):
                               torch.as_tensor(data['adv_r'])).item()
     np.testing.assert_allclose(ev2['kl'], kl, rtol=1e-3, atol=1e-8)
     np.testing.assert_allclose(ev2['loss_r'], lr_, rtol=1e-4, atol=1e-6)
+
+
+def test_focops_update_epoch_golden(cuda, golden_dir):
+    """FOCOPS on the device (incl. the reference's broadcast quirk, via the forward-only mask pass)
+    vs the unmodified FOCOPS._update: same parameters afterwards."""
+    g = np.load(os.path.join(golden_dir, 'update_focops.npz'))
+    data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, g['theta0'])
+    lag = torch.tensor([float(g['lam1']), 0, 0, 0], dtype=torch.float32, device=cuda)
+    perms = torch.as_tensor(np.stack([_rows(p_, N, T) for p_ in g['perms'][::2]])).to(cuda)
+    eng.ppo_epoch(loss_kind=2, lagrange=lag, net_mask=7, batch_size=int(g['batch_size']),
+                  update_iters=int(g['update_iters']), entropy_coef=0.0, focops_lam=float(g['focops_lam']),
+                  focops_eta=float(g['focops_eta']), critic_norm_coef=0.001, max_grad_norm=40.0, lr_actor=3e-4,
+                  lr_critic=3e-4, target_kl=0.02, kl_early_stop=True, perm=perms)
+    torch.cuda.synchronize()
+    got, want = agent.theta.cpu().numpy(), g['theta1']
+    bad = ~np.isclose(got, want, rtol=2e-4, atol=2e-6)
+    assert bad.mean() < 1e-3 and np.abs(got - want).max() < 2e-3, (bad.sum(), np.abs(got - want).max())
+    np.testing.assert_allclose(float(eng.kl_state[0]), g['kl'][-1], rtol=2e-3, atol=1e-6)
+    ts = eng.train_stats.cpu().numpy().reshape(3, 8)
+    np.testing.assert_allclose(ts[0, 0] / ts[0, 3], g['loss_pi'].mean(), rtol=2e-3, atol=1e-5)
