@@ -183,6 +183,20 @@ int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, in
                     float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
                     float lr_critic_c, int net_mask, float* sumsq_part, float* train_stats,
                     const int* stop_flag, void* stream);
+/* Multi-rank fusion: reduce + clip + one-shot all-reduce over NVLink peer memory + Adam in one
+ * cooperative kernel (reference order clip -> average -> step, policy_gradient.py:L437-443,
+ * utils/distributed.py:L193-198).  Exchange buffers: every rank osb_p2p_alloc()s [2][P] floats and
+ * [2][world] uint32 flags, the 64-byte cudaIpc handles are exchanged by the host, peers
+ * osb_p2p_open() them; peer_buf / peer_flag are DEVICE arrays of `world` pointers.  step_id must
+ * increase by one per call identically on every rank.  error_flag <- 1 on a peer timeout. */
+int osb_p2p_alloc(long long bytes, void** ptr, unsigned char* handle64);
+int osb_p2p_open(const unsigned char* handle64, void** ptr);
+int osb_optim_fused_p2p(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                        float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                        float critic_norm_coef, float max_grad_norm, float lr_actor,
+                        float lr_critic_r, float lr_critic_c, int net_mask, float* sumsq_part,
+                        float* train_stats, const int* stop_flag, void* peer_buf, void* peer_flag,
+                        int world, int rank, unsigned step_id, int* error_flag, void* stream);
 /* Lagrange.update_lagrange_multiplier (common/lagrange.py:L114-136) on the device: Adam step on
  * lambda with grad -(Jc - cost_limit), Jc = window_sums[1]/window_sums[3], clamp to
  * [0, upper_bound] (upper_bound < 0 = none).  state[4] = {lambda, m, v, t}.  nan_flag <- 1 when no
@@ -207,7 +221,9 @@ int osb_axpy(const float* x, const float* y, float alpha, int n, float* out, voi
  * One epoch of PolicyGradient._update (policy_gradient.py:L345-405) issued from C: old-policy
  * snapshot, update_iters passes of minibatch steps (grad -> reduce -> clip -> [all-reduce] ->
  * Adam), full-batch KL after each pass, device-side early stop.  comm = handle from osb_nccl_init
- * (or NULL for a single rank). */
+ * (or NULL for a single rank).  With peer_buf / peer_flag (device arrays of `world_size` cudaIpc-mapped
+ * pointers, see osb_p2p_alloc) the per-step gradient exchange is the fused one-shot NVLink kernel
+ * osb_optim_fused_p2p instead of NCCL; NCCL then only carries the per-pass KL scalar. */
 int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
                          int O, int A, const float* obs, const float* act, const float* logp,
                          const float* adv_r, const float* adv_c, const float* tv_r,
@@ -219,7 +235,8 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                          float lr_critic, float target_kl, int kl_early_stop, float* gpart,
                          float* stats_part, float* sumsq_part, float* train_stats, double* eval_ws,
                          double* eval_out, int* stop_flag, float* kl_state, int precision,
-                         void* comm, int world_size, void* stream);
+                         void* comm, int world_size, void* peer_buf, void* peer_flag, int rank,
+                         int* p2p_error, void* stream);
 /* NCCL via dlopen(libpath) of the libnccl.so.2 torch already loaded (distributed.py:L142-228). */
 int osb_nccl_unique_id(const char* libpath, unsigned char* id128);
 int osb_nccl_init(const char* libpath, const unsigned char* id128, int nranks, int rank,

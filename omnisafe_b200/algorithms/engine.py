@@ -74,7 +74,8 @@ class UpdateEngine:
             ptr(self.gpart), ptr(self.stats_part), ptr(self.sumsq_part), ptr(self.train_stats),
             ptr(self.eval_ws), ptr(self.eval_out), ptr(self.stop_flag), ptr(self.kl_state),
             self.precision if precision is None else int(precision),
-            distributed.nccl_comm(), distributed.world_size(), current_stream())
+            distributed.nccl_comm(), distributed.world_size(), *distributed.p2p_exchange(self.P)[:2],
+            distributed.get_rank(), distributed.p2p_exchange(self.P)[2], current_stream())
 
     # ---- full-batch pieces for the natural-gradient family ---------------------------------
     def snapshot_old_policy(self) -> None:

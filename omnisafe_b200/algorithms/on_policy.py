@@ -119,6 +119,7 @@ class PolicyGradient(BaseAlgo):
 
     def _log_epoch(self, epoch, start, epoch_time, roll) -> None:
         torch.cuda.synchronize()
+        distributed.p2p_check()
         now = time.time()
         ep_ret, ep_cost, ep_len = self._window_means()
         ts = self._engine.train_stats.view(3, 8).tolist()

@@ -47,6 +47,12 @@ int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, in
                     float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
                     float lr_critic_c, int net_mask, float* sumsq_part, float* train_stats,
                     const int* stop_flag, void* stream);
+int osb_optim_fused_p2p(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                        float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                        float critic_norm_coef, float max_grad_norm, float lr_actor,
+                        float lr_critic_r, float lr_critic_c, int net_mask, float* sumsq_part,
+                        float* train_stats, const int* stop_flag, void* peer_buf, void* peer_flag,
+                        int world, int rank, unsigned step_id, int* error_flag, void* stream);
 int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
                  float* kl_state, void* stream);
 }
@@ -150,7 +156,8 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                          float lr_critic, float target_kl, int kl_early_stop, float* gpart,
                          float* stats_part, float* sumsq_part, float* train_stats, double* eval_ws,
                          double* eval_out, int* stop_flag, float* kl_state, int precision,
-                         void* comm, int world_size, void* stream) {
+                         void* comm, int world_size, void* peer_buf, void* peer_flag, int rank,
+                         int* p2p_error, void* stream) {
     OSB_CHECK_ARG(theta && grad && adam_m && adam_v && adam_step && obs && moments, "null pointer");
     OSB_CHECK_ARG(batch_size > 0 && update_iters >= 0 && total > 0 && world_size >= 1, "bad argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -187,7 +194,14 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
                                         focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part,
                                         stop_flag, stream);
             if (rc) return rc;
-            if (!(comm && world_size > 1)) {
+            if (world_size > 1 && peer_buf && peer_flag && p2p_error) {
+                // one cooperative kernel: reduce + clip + one-shot NVLink peer-memory all-reduce + Adam
+                static unsigned p2p_step = 0;
+                rc = osb_optim_fused_p2p(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                                         adam_m, adam_v, adam_step, critic_norm_coef, max_grad_norm, lr_actor,
+                                         lr_critic, lr_critic, net_mask, sumsq_part, train_stats, stop_flag,
+                                         peer_buf, peer_flag, world_size, rank, ++p2p_step, p2p_error, stream);
+            } else if (!(comm && world_size > 1)) {
                 rc = osb_optim_fused(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
                                      adam_m, adam_v, adam_step, critic_norm_coef, max_grad_norm, lr_actor,
                                      lr_critic, lr_critic, net_mask, sumsq_part, train_stats, stop_flag, stream);

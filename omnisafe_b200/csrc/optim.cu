@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "mlp.cuh"
 #include <cooperative_groups.h>
+#include <string.h>
 
 namespace osb {
 
@@ -208,6 +209,126 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
     }
 }
 
+// Multi-rank fast path: partial reduction + clip + ALL-REDUCE + Adam in ONE cooperative kernel.  The
+// all-reduce is a one-shot exchange over NVLink peer memory (cudaIpc-mapped buffers, NVSwitch gives every
+// peer full bandwidth): each rank publishes its clipped flat gradient (99 KB) in its own exchange buffer,
+// raises a step flag in every peer's memory, waits for the peers' flags, then sums the peers' buffers in
+// rank order (deterministic, identical on every rank) straight into the Adam update -- the reference's
+// order clip -> average -> step (policy_gradient.py:L437-443; distributed.py:L193-198 avg_grads).
+struct P2POptArgs {
+    FusedOptArgs f;
+    float* const* peer_buf;        // [world] exchange buffers, each [2][P] (double-buffered by step parity)
+    unsigned int* const* peer_flag; // [world] flag arrays, each [2][world]
+    int world, rank;
+    unsigned int step_id;          // monotonically increasing, identical on all ranks
+    int* error_flag;               // set when a peer does not show up (timeout) instead of hanging the GPU
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(OT) optim_fused_p2p_kernel(P2POptArgs a) {
+    namespace cg = cooperative_groups;
+    const FusedOptArgs& p = a.f;
+    if (p.r.stop_flag && *p.r.stop_flag) return;          // uniform across the grid and across ranks
+    const int net = blockIdx.y;
+    const bool active = ((p.r.net_mask >> net) & 1) != 0;
+    __shared__ float red[OT / 32], red2[OT / 32];
+    __shared__ float s_scale, s_step, s_bc2;
+    const NetLayout L = net_layout(net, p.r.O, p.r.A);
+    const int noff = net_offset(net, p.r.O, p.r.A);
+    const int pl = blockIdx.x * OT + threadIdx.x;
+    const int q = noff + pl;
+    const int par = (int)(a.step_id & 1u);
+    float g = 0.f, th = 0.f;
+    int step_t = 0;
+    if (active) {
+        step_t = p.r.adam_step[net] + 1;
+        if (pl < L.size) {
+            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int b = 0;
+            for (; b + 7 <= p.r.nblocks; b += 7)
+#pragma unroll
+                for (int u = 0; u < 7; ++u) acc[u] += p.r.gpart[(size_t)(b + u) * p.r.P + q];
+            for (; b < p.r.nblocks; ++b) acc[0] += p.r.gpart[(size_t)b * p.r.P + q];
+            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + acc[6]);
+            th = p.r.theta[q];
+            if (net != 0 && p.r.critic_norm_coef > 0.f) g += 2.f * p.r.critic_norm_coef * th;
+        }
+        float s = warp_sum(g * g), s2 = warp_sum(net != 0 ? th * th : 0.f);
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red2[threadIdx.x >> 5] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f, t2 = 0.f;
+            for (int w = 0; w < OT / 32; ++w) { t += red[w]; t2 += red2[w]; }
+            p.r.sumsq_part[net * gridDim.x + blockIdx.x] = t;
+            p.r.sumsq_part[(3 + net) * gridDim.x + blockIdx.x] = t2;
+        }
+    }
+    cg::this_grid().sync();
+    if (active && threadIdx.x == 0) {
+        float tot = 0.f, t2 = 0.f;
+        for (int b = 0; b < (int)gridDim.x; ++b) { tot += p.r.sumsq_part[net * gridDim.x + b]; t2 += p.r.sumsq_part[(3 + net) * gridDim.x + b]; }
+        s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
+        const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
+        s_step = (float)((double)p.lr[net] / bc1);
+        s_bc2 = (float)sqrt(bc2);
+        if (blockIdx.x == 0) {
+            p.r.adam_step[net] = step_t;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int b = 0; b < p.r.nblocks; ++b)
+                for (int i = 0; i < 4; ++i) acc[i] += p.r.stats_part[((size_t)b * 3 + net) * 8 + i];
+            const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
+            float* ts = p.r.train_stats + net * 8;
+            ts[0] += acc[0] * inv + ((net != 0) ? p.r.critic_norm_coef * t2 : 0.f);
+            ts[1] += acc[1] * inv;
+            ts[2] += acc[2] * inv;
+            ts[3] += 1.f;
+        }
+    }
+    __syncthreads();
+    // ---- publish the clipped gradient, exchange flags over NVLink, sum the peers ---------------------
+    float* mine = a.peer_buf[a.rank] + (size_t)par * p.r.P;
+    if (pl < L.size) mine[q] = active ? g * s_scale : 0.f;
+    __threadfence_system();
+    cg::this_grid().sync();
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if ((int)threadIdx.x < a.world)       // tell every peer (and myself) that my buffer for this step is ready
+            st_release_sys(a.peer_flag[threadIdx.x] + par * a.world + a.rank, a.step_id);
+        if ((int)threadIdx.x < a.world) {     // wait until every peer's buffer for this step is ready
+            const unsigned int* f = a.peer_flag[a.rank] + par * a.world + threadIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != a.step_id) {
+                if (clock64() - t0 > 4000000000LL) { *a.error_flag = 1; break; }   // ~2 s: fail instead of hanging
+            }
+        }
+    }
+    cg::this_grid().sync();
+    if (active && pl < L.size) {
+        float sum = 0.f;
+        for (int r = 0; r < a.world; ++r) {
+            const float* pb = a.peer_buf[r] + (size_t)par * p.r.P;
+            float v;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(pb + q) : "memory");
+            sum += v;
+        }
+        const float gavg = sum / (float)a.world;
+        p.r.grad[q] = gavg;
+        float m = p.m[q], v = p.v[q];
+        m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(gavg, -m)));
+        v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, gavg), gavg));
+        const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), s_bc2), 1e-8f);
+        p.r.theta[q] = __fadd_rn(th, __fmul_rn(-s_step, __fdiv_rn(m, denom)));
+        p.m[q] = m; p.v[q] = v;
+    }
+}
+
 // lambda <- clamp(Adam(lambda, grad = -(Jc - limit)), 0, upper).  state[4] = {lambda, m, v, t}.
 // window_sums[4] = {sum EpRet, sum EpCost, sum EpLen, count} (already all-reduced).
 __global__ void lagrange_update_kernel(const double* __restrict__ window_sums, float cost_limit,
@@ -385,6 +506,56 @@ int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, in
     p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
     void* args[] = {&p};
     OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
+                                         (cudaStream_t)stream));
+    return OSB_OK;
+}
+
+// ---- NVLink peer-memory exchange buffers (cudaIpc) -----------------------------------------------------
+int osb_p2p_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+    OSB_CHECK_ARG(bytes > 0 && ptr && handle64, "bad argument");
+    void* d = nullptr;
+    OSB_CUDA(cudaMalloc(&d, (size_t)bytes));
+    OSB_CUDA(cudaMemset(d, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    OSB_CUDA(cudaIpcGetMemHandle(&h, d));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *ptr = d;
+    return OSB_OK;
+}
+
+int osb_p2p_open(const unsigned char* handle64, void** ptr) {
+    OSB_CHECK_ARG(handle64 && ptr, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* d = nullptr;
+    OSB_CUDA(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = d;
+    return OSB_OK;
+}
+
+// grad_reduce + clip + one-shot NVLink all-reduce + Adam in one cooperative launch (multi-rank path).
+// peer_buf / peer_flag: DEVICE arrays of `world` pointers (own entry = own allocation).
+int osb_optim_fused_p2p(const float* gpart, const float* stats_part, int nblocks, int O, int A,
+                        float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step,
+                        float critic_norm_coef, float max_grad_norm, float lr_actor,
+                        float lr_critic_r, float lr_critic_c, int net_mask, float* sumsq_part,
+                        float* train_stats, const int* stop_flag, void* peer_buf, void* peer_flag,
+                        int world, int rank, unsigned step_id, int* error_flag, void* stream) {
+    OSB_CHECK_ARG(gpart && stats_part && theta && grad && adam_m && adam_v && adam_step && sumsq_part && train_stats, "null pointer");
+    OSB_CHECK_ARG(peer_buf && peer_flag && error_flag && world > 1 && world <= OT && rank >= 0 && rank < world, "bad p2p argument");
+    P2POptArgs a;
+    FusedOptArgs& p = a.f;
+    p.r.gpart = gpart; p.r.stats_part = stats_part; p.r.nblocks = nblocks; p.r.O = O; p.r.A = A;
+    p.r.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size;
+    p.r.theta = theta; p.r.grad = grad; p.r.critic_norm_coef = critic_norm_coef; p.r.net_mask = net_mask;
+    p.r.sumsq_part = sumsq_part; p.r.adam_step = adam_step; p.r.train_stats = train_stats; p.r.stop_flag = stop_flag;
+    p.m = adam_m; p.v = adam_v; p.max_grad_norm = max_grad_norm;
+    p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
+    a.peer_buf = (float* const*)peer_buf; a.peer_flag = (unsigned int* const*)peer_flag;
+    a.world = world; a.rank = rank; a.step_id = step_id; a.error_flag = error_flag;
+    void* args[] = {&a};
+    OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_p2p_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
                                          (cudaStream_t)stream));
     return OSB_OK;
 }

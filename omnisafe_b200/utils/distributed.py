@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 _COMM = None  # ctypes.c_void_p of the NCCL communicator used from C
+_P2P = {}     # param count -> (device ptr-array of peer buffers, device ptr-array of peer flags, error flag)
 
 
 def world_size() -> int:
@@ -78,6 +79,48 @@ def _create_nccl_comm():
     comm = ctypes.c_void_p()
     lib().osb_nccl_init(path, uid, dist.get_world_size(), dist.get_rank(), ctypes.byref(comm))
     return comm
+
+
+def p2p_exchange(n_params: int):
+    """NVLink peer-memory exchange buffers for the fused reduce+clip+all-reduce+Adam kernel: every
+    rank allocates [2][P] floats + [2][world] flags with cudaMalloc, the cudaIpc handles travel
+    through torch.distributed, peers map them.  Returns (peer_buf_array_ptr, peer_flag_array_ptr,
+    error_flag_ptr) as ints, or (0, 0, 0) for a single rank / when OSB_NO_P2P is set."""
+    if world_size() == 1 or os.getenv('OSB_NO_P2P'):
+        return 0, 0, 0
+    if n_params in _P2P:
+        bufs, flags, err = _P2P[n_params]
+        return bufs.data_ptr(), flags.data_ptr(), err.data_ptr()
+    from omnisafe_b200._lib import lib  # noqa: PLC0415
+
+    w, r = world_size(), get_rank()
+    ptrs = []
+    for nbytes in (2 * n_params * 4, 2 * w * 4):
+        mine = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        lib().osb_p2p_alloc(nbytes, ctypes.byref(mine), handle)
+        t = torch.tensor(list(handle), dtype=torch.uint8, device='cuda')
+        gathered = [torch.zeros_like(t) for _ in range(w)]
+        dist.all_gather(gathered, t)
+        addr = []
+        for peer in range(w):
+            if peer == r:
+                addr.append(mine.value)
+            else:
+                h = (ctypes.c_ubyte * 64)(*gathered[peer].cpu().tolist())
+                p = ctypes.c_void_p()
+                lib().osb_p2p_open(h, ctypes.byref(p))
+                addr.append(p.value)
+        ptrs.append(torch.tensor(addr, dtype=torch.int64, device='cuda'))
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    dist.barrier()
+    _P2P[n_params] = (ptrs[0], ptrs[1], err)
+    return ptrs[0].data_ptr(), ptrs[1].data_ptr(), err.data_ptr()
+
+
+def p2p_check() -> None:
+    for bufs, flags, err in _P2P.values():
+        assert int(err.item()) == 0, 'NVLink gradient exchange timed out waiting for a peer rank'
 
 
 def all_reduce_(t: torch.Tensor) -> torch.Tensor:

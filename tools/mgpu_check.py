@@ -23,7 +23,7 @@ for algo in ('PPOLag', 'CPO'):
     obs0 = agent.agent._buf.data['obs'][0, 0, :4].clone()
     g = [torch.zeros_like(obs0) for _ in range(w)]; dist.all_gather(g, obs0)
     if dist.get_rank() == 0:
-        print(algo, 'world', w, 'params identical across ranks:', same, 'finite:', bool(torch.isfinite(th).all()),
+        print(algo, 'p2p' if not os.environ.get('OSB_NO_P2P') else 'nccl', 'theta checksum %.9e' % float(th.double().sum()), 'world', w, 'params identical across ranks:', same, 'finite:', bool(torch.isfinite(th).all()),
               'env shards differ:', not torch.equal(g[0], g[1]), 'learn() ->', [round(x, 3) for x in out], flush=True)
     assert same
 dist.barrier()
