@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned long long tc_feistel(unsigned long long k, u
 }
 
 // TMEM column map
-constexpr uint32_t C_Z = 0, C_ZT = 64, C_OUT = 192, C_DW2 = 224, C_DW1 = 288, C_DW3 = 352, TMEM_COLS = 512;
+constexpr uint32_t C_Z = 0, C_ZT = 64, C_ZT2 = 192, C_OUT = 320, C_DW2 = 336, C_DW1 = 400, C_DW3 = 464, TMEM_COLS = 512;
 constexpr int NTC = 512;   // 16 warps: lane quarter q = warp % 4, column group h = warp / 4 (0..3)
 
 // 16-column variants of the row accessors (c0 % 16 == 0)
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     float* sStat = sLs + 48;          // [8]
     float* sRed = sStat + 8;          // [16 + 4 * 16 + 4 * 16]
     float* sB3acc = sRed + 144;       // [16]
-    long long* sRow = reinterpret_cast<long long*>(sB3acc + 16);   // [128]
+    long long* sRowBuf = reinterpret_cast<long long*>(sB3acc + 16);   // [2][128] rows of this / the next tile
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
 
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     const int c16 = 16 * h;                // 16-column group of the plain epilogues
     const int c32 = 32 * h;                // 32-column group of the transposed epilogues
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- P0: gather X and X^T --------------------------------------------------------------
+    const bool vec = (O & 3) == 0;            // rows 16 B aligned: 128-bit gathers, prefetched one tile ahead
+    auto tile_rows = [&](int tile, long long* dst) {
         if (tid < TT) {
             const int local = tile * TT + tid;
             long long row = -1;
@@ -196,22 +196,36 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                 const long long k = p.b.mb_start + local;
                 row = p.b.perm ? (long long)p.b.perm[k] : (long long)tc_feistel((unsigned long long)k, (unsigned long long)p.b.total, p.b.perm_seed);
             }
-            sRow[tid] = row;
+            dst[tid] = row;
         }
-        __syncthreads();
-        if ((O & 3) == 0) {   // rows are 16 B aligned: 128-bit gathers, one swizzled 16 B chunk per load
-            const int kq = tid & 15, k4 = kq << 2;
-            float4 xv[4];
+    };
+    float4 xpre[4];
+    auto prefetch_x = [&](const long long* rows) {
+        const int k4 = (tid & 15) << 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long long row = sRow[(tid >> 4) + 32 * j];
-                xv[j] = (row >= 0 && k4 < O) ? __ldg(reinterpret_cast<const float4*>(p.b.obs + row * O + k4))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int j = 0; j < 4; ++j) {
+            const long long row = rows[(tid >> 4) + 32 * j];
+            xpre[j] = (row >= 0 && k4 < O) ? __ldg(reinterpret_cast<const float4*>(p.b.obs + row * O + k4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int rpar = 0;
+    tile_rows(blockIdx.x, sRowBuf);
+    __syncthreads();
+    if (vec) prefetch_x(sRowBuf);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- P0: X and X^T tiles (data of this tile was prefetched into registers) ---------------
+        long long* sRow = sRowBuf + rpar * TT;
+        long long* sRowNext = sRowBuf + (rpar ^ 1) * TT;
+        const bool has_next = tile + (int)gridDim.x < ntiles;
+        if (has_next) tile_rows(tile + gridDim.x, sRowNext);     // visible after the next barrier
+        if (vec) {
+            const int k4 = (tid & 15) << 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int m = (tid >> 4) + 32 * j;
-                const float4 v = make_float4(tf32r(xv[j].x), tf32r(xv[j].y), tf32r(xv[j].z), tf32r(xv[j].w));
+                const float4 v = make_float4(tf32r(xpre[j].x), tf32r(xpre[j].y), tf32r(xpre[j].z), tf32r(xpre[j].w));
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, m, k4, TT)), "f"(v.x),
                              "f"(v.y), "f"(v.z), "f"(v.w)
                              : "memory");
@@ -247,12 +261,24 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        {
+        {   // plain epilogue only: H1 is all that layer 2 needs
             float v[16];
             tmem_ld16(tmem + lane_base + C_Z + c16, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] + sB1[c16 + i]);
             store_row16(B2, s_row, c16, TT, v);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- P2: Z2 (-> C_Z) and Z2^T (-> C_ZT2); the H1^T epilogue runs while these MMAs execute ----
+        if (tid == 0) {
+            tc_fence_after();
+            tc_gemm(tmem + C_Z, B2, TT, sW2, 64, 128, 64, 64, false);
+            tc_gemm(tmem + C_ZT2, sW2, 64, B2, TT, 64, 128, 64, false);
+            mma_commit(&bar);
+        }
+        {   // deferred: H1^T = tanh(Z1^T + b1) -> B3 (B operand of dW2, needed only in P5)
             float w[32];
             tmem_ld32(tmem + lane_base + C_ZT + c32, w);
             if (lane < 16) {
@@ -262,16 +288,6 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                 store_row32(B3, t_row, c32, 64, w);
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- P2: Z2 -> H2 (into B0; X is dead) and Z2^T -> H2^T (into B2; H1 is dead afterwards) ----
-        if (tid == 0) {
-            tc_fence_after();
-            tc_gemm(tmem + C_Z, B2, TT, sW2, 64, 128, 64, 64, false);
-            tc_gemm(tmem + C_ZT, sW2, 64, B2, TT, 64, 128, 64, false);
-            mma_commit(&bar);
-        }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         {
@@ -279,15 +295,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             tmem_ld16(tmem + lane_base + C_Z + c16, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = tanh_fast(v[i] + sB2[c16 + i]);
-            store_row16(B0, s_row, c16, TT, v);
-            float w[32];
-            tmem_ld32(tmem + lane_base + C_ZT + c32, w);
-            if (lane < 16) {
-                const float bb = sB2[t_row];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) w[i] = tanh_fast(w[i] + bb);
-                store_row32(B2, t_row, c32, 64, w);              // H2^T [k][s]
-            }
+            store_row16(B0, s_row, c16, TT, v);                  // H2 (X is dead)
         }
         fence_async_smem();
         tc_fence_before();
@@ -297,6 +305,16 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             tc_fence_after();
             tc_gemm(tmem + C_OUT, B0, TT, sW3, 16, 128, 16, 64, false);
             mma_commit(&bar);
+        }
+        {   // deferred: H2^T = tanh(Z2^T + b2) -> B2 (H1 is dead: MMA3 / MMA3T completed)
+            float w[32];
+            tmem_ld32(tmem + lane_base + C_ZT2 + c32, w);
+            if (lane < 16) {
+                const float bb = sB2[t_row];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) w[i] = tanh_fast(w[i] + bb);
+                store_row32(B2, t_row, c32, 64, w);
+            }
         }
         // per-sample scalars: issue the global loads before blocking on the MMA
         float pf_act[16], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
@@ -436,6 +454,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         tc_fence_before();
         __syncthreads();
         // ---- P5: dW2 += dZ2^T H1 ; dZ1^T = W2^T dZ2^T --------------------------------------------
+        if (vec && has_next) prefetch_x(sRowNext);    // global loads of the next tile fly during P5 / P6
         if (tid == 0) {
             tc_fence_after();
             tc_gemm(tmem + C_DW2, B4, 64, B3, 64, 64, 64, 128, !first_tile);
@@ -486,6 +505,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         mbar_wait(&bar, phase); phase ^= 1;      // B0 / B1 are rewritten by the next tile's gather
         tc_fence_after();
         first_tile = false;
+        rpar ^= 1;
         __syncthreads();
     }
 
@@ -530,7 +550,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
 using namespace osb;
 
 static size_t tc_smem_bytes() {
-    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 160) * 4 + 128 * 8 + 64;
+    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 160) * 4 + 2 * 128 * 8 + 64;
 }
 
 extern "C" {

@@ -16,6 +16,8 @@ def discount_cumsum(vector_x: torch.Tensor, discount: float) -> torch.Tensor:
         x = x.to(torch.float32)
     rows, length = (1, x.shape[0]) if x.dim() == 1 else (x.shape[0], x.shape[1])
     out = torch.empty(x.shape, dtype=torch.float64, device=x.device)
+    if x.numel() == 0:
+        return out
     lib().osb_discount_cumsum(ptr(x), int(x.dtype == torch.float64), rows, length, float(discount),
                               ptr(out), current_stream())
     return out

@@ -121,3 +121,34 @@ def test_discount_cumsum_known_answers(cuda, golden_dir):
     for i in range(int(g['n'])):
         got = discount_cumsum(torch.as_tensor(g[f'x{i}']).to(cuda), float(g[f'd{i}'])).cpu().numpy()
         np.testing.assert_allclose(got, g[f'y{i}'], rtol=1e-12, atol=1e-12)
+
+
+def test_discount_cumsum_batched_and_empty(cuda):
+    from omnisafe_b200.utils.math import discount_cumsum
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((7, 53))
+    got = discount_cumsum(torch.as_tensor(x).to(cuda), 0.97).cpu().numpy()      # fp64 input, batched rows
+    want = np.stack([ogae.discount_cumsum(r, 0.97) for r in x])
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13)
+    empty = discount_cumsum(torch.zeros(0, dtype=torch.float32, device=cuda), 0.9)
+    assert empty.shape == (0,) and empty.dtype == torch.float64
+    one = discount_cumsum(torch.tensor([3.5], device=cuda), 0.9)
+    assert float(one[0]) == 3.5
+
+
+def test_buffer_argument_checks(cuda):
+    from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
+
+    with pytest.raises(ValueError):
+        VectorOnPolicyBuffer(3, 2, 8, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=0, device=cuda)
+    with pytest.raises(AssertionError):
+        VectorOnPolicyBuffer(3, 2, 8, 0.99, 0.95, 0.95, 'gae', -1.0, True, True, num_envs=2, device=cuda)
+    with pytest.raises(AssertionError):
+        VectorOnPolicyBuffer(3, 2, 8, 0.99, 0.95, 0.95, 'vtrace', 0.0, True, True, num_envs=2, device=cuda)
+    buf = VectorOnPolicyBuffer(3, 2, 8, 0.99, 0.95, 0.95, 'gae', 0.0, False, False, num_envs=2, device=cuda)
+    buf.data['reward'].fill_(1.0)
+    buf.finish_paths(); buf.finalize_statistics()
+    got = buf.get()                      # standardisation off: raw advantages come back
+    assert got['obs'].shape == (16, 3) and got['adv_r'].shape == (16,)
+    np.testing.assert_allclose(got['adv_r'].cpu().numpy().reshape(2, 8), buf.data['adv_r'].cpu().numpy().T)
