@@ -193,8 +193,8 @@ def run_b200(args) -> dict:
     def grad_launch():
         lib().osb_minibatch_grad_tc(ptr(ac.theta), w['obs_dim'], A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
                                     ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']),
-                                    ptr(buf.adv_moments), 0, total, 12345, 0, w['batch_size'], 0, 0.2, 0.0,
-                                    ptr(algo._lagrange.state), 7, ptr(eng.gpart), ptr(eng.stats_part), 0,
+                                    ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 12345, 0, w['batch_size'], 0, 0.2, 0.0,
+                                    1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7, ptr(eng.gpart), ptr(eng.stats_part), 0,
                                     current_stream())
 
     ms_grad = timed(grad_launch, 50) / 50

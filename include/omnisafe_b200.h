@@ -131,15 +131,19 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
                        float* stats_part, const int* stop_flag, void* stream);
 /* Tensor-core variant of osb_minibatch_grad: the tile GEMMs run as tcgen05.mma kind::tf32 with TMEM
  * accumulators (operands fp32 in 128B-swizzled smem tiles; transposed activations produced by
- * role-swapped MMAs).  Same outputs; O <= 64, loss kinds 0 / 1 / 3.  This is arithmetic mode
- * `precision = 1` of osb_ppo_update_epoch; mode 0 is the exact-fp32 FMA parity path. */
+ * role-swapped MMAs).  Same arguments and outputs; O <= 64, A <= 16.  This is arithmetic mode
+ * `precision = 1` of osb_ppo_update_epoch; mode 0 is the exact-fp32 FMA parity path.
+ * gpart / stats_part rows: osb_tc_grid_blocks(mb_count, net_mask) -- 49 CTAs per network when
+ * several networks share the launch, up to 148 when net_mask names a single network. */
+int osb_tc_grid_blocks(long long rows, int net_mask);
 int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
                           const float* logp, const float* adv_r, const float* adv_c,
-                          const float* tv_r, const float* tv_c, const float* moments,
-                          const int* perm, long long total, unsigned perm_seed, long long mb_start,
-                          int mb_count, int loss_kind, float clip, float entropy_coef,
-                          const float* lagrange, int net_mask, float* gpart, float* stats_part,
-                          const int* stop_flag, void* stream);
+                          const float* tv_r, const float* tv_c, const float* mu_old,
+                          const float* moments, const int* perm, long long total, unsigned perm_seed,
+                          long long mb_start, int mb_count, int loss_kind, float clip,
+                          float entropy_coef, float focops_lam, float focops_eta,
+                          const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                          float* stats_part, const int* stop_flag, void* stream);
 /* Full-batch actor pass (KL early stop policy_gradient.py:L383-397; TRPO/CPO line-search
  * evaluations trpo.py:L102-138, cpo.py:L114-171).  mu_store != NULL: write mu(theta) per row.
  * Otherwise out[8] <- {sum_s sum_a KL(old||new), sum ratio*adv, sum ratio*adv_c, sum ratio, count,
@@ -160,6 +164,13 @@ int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, 
 int osb_fvp_grid_blocks(long long total, int stride);
 int osb_fvp_partials(const float* theta_actor, const float* vec, int O, int A, const float* obs,
                      long long total, int stride, float* gpart, void* stream);
+/* Tensor-core Fisher-vector product (O <= 64): forward-mode tangent pass with stacked [W;V] weight
+ * tiles (dmu scratch [total][A]) + the actor backward of the tensor-core gradient kernel.
+ * gpart: osb_tc_grid_blocks(rows, 1) rows of P_actor floats, rows = ceil(total / stride);
+ * stats_scratch: that many * 24 floats.  Reduce with osb_reduce_partials. */
+int osb_fvp_partials_tc(const float* theta_actor, const float* vec, int O, int A, const float* obs,
+                        long long total, int stride, float* dmu, float* gpart, float* stats_scratch,
+                        void* stream);
 
 /* ---- optimiser side --------------------------------------------------------------------------
  * osb_grad_reduce: grad <- sum of CTA partials (+ 2*critic_norm_coef*theta for critics,

@@ -34,6 +34,7 @@ class UpdateEngine:
         self.logstd_old = torch.zeros(self.A, **f32)
         # natural-gradient workspace
         self.fvp_part = torch.zeros(148 * self.Pa, **f32)
+        self.fvp_dmu = torch.zeros(self.total * self.A, **f32)     # tangent of mu per row (tensor-core FVP)
         self.cg_x = torch.zeros(self.Pa, **f32)
         self.cg_r = torch.zeros(self.Pa, **f32)
         self.cg_p = torch.zeros(self.Pa, **f32)
@@ -44,8 +45,11 @@ class UpdateEngine:
         self.precision = 0   # 0 = exact fp32 FMA tiles (parity), 1 = TF32 tcgen05 tiles (fast)
 
     # ---- helpers ----------------------------------------------------------------------------
+    def _tc(self) -> bool:
+        return self.precision == 1 and self.O <= 64
+
     def _eval_fn(self):
-        return lib().osb_actor_eval_tc if (self.precision == 1 and self.O <= 64) else lib().osb_actor_eval
+        return lib().osb_actor_eval_tc if self._tc() else lib().osb_actor_eval
 
     def _batch_ptrs(self):
         d = self.buf.data
@@ -89,12 +93,20 @@ class UpdateEngine:
         """loss.backward() of the full-batch surrogate + avg_grads (natural_pg.py:L150-157):
         out_grad <- sign * d loss / d theta_actor; returns the device scalar `loss` (rank-averaged)."""
         a = self.agent
-        nb = lib().osb_update_grid_blocks(self.total)
-        lib().osb_minibatch_grad(
-            ptr(a.theta), self.O, self.A, *self._batch_ptrs(), ptr(self.mu_old),
-            ptr(self.buf.adv_moments), 0, self.total, 0, 0, self.total, int(loss_kind), 0.0, 0.0, 1.0,
-            0.0, ptr(lagrange), ptr(self.logstd_old), NET_ACTOR, ptr(self.gpart),
-            ptr(self.stats_part), 0, current_stream())
+        if self._tc() and loss_kind in (LOSS_RATIO, LOSS_COST):
+            nb = lib().osb_tc_grid_blocks(self.total, NET_ACTOR)
+            lib().osb_minibatch_grad_tc(
+                ptr(a.theta), self.O, self.A, *self._batch_ptrs(), ptr(self.mu_old), ptr(self.buf.adv_moments),
+                0, self.total, self.next_perm_seed(), 0, self.total, int(loss_kind), 0.0, 0.0, 1.0, 0.0,
+                ptr(lagrange), ptr(self.logstd_old), NET_ACTOR, ptr(self.gpart), ptr(self.stats_part), 0,
+                current_stream())
+        else:
+            nb = lib().osb_update_grid_blocks(self.total)
+            lib().osb_minibatch_grad(
+                ptr(a.theta), self.O, self.A, *self._batch_ptrs(), ptr(self.mu_old),
+                ptr(self.buf.adv_moments), 0, self.total, 0, 0, self.total, int(loss_kind), 0.0, 0.0, 1.0,
+                0.0, ptr(lagrange), ptr(self.logstd_old), NET_ACTOR, ptr(self.gpart),
+                ptr(self.stats_part), 0, current_stream())
         w = distributed.world_size()
         lib().osb_reduce_partials(ptr(self.gpart), nb, self.P, self.Pa, sign / w, 0, 0.0, ptr(out_grad),
                                   current_stream())
@@ -108,9 +120,15 @@ class UpdateEngine:
     def fvp(self, vec: torch.Tensor, out: torch.Tensor, damping: float, stride: int = 1) -> None:
         """NaturalPG._fvp (natural_pg.py:L74-119): out <- avg_ranks(F vec) + damping * vec."""
         a = self.agent
-        nb = lib().osb_fvp_grid_blocks(self.total, stride)
-        lib().osb_fvp_partials(ptr(a.theta), ptr(vec), self.O, self.A, ptr(self.buf.data['obs']),
-                               self.total, stride, ptr(self.fvp_part), current_stream())
+        if self._tc():
+            nb = lib().osb_tc_grid_blocks((self.total + stride - 1) // stride, NET_ACTOR)
+            lib().osb_fvp_partials_tc(ptr(a.theta), ptr(vec), self.O, self.A, ptr(self.buf.data['obs']),
+                                      self.total, stride, ptr(self.fvp_dmu), ptr(self.fvp_part),
+                                      ptr(self.stats_part), current_stream())
+        else:
+            nb = lib().osb_fvp_grid_blocks(self.total, stride)
+            lib().osb_fvp_partials(ptr(a.theta), ptr(vec), self.O, self.A, ptr(self.buf.data['obs']),
+                                   self.total, stride, ptr(self.fvp_part), current_stream())
         w = distributed.world_size()
         if w == 1:
             lib().osb_reduce_partials(ptr(self.fvp_part), nb, self.Pa, self.Pa, 1.0, ptr(vec), float(damping),

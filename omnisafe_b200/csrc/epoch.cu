@@ -8,6 +8,7 @@
 
 extern "C" {
 int osb_update_grid_blocks(int mb_count);
+int osb_tc_grid_blocks(long long rows, int net_mask);
 int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const float* act,
                        const float* logp, const float* adv_r, const float* adv_c,
                        const float* tv_r, const float* tv_c, const float* mu_old,
@@ -18,11 +19,12 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
                        float* stats_part, const int* stop_flag, void* stream);
 int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
                           const float* logp, const float* adv_r, const float* adv_c,
-                          const float* tv_r, const float* tv_c, const float* moments,
-                          const int* perm, long long total, unsigned perm_seed, long long mb_start,
-                          int mb_count, int loss_kind, float clip, float entropy_coef,
-                          const float* lagrange, int net_mask, float* gpart, float* stats_part,
-                          const int* stop_flag, void* stream);
+                          const float* tv_r, const float* tv_c, const float* mu_old,
+                          const float* moments, const int* perm, long long total, unsigned perm_seed,
+                          long long mb_start, int mb_count, int loss_kind, float clip,
+                          float entropy_coef, float focops_lam, float focops_eta,
+                          const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                          float* stats_part, const int* stop_flag, void* stream);
 int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, const float* act,
                    const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
                    const float* logstd_old, const float* moments, const float* lagrange,
@@ -167,7 +169,7 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     OSB_CUDA(cudaMemsetAsync(train_stats, 0, 3 * 8 * sizeof(float), s));
     int rc;
     // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
-    const bool use_tc = precision == 1 && O <= 64 && loss_kind != 2;
+    const bool use_tc = precision == 1 && O <= 64;
     const bool train_actor = (net_mask & 1) != 0;
     if (train_actor) {
         OSB_CHECK_ARG(mu_old && logstd_old && eval_ws && eval_out, "actor update needs mu_old/logstd_old/eval buffers");
@@ -182,31 +184,25 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
         for (long long start = 0; start < total; start += batch_size) {
             const int count = (int)((total - start < batch_size) ? (total - start) : batch_size);
-            if (use_tc)
-                rc = osb_minibatch_grad_tc(theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c,
-                                           moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it,
-                                           start, count, loss_kind, clip, entropy_coef, lagrange,
-                                           net_mask, gpart, stats_part, stop_flag, stream);
-            else
-                rc = osb_minibatch_grad(theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old,
-                                        moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it,
-                                        start, count, loss_kind, clip, entropy_coef, focops_lam,
-                                        focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part,
-                                        stop_flag, stream);
+            rc = (use_tc ? osb_minibatch_grad_tc : osb_minibatch_grad)(
+                theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old, moments, perm_it, total,
+                perm_seed + 0x9E3779B9u * (unsigned)it, start, count, loss_kind, clip, entropy_coef,
+                focops_lam, focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part, stop_flag, stream);
             if (rc) return rc;
+            const int nb = use_tc ? osb_tc_grid_blocks(count, net_mask) : osb_update_grid_blocks(count);
             if (world_size > 1 && peer_buf && peer_flag && p2p_error) {
                 // one cooperative kernel: reduce + clip + one-shot NVLink peer-memory all-reduce + Adam
                 static unsigned p2p_step = 0;
-                rc = osb_optim_fused_p2p(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                rc = osb_optim_fused_p2p(gpart, stats_part, nb, O, A, theta, grad,
                                          adam_m, adam_v, adam_step, critic_norm_coef, max_grad_norm, lr_actor,
                                          lr_critic, lr_critic, net_mask, sumsq_part, train_stats, stop_flag,
                                          peer_buf, peer_flag, world_size, rank, ++p2p_step, p2p_error, stream);
             } else if (!(comm && world_size > 1)) {
-                rc = osb_optim_fused(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                rc = osb_optim_fused(gpart, stats_part, nb, O, A, theta, grad,
                                      adam_m, adam_v, adam_step, critic_norm_coef, max_grad_norm, lr_actor,
                                      lr_critic, lr_critic, net_mask, sumsq_part, train_stats, stop_flag, stream);
             } else {
-                rc = osb_grad_reduce(gpart, stats_part, osb_update_grid_blocks(count), O, A, theta, grad,
+                rc = osb_grad_reduce(gpart, stats_part, nb, O, A, theta, grad,
                                      critic_norm_coef, net_mask, sumsq_part, adam_step, train_stats,
                                      stop_flag, stream);
                 if (rc) return rc;

@@ -29,12 +29,13 @@ using namespace umma;
 constexpr int TT = 128;                 // samples per tile
 constexpr uint32_t BUF = TT * 64 * 4;   // 32 KB activation buffer ([128][64] or [64][128] fp32)
 
-enum TcLoss { TC_PPO_CLIP = 0, TC_RATIO = 1, TC_COST = 3 };
+enum TcLoss { TC_PPO_CLIP = 0, TC_RATIO = 1, TC_FOCOPS = 2, TC_COST = 3, TC_FVP = 4 };   // TC_FVP: dOUT supplied (Fisher-vector product)
 
 struct TcBatch {
     const float* obs; const float* act; const float* logp; const float* adv_r; const float* adv_c;
     const float* tv_r; const float* tv_c; const float* moments; const int* perm;
     long long total; unsigned perm_seed; long long mb_start; int mb_count;
+    int identity_stride;     // > 0: row = (mb_start + local) * identity_stride (full-batch passes, fvp_sample_freq)
 };
 struct TcArgs {
     TcBatch b;
@@ -45,6 +46,14 @@ struct TcArgs {
     float* stats_part;
     const int* stop_flag;
     int O, A, P, net_mask;
+    const float* fvp_dmu;    // TC_FVP: tangent of mu per row [total][A] (fvp_tangent_tc_kernel)
+    const float* fvp_vec;    // TC_FVP: direction v (log_std block of F v)
+    float fvp_scale;         // TC_FVP: 1 / (rows * A)
+    const float* mu_old;     // TC_FOCOPS: old-policy mean per row, log_std of the old policy,
+    const float* logstd_old;
+    float focops_lam, focops_eta;
+    const float* focops_mask_mean;   // device scalar mean_i 1{KL_i <= eta} of this minibatch (pass 2) or null (pass 1)
+    int forward_only;        // pass 1 of FOCOPS: statistics only, no backward
 };
 
 __device__ __forceinline__ unsigned long long tc_feistel(unsigned long long k, unsigned long long n, unsigned seed) {
@@ -93,7 +102,8 @@ __device__ __forceinline__ void load_row16(uint32_t base, int r, int c0, int R, 
 
 __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     if (p.stop_flag && *p.stop_flag) return;
-    const int net = blockIdx.y;
+    // one network selected: grid.y == 1 and all of grid.x (up to one CTA per SM) works on that network
+    const int net = (gridDim.y == 1) ? (__ffs(p.net_mask) - 1) : (int)blockIdx.y;
     if (!((p.net_mask >> net) & 1)) return;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -113,9 +123,10 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     float* sB3 = sB2 + 64;            // [16]
     float* sLs = sB3 + 16;            // logstd[16], sigma[16], dlogstd acc[16]
     float* sStat = sLs + 48;          // [8]
-    float* sRed = sStat + 8;          // [16 + 4 * 16 + 4 * 16]
-    float* sB3acc = sRed + 144;       // [16]
-    long long* sRowBuf = reinterpret_cast<long long*>(sB3acc + 16);   // [2][128] rows of this / the next tile
+    float* sRed = sStat + 8;          // [4 * 8 + 4 * 16 + 4 * 16]
+    float* sB3acc = sRed + 160;       // [16]
+    float* sOld = sB3acc + 16;        // old policy: log_std[16], 1 / sigma_old^2 [16]
+    long long* sRowBuf = reinterpret_cast<long long*>(sOld + 32);   // [2][128] rows of this / the next tile
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
 
@@ -166,6 +177,8 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         sB3[tid] = (tid < L.out) ? __ldg(theta + L.off_b3 + tid) : 0.f;
         const float ls = (net == 0 && tid < A) ? __ldg(theta + L.off_logstd + tid) : 0.f;
         sLs[tid] = ls; sLs[16 + tid] = expf(ls); sLs[32 + tid] = 0.f;
+        const float lso = (net == 0 && tid < A && p.logstd_old) ? __ldg(p.logstd_old + tid) : 0.f;
+        sOld[tid] = lso; sOld[16 + tid] = expf(-2.f * lso);
     }
     if (tid < 8) sStat[tid] = 0.f;
     if (tid < 16) sB3acc[tid] = 0.f;
@@ -179,7 +192,9 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     uint32_t phase = 0;
 
     const float lam = (p.lagrange != nullptr) ? __ldg(p.lagrange) : 0.f;
-    const float m_r = __ldg(p.b.moments + 0), s_r = __ldg(p.b.moments + 1), m_c = __ldg(p.b.moments + 2);
+    float m_r = 0.f, s_r = 1.f, m_c = 0.f;
+    if (p.b.moments) { m_r = __ldg(p.b.moments + 0); s_r = __ldg(p.b.moments + 1); m_c = __ldg(p.b.moments + 2); }
+    const bool is_fvp = p.kind == TC_FVP, is_focops = p.kind == TC_FOCOPS;
     float ab1 = 0.f, ab2 = 0.f;
     bool first_tile = true;
     const int s_row = 32 * q + lane;       // sample row of this thread in [s][.] accumulators
@@ -194,7 +209,8 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             long long row = -1;
             if (local < p.b.mb_count) {
                 const long long k = p.b.mb_start + local;
-                row = p.b.perm ? (long long)p.b.perm[k] : (long long)tc_feistel((unsigned long long)k, (unsigned long long)p.b.total, p.b.perm_seed);
+                if (p.b.identity_stride > 0) row = k * p.b.identity_stride;
+                else row = p.b.perm ? (long long)p.b.perm[k] : (long long)tc_feistel((unsigned long long)k, (unsigned long long)p.b.total, p.b.perm_seed);
             }
             dst[tid] = row;
         }
@@ -317,19 +333,27 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             }
         }
         // per-sample scalars: issue the global loads before blocking on the MMA
-        float pf_act[16], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
+        float pf_act[16], pf_mu[16], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
         const long long prow = (h == 0) ? sRow[s_row] : -1;
         {
 #pragma unroll
-            for (int a = 0; a < 16; ++a) pf_act[a] = 0.f;
+            for (int a = 0; a < 16; ++a) { pf_act[a] = 0.f; pf_mu[a] = 0.f; }
             if (prow >= 0) {
                 if (net == 0) {
+                    const float* src = is_fvp ? p.fvp_dmu : p.b.act;
 #pragma unroll
                     for (int a = 0; a < 16; ++a)
-                        if (a < A) pf_act[a] = __ldg(p.b.act + prow * A + a);
-                    pf_logp = __ldg(p.b.logp + prow);
-                    pf_advr = __ldg(p.b.adv_r + prow);
-                    pf_advc = __ldg(p.b.adv_c + prow);
+                        if (a < A) pf_act[a] = __ldg(src + prow * A + a);
+                    if (is_focops) {
+#pragma unroll
+                        for (int a = 0; a < 16; ++a)
+                            if (a < A) pf_mu[a] = __ldg(p.mu_old + prow * A + a);
+                    }
+                    if (!is_fvp) {
+                        pf_logp = __ldg(p.b.logp + prow);
+                        pf_advr = __ldg(p.b.adv_r + prow);
+                        pf_advc = __ldg(p.b.adv_c + prow);
+                    }
                 } else {
                     pf_tv = __ldg((net == 1 ? p.b.tv_r : p.b.tv_c) + prow);
                 }
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         if (h == 0) {
-            float st[4] = {0.f, 0.f, 0.f, 0.f};
+            float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // loss, ratio, kl, count, focops mask
             float dls[16];
 #pragma unroll
             for (int a = 0; a < 16; ++a) dls[a] = 0.f;
@@ -351,6 +375,15 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                     const float d = o16[0] + sB3[0] - pf_tv;
                     st[0] = d * d; st[3] = 1.f;
                     d32[0] = 2.f * d * inv_b;
+                } else if (is_fvp) {
+                    // dOUT = diag(sigma^-2) J v / (rows * A): the backward below then yields J^T of it
+#pragma unroll
+                    for (int a = 0; a < 16; ++a)
+                        if (a < A) {
+                            const float sd = sLs[16 + a];
+                            d32[a] = pf_act[a] / (sd * sd) * p.fvp_scale;
+                        }
+                    st[3] = 1.f;
                 } else {
                     float logp_new = 0.f, diff[16];
 #pragma unroll
@@ -367,8 +400,24 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                     const float adv_r = (pf_advr - m_r) / s_r;
                     const float adv_c = pf_advc - m_c;
                     const float adv = (adv_r - lam * adv_c) / (1.f + lam);
-                    float dlogp, loss;
-                    if (p.kind == TC_PPO_CLIP) {
+                    float dlogp, loss, dmask = 0.f;
+                    if (is_focops) {
+                        // first_order/focops.py:L62-108 incl. the reference's [b,1] x [b] broadcast:
+                        //   loss = mean_i(mask_i kl_i) - mean_i(mask_i) * mean_j(ratio_j adv_j) / lam
+                        float kl = 0.f;
+#pragma unroll
+                        for (int a = 0; a < 16; ++a)
+                            if (a < A) {
+                                const float sn = sLs[16 + a];
+                                const float dm = (o16[a] + sB3[a]) - pf_mu[a];
+                                kl += (sOld[a] - sLs[a]) + (sn * sn + dm * dm) * 0.5f * sOld[16 + a] - 0.5f;
+                            }
+                        dmask = (kl <= p.focops_eta) ? 1.f : 0.f;
+                        const float mbar = p.focops_mask_mean ? __ldg(p.focops_mask_mean) : dmask;
+                        loss = kl * dmask - mbar * ratio * adv / p.focops_lam;
+                        dlogp = -mbar * adv * ratio / p.focops_lam * inv_b;
+                        st[2] = kl; st[4] = dmask;
+                    } else if (p.kind == TC_PPO_CLIP) {
                         const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
                         const float s1 = ratio * adv, s2 = rc * adv;
                         loss = -fminf(s1, s2);
@@ -386,6 +435,11 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                             const float iv = 1.f / (sd * sd);
                             d32[a] = dlogp * diff[a] * iv;
                             dls[a] = dlogp * (diff[a] * diff[a] * iv - 1.f);
+                            if (is_focops) {
+                                const float dm = (o16[a] + sB3[a]) - pf_mu[a];
+                                d32[a] += dmask * inv_b * dm * sOld[16 + a];
+                                dls[a] += dmask * inv_b * (sd * sd * sOld[16 + a] - 1.f);
+                            }
                         }
                 }
             }
@@ -394,7 +448,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             for (int o = 0; o < 16; ++o) sts(tile_addr(B4 + 16384u, o, s_row, 16), tf32r(d32[o]));   // dOUT^T [o][s]
             // deterministic reductions over the 128 sample threads (warps with h == 0)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) st[i] = warp_sum(st[i]);
+            for (int i = 0; i < 5; ++i) st[i] = warp_sum(st[i]);
             if (net == 0) {
 #pragma unroll
                 for (int a = 0; a < 16; ++a) dls[a] = warp_sum(dls[a]);
@@ -404,22 +458,29 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             for (int a = 0; a < 16; ++a) db[a] = (a < L.out) ? warp_sum(d32[a]) : 0.f;
             if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sRed[q * 4 + i] = st[i];
+                for (int i = 0; i < 5; ++i) sRed[q * 8 + i] = st[i];
 #pragma unroll
-                for (int a = 0; a < 16; ++a) { sRed[16 + q * 16 + a] = dls[a]; sRed[80 + q * 16 + a] = db[a]; }
+                for (int a = 0; a < 16; ++a) { sRed[32 + q * 16 + a] = dls[a]; sRed[96 + q * 16 + a] = db[a]; }
             }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid < 4) sStat[tid] += sRed[tid] + sRed[4 + tid] + sRed[8 + tid] + sRed[12 + tid];
+        if (tid < 5) sStat[tid] += sRed[tid] + sRed[8 + tid] + sRed[16 + tid] + sRed[24 + tid];
         if (net == 0 && tid >= 32 && tid < 48) {
             const int a = tid - 32;
-            sLs[32 + a] += sRed[16 + a] + sRed[32 + a] + sRed[48 + a] + sRed[64 + a];
+            sLs[32 + a] += sRed[32 + a] + sRed[48 + a] + sRed[64 + a] + sRed[80 + a];
         }
         if (tid >= 64 && tid < 64 + L.out) {
             const int a = tid - 64;
-            sB3acc[a] += sRed[80 + a] + sRed[96 + a] + sRed[112 + a] + sRed[128 + a];
+            sB3acc[a] += sRed[96 + a] + sRed[112 + a] + sRed[128 + a] + sRed[144 + a];
+        }
+        if (p.forward_only) {   // FOCOPS pass 1: statistics only
+            if (vec && has_next) prefetch_x(sRowNext);
+            first_tile = false;
+            rpar ^= 1;
+            __syncthreads();
+            continue;
         }
         // ---- P4: dZ2, dZ2^T and dW3^T += H2^T dOUT ------------------------------------------------
         if (tid == 0) {
@@ -510,7 +571,9 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     }
 
     // ---- write this CTA's partial gradient segment (staged through smem so that stores coalesce) ----
-    {
+    if (p.forward_only) {
+        if (tid < 8) p.stats_part[((size_t)blockIdx.x * 3 + net) * 8 + tid] = sStat[tid];
+    } else {
         float v[16];
         float* stage = reinterpret_cast<float*>(smem_raw + pad);            // B0 region: [2][64][65]
         tmem_ld16(tmem + lane_base + C_DW2 + c16, v);
@@ -535,10 +598,226 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         if (tid < L.out) gout[L.off_b3 + tid] = sB3acc[tid];
         if (net == 0 && tid < A) {
             float g = sLs[32 + tid];
-            if (blockIdx.x == 0 && p.kind == TC_PPO_CLIP) g -= p.entropy_coef / (float)A;
+            if (blockIdx.x == 0 && (p.kind == TC_PPO_CLIP || is_focops)) g -= p.entropy_coef / (float)A;
+            // log_std block of the Fisher matrix: (2/A) v, counted once (natural_pg.py:L74-119, analytic form)
+            if (is_fvp) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + tid) : 0.f;
             gout[L.off_logstd + tid] = g;
         }
         if (tid < 8) p.stats_part[((size_t)blockIdx.x * 3 + net) * 8 + tid] = sStat[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward-mode tangent pass of the Fisher-vector product (NaturalPG._fvp, base/natural_pg.py:L74-119):
+//   dmu[row][a] = J_mu(row) v      for the rows 0, stride, 2*stride, ...
+// The weight tile of every layer is stored with the direction's block stacked under it
+// ([W ; V], 128 rows), so ONE N = 128 MMA yields the pre-activation and the first tangent term:
+//     [Z1 | X V1^T]            = X   [W1;V1]^T
+//     [Z2 | H1 V2^T + dH1 W2^T] = H1 [W2;V2]^T  (+)  dH1 W2^T   (accumulated into the right half)
+//     dmu                       = H2 V3^T + dH2 W3^T + vb3
+// The backward half (J^T diag(sigma^-2) dmu) is minibatch_grad_tc_kernel with kind TC_FVP.
+struct FvpTanArgs {
+    const float* obs; long long total; int stride;
+    const float* theta; const float* vec; float* dmu; int O, A;
+};
+constexpr uint32_t F_Z1 = 0, F_Z2 = 128, F_DMU = 256;
+
+__global__ void __launch_bounds__(NTC, 1) fvp_tangent_tc_kernel(FvpTanArgs p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    const uint32_t B0 = smem_u32(smem_raw) + pad;   // X -> H2
+    const uint32_t B1 = B0 + BUF;                   // H1 -> dH2
+    const uint32_t B2 = B1 + BUF;                   // dH1
+    const uint32_t sWV1 = B2 + BUF;                 // [128][64]: rows 0..63 W1, 64..127 V1
+    const uint32_t sWV2 = sWV1 + 32768;             // [128][64]: W2 ; V2
+    const uint32_t sWV3 = sWV2 + 32768;             // [32][64]:  rows 0..15 W3, 16..31 V3
+    float* sB1 = reinterpret_cast<float*>(smem_raw + pad + 3 * BUF + 2 * 32768 + 8192);
+    float* sB2 = sB1 + 64;
+    float* sVB1 = sB2 + 64;
+    float* sVB2 = sVB1 + 64;
+    float* sVB3 = sVB2 + 64;           // [16]
+    long long* sRowBuf = reinterpret_cast<long long*>(sVB3 + 16);   // [2][128]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int O = p.O, A = p.A;
+    const NetLayout L = actor_layout(O, A);
+    const long long nrows = (p.total + p.stride - 1) / p.stride;
+    const int ntiles = (int)((nrows + TT - 1) / TT);
+
+    {   // stacked weight tiles (loads batched so they are all in flight together)
+        float w1v[8], v1v[8], w2v[8], v2v[8], w3v[2], v3v[2];
+        const int k = tid & 63;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
+            w1v[j] = (k < O) ? __ldg(p.theta + L.off_w1 + n * O + k) : 0.f;
+            v1v[j] = (k < O) ? __ldg(p.vec + L.off_w1 + n * O + k) : 0.f;
+            w2v[j] = __ldg(p.theta + L.off_w2 + n * 64 + k);
+            v2v[j] = __ldg(p.vec + L.off_w2 + n * 64 + k);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int o = (tid >> 6) + 8 * j;
+            w3v[j] = (o < A) ? __ldg(p.theta + L.off_w3 + o * 64 + k) : 0.f;
+            v3v[j] = (o < A) ? __ldg(p.vec + L.off_w3 + o * 64 + k) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
+            sts(tile_addr(sWV1, n, k, 128), tf32r(w1v[j]));
+            sts(tile_addr(sWV1, 64 + n, k, 128), tf32r(v1v[j]));
+            sts(tile_addr(sWV2, n, k, 128), tf32r(w2v[j]));
+            sts(tile_addr(sWV2, 64 + n, k, 128), tf32r(v2v[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int o = (tid >> 6) + 8 * j;
+            sts(tile_addr(sWV3, o, k, 32), tf32r(w3v[j]));
+            sts(tile_addr(sWV3, 16 + o, k, 32), tf32r(v3v[j]));
+        }
+    }
+    if (tid < 64) {
+        sB1[tid] = __ldg(p.theta + L.off_b1 + tid); sB2[tid] = __ldg(p.theta + L.off_b2 + tid);
+        sVB1[tid] = __ldg(p.vec + L.off_b1 + tid); sVB2[tid] = __ldg(p.vec + L.off_b2 + tid);
+    }
+    if (tid < 16) sVB3[tid] = (tid < A) ? __ldg(p.vec + L.off_b3 + tid) : 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t phase = 0;
+    const int s_row = 32 * q + lane, c16 = 16 * h;
+
+    const bool vec4 = (O & 3) == 0;
+    auto tile_rows = [&](int tile, long long* dst) {
+        if (tid < TT) {
+            const long long k = (long long)tile * TT + tid;
+            dst[tid] = (k < nrows) ? k * p.stride : -1;
+        }
+    };
+    float4 xpre[4];
+    auto prefetch_x = [&](const long long* rows) {
+        const int k4 = (tid & 15) << 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long row = rows[(tid >> 4) + 32 * j];
+            xpre[j] = (row >= 0 && k4 < O) ? __ldg(reinterpret_cast<const float4*>(p.obs + row * O + k4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int rpar = 0;
+    tile_rows(blockIdx.x, sRowBuf);
+    __syncthreads();
+    if (vec4) prefetch_x(sRowBuf);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long* sRow = sRowBuf + rpar * TT;
+        long long* sRowNext = sRowBuf + (rpar ^ 1) * TT;
+        const bool has_next = tile + (int)gridDim.x < ntiles;
+        if (has_next) tile_rows(tile + gridDim.x, sRowNext);
+        if (vec4) {
+            const int k4 = (tid & 15) << 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = (tid >> 4) + 32 * j;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, m, k4, TT)),
+                             "f"(tf32r(xpre[j].x)), "f"(tf32r(xpre[j].y)), "f"(tf32r(xpre[j].z)), "f"(tf32r(xpre[j].w))
+                             : "memory");
+            }
+        } else {
+            const int k = tid & 63;
+            float xv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long row = sRow[(tid >> 6) + 8 * j];
+                xv[j] = (row >= 0 && k < O) ? __ldg(p.obs + row * O + k) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sts(tile_addr(B0, (tid >> 6) + 8 * j, k, TT), tf32r(xv[j]));
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (vec4 && has_next) prefetch_x(sRowNext);      // next tile's rows fly during the three layers
+        // ---- layer 1: [Z1 | X V1^T] ----------------------------------------------------------------
+        if (tid == 0) {
+            tc_fence_after();
+            tc_gemm(tmem + F_Z1, B0, TT, sWV1, 128, 128, 128, 64, false);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float z[16], dz[16];
+            tmem_ld16(tmem + lane_base + F_Z1 + c16, z);
+            tmem_ld16(tmem + lane_base + F_Z1 + 64 + c16, dz);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float hh = tanh_fast(z[i] + sB1[c16 + i]);
+                dz[i] = (1.f - hh * hh) * (dz[i] + sVB1[c16 + i]);
+                z[i] = hh;
+            }
+            store_row16(B1, s_row, c16, TT, z);      // H1
+            store_row16(B2, s_row, c16, TT, dz);     // dH1
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 2: [Z2 | H1 V2^T + dH1 W2^T] ------------------------------------------------------
+        if (tid == 0) {
+            tc_fence_after();
+            tc_gemm(tmem + F_Z2, B1, TT, sWV2, 128, 128, 128, 64, false);
+            tc_gemm(tmem + F_Z2 + 64, B2, TT, sWV2, 128, 128, 64, 64, true);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float z[16], dz[16];
+            tmem_ld16(tmem + lane_base + F_Z2 + c16, z);
+            tmem_ld16(tmem + lane_base + F_Z2 + 64 + c16, dz);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float hh = tanh_fast(z[i] + sB2[c16 + i]);
+                dz[i] = (1.f - hh * hh) * (dz[i] + sVB2[c16 + i]);
+                z[i] = hh;
+            }
+            store_row16(B0, s_row, c16, TT, z);      // H2  (X is dead)
+            store_row16(B1, s_row, c16, TT, dz);     // dH2 (H1 is dead: layer-2 MMAs completed)
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- output tangent: dmu = H2 V3^T + dH2 W3^T + vb3 -------------------------------------------
+        if (tid == 0) {
+            tc_fence_after();
+            tc_gemm(tmem + F_DMU, B0, TT, sWV3 + 2048u, 32, 128, 16, 64, false);
+            tc_gemm(tmem + F_DMU, B1, TT, sWV3, 32, 128, 16, 64, true);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        if (h == 0) {
+            float o16[16];
+            tmem_ld16(tmem + lane_base + F_DMU, o16);
+            const long long row = sRow[s_row];
+            if (row >= 0) {
+#pragma unroll
+                for (int a = 0; a < 16; ++a)
+                    if (a < A) p.dmu[row * A + a] = o16[a] + sVB3[a];
+            }
+        }
+        tc_fence_before();
+        rpar ^= 1;
+        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
@@ -550,40 +829,120 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
 using namespace osb;
 
 static size_t tc_smem_bytes() {
-    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 160) * 4 + 2 * 128 * 8 + 64;
+    return 1024 + 5 * (size_t)BUF + 3 * 16384 + 4096 + 8192 + (64 + 64 + 16 + 48 + 8 + 160 + 16 + 32) * 4 + 2 * 128 * 8 + 64;
+}
+static size_t fvp_tan_smem_bytes() {
+    return 1024 + 3 * (size_t)BUF + 2 * 32768 + 8192 + (4 * 64 + 16) * 4 + 2 * 128 * 8 + 64;
 }
 
-extern "C" {
-
-int osb_update_grid_blocks(int mb_count);
-
-// Tensor-core (TF32 tcgen05) variant of osb_minibatch_grad; O <= 64, loss kinds 0 / 1 / 3.
-int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
-                          const float* logp, const float* adv_r, const float* adv_c,
-                          const float* tv_r, const float* tv_c, const float* moments,
-                          const int* perm, long long total, unsigned perm_seed, long long mb_start,
-                          int mb_count, int loss_kind, float clip, float entropy_coef,
-                          const float* lagrange, int net_mask, float* gpart, float* stats_part,
-                          const int* stop_flag, void* stream) {
-    OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
-    OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "tensor-core path needs O <= 64, A <= 16");
-    OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
-    OSB_CHECK_ARG(loss_kind == 0 || loss_kind == 1 || loss_kind == 3, "tensor-core path: loss kind 0, 1 or 3");
-    TcArgs p;
-    p.b = TcBatch{obs, act, logp, adv_r, adv_c, tv_r, tv_c, moments, perm, total, perm_seed, mb_start, mb_count};
-    p.kind = loss_kind; p.clip = clip; p.entropy_coef = entropy_coef; p.lagrange = lagrange;
-    p.theta = theta; p.gpart = gpart; p.stats_part = stats_part; p.stop_flag = stop_flag;
-    p.O = O; p.A = A; p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size; p.net_mask = net_mask;
+static int launch_grad_tc(const TcArgs& p, int nblocks, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes();
     static bool attr = false;
     if (!attr) {
         OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    dim3 grid(osb_update_grid_blocks(mb_count), 3);
-    minibatch_grad_tc_kernel<<<grid, NTC, smem, (cudaStream_t)stream>>>(p);
+    const bool single = (p.net_mask & (p.net_mask - 1)) == 0;     // one network: it gets every CTA
+    dim3 grid(nblocks, single ? 1 : 3);
+    minibatch_grad_tc_kernel<<<grid, NTC, smem, stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
+}
+
+extern "C" {
+
+int osb_update_grid_blocks(int mb_count);
+
+// CTAs along x of the tensor-core kernel: three networks share the 148 SMs (49 each); a single
+// network (full-batch actor passes of the natural-gradient family) spreads over all of them.
+int osb_tc_grid_blocks(long long rows, int net_mask) {
+    const long long tiles = (rows + TT - 1) / TT;
+    const int cap = ((net_mask & (net_mask - 1)) == 0) ? 148 : 49;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+// FOCOPS pass 1 -> mean_i mask_i of the minibatch (stats slot 4 / slot 3 of the actor), fixed order.
+__global__ void tc_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
+                                    const int* __restrict__ stop_flag) {
+    if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    float m = 0.f, n = 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + 4]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
+    out[0] = n > 0.f ? m / n : 0.f;
+}
+
+// Tensor-core (TF32 tcgen05) variant of osb_minibatch_grad: same arguments, O <= 64, A <= 16.
+// gpart holds osb_tc_grid_blocks(mb_count, net_mask) rows of P floats.
+int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, const float* act,
+                          const float* logp, const float* adv_r, const float* adv_c,
+                          const float* tv_r, const float* tv_c, const float* mu_old,
+                          const float* moments, const int* perm, long long total, unsigned perm_seed,
+                          long long mb_start, int mb_count, int loss_kind, float clip,
+                          float entropy_coef, float focops_lam, float focops_eta,
+                          const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                          float* stats_part, const int* stop_flag, void* stream) {
+    static float* d_mask_mean = nullptr;   // FOCOPS scratch scalar
+    OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
+    OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "tensor-core path needs O <= 64, A <= 16");
+    OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
+    OSB_CHECK_ARG(loss_kind >= 0 && loss_kind <= 3, "loss kind");
+    OSB_CHECK_ARG(loss_kind != TC_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old/logstd_old");
+    OSB_CHECK_ARG(net_mask > 0 && net_mask < 8, "net_mask");
+    TcArgs p;
+    p.b = TcBatch{obs, act, logp, adv_r, adv_c, tv_r, tv_c, moments, perm, total, perm_seed, mb_start, mb_count, 0};
+    p.kind = loss_kind; p.clip = clip; p.entropy_coef = entropy_coef; p.lagrange = lagrange;
+    p.theta = theta; p.gpart = gpart; p.stats_part = stats_part; p.stop_flag = stop_flag;
+    p.O = O; p.A = A; p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size; p.net_mask = net_mask;
+    p.fvp_dmu = nullptr; p.fvp_vec = nullptr; p.fvp_scale = 0.f;
+    p.mu_old = mu_old; p.logstd_old = logstd_old; p.focops_lam = focops_lam; p.focops_eta = focops_eta;
+    p.focops_mask_mean = nullptr; p.forward_only = 0;
+    const int nb = osb_tc_grid_blocks(mb_count, net_mask);
+    if (loss_kind == TC_FOCOPS && (net_mask & 1)) {
+        // pass 1: actor forward only -> mean mask of the minibatch (the reference's [b,1] x [b] broadcast)
+        if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
+        TcArgs q = p;
+        q.forward_only = 1; q.net_mask = 1;
+        const int nb1 = osb_tc_grid_blocks(mb_count, 1);
+        int rc = launch_grad_tc(q, nb1, (cudaStream_t)stream);
+        if (rc) return rc;
+        tc_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag);
+        OSB_LAUNCH_CHECK();
+        p.focops_mask_mean = d_mask_mean;
+    }
+    return launch_grad_tc(p, nb, (cudaStream_t)stream);
+}
+
+// Tensor-core Fisher-vector product partials (O <= 64): tangent forward (dmu scratch [total][A]) then
+// the actor backward of minibatch_grad_tc_kernel.  gpart: osb_tc_grid_blocks(rows, 1) rows of
+// P_actor floats; stats_scratch: that many * 24 floats.  Reduce with osb_reduce_partials.
+int osb_fvp_partials_tc(const float* theta_actor, const float* vec, int O, int A, const float* obs,
+                        long long total, int stride, float* dmu, float* gpart, float* stats_scratch,
+                        void* stream) {
+    OSB_CHECK_ARG(theta_actor && vec && obs && dmu && gpart && stats_scratch && total > 0 && stride > 0, "bad argument");
+    OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16, "tensor-core path needs O <= 64, A <= 16");
+    const long long nrows = (total + stride - 1) / stride;
+    OSB_CHECK_ARG(nrows < (1ll << 31), "too many rows");
+    const int nb = osb_tc_grid_blocks(nrows, 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        FvpTanArgs t{obs, total, stride, theta_actor, vec, dmu, O, A};
+        const size_t smem = fvp_tan_smem_bytes();
+        static bool attr = false;
+        if (!attr) {
+            OSB_CUDA(cudaFuncSetAttribute(fvp_tangent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        fvp_tangent_tc_kernel<<<nb, NTC, smem, s>>>(t);
+        OSB_LAUNCH_CHECK();
+    }
+    TcArgs p;
+    p.b = TcBatch{obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, 0u, 0, (int)nrows, stride};
+    p.kind = TC_FVP; p.clip = 0.f; p.entropy_coef = 0.f; p.lagrange = nullptr;
+    p.theta = theta_actor; p.gpart = gpart; p.stats_part = stats_scratch; p.stop_flag = nullptr;
+    p.O = O; p.A = A; p.P = actor_layout(O, A).size; p.net_mask = 1;
+    p.fvp_dmu = dmu; p.fvp_vec = vec; p.fvp_scale = 1.0f / ((float)nrows * (float)A);
+    p.mu_old = nullptr; p.logstd_old = nullptr; p.focops_lam = 1.f; p.focops_eta = 0.f;
+    p.focops_mask_mean = nullptr; p.forward_only = 0;
+    return launch_grad_tc(p, nb, s);
 }
 
 }  // extern "C"

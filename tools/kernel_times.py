@@ -26,7 +26,7 @@ def timeit(name, fn, iters=30):
 
 
 nb = lib().osb_update_grid_blocks(bs)
-timeit('minibatch_grad_tc', lambda: lib().osb_minibatch_grad_tc(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(buf.adv_moments), 0, total, 1, 0, bs, 0, 0.2, 0.0, ptr(algo._lagrange.state), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, s()))
+timeit('minibatch_grad_tc', lambda: lib().osb_minibatch_grad_tc(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 1, 0, bs, 0, 0.2, 0.0, 1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, s()))
 timeit('minibatch_grad (fp32)', lambda: lib().osb_minibatch_grad(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 1, 0, bs, 0, 0.2, 0.0, 1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, s()))
 timeit('grad_reduce', lambda: lib().osb_grad_reduce(ptr(eng.gpart), ptr(eng.stats_part), nb, O, A, ptr(ac.theta), ptr(ac.grad), 0.001, 7, ptr(eng.sumsq_part), ptr(ac.adam_step), ptr(eng.train_stats), 0, s()))
 timeit('clip_adam', lambda: lib().osb_clip_adam(ptr(ac.grad), ptr(ac.theta), ptr(ac.adam_m), ptr(ac.adam_v), ptr(ac.adam_step), ptr(eng.sumsq_part), O, A, 40.0, 0.0, 0.0, 0.0, 1.0, 0.001, ptr(eng.train_stats), 1, 1, 7, 0, s()))

@@ -9,5 +9,5 @@ eng, buf, ac, d = algo._engine, algo._buf, algo._actor_critic, algo._buf.data
 O, A, total = w['obs_dim'], w['act_dim'], buf.T * buf.N
 for bs in (128, 6272, 16384, 6272 * 6):
     for rep in range(3):
-        lib().osb_minibatch_grad_tc(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(buf.adv_moments), 0, total, 1, 0, bs, 0, 0.2, 0.0, ptr(algo._lagrange.state), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, current_stream())
+        lib().osb_minibatch_grad_tc(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 1, 0, bs, 0, 0.2, 0.0, 1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7, ptr(eng.gpart), ptr(eng.stats_part), 0, current_stream())
         torch.cuda.synchronize()
