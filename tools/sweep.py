@@ -38,7 +38,8 @@ def run(algo, O, epochs=4, N=4096, T=128):
 
 
 if __name__ == '__main__':
+    dims = (17, 60) if '--tc-only' in sys.argv else (17, 60, 111, 376)
     run('CPO', 60)
     for algo in ('TRPOLag', 'FOCOPS'):
-        for O in (17, 60, 111, 376):
+        for O in dims:
             run(algo, O)
