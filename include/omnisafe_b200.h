@@ -214,6 +214,15 @@ int osb_optim_fused_p2p(const float* gpart, const float* stats_part, int nblocks
  * episode has finished yet (the reference asserts, naive_lagrange/ppo_lag.py:L74). */
 int osb_lagrange_update(const double* window_sums, float cost_limit, float lambda_lr,
                         float upper_bound, float* state, int* nan_flag, void* stream);
+/* PID-Lagrangian controller step (PIDLagrangian.pid_update, common/pid_lagrange.py:L95-125) in the
+ * reference's Python-float (fp64) arithmetic.  pid_state: 64 doubles {integral, EMA(delta), EMA(Jc),
+ * penalty, deque length, deque head, -, -, ring[pid_d_delay]}, initialised by the host to
+ * {lagrangian_multiplier_init, 0, 0, 0, 1, 0, ..., ring[0] = 0}.  lagrange_state[0] <- (float) penalty.
+ * Jc = window_sums[1] / window_sums[3]; an empty window sets *nan_flag. */
+int osb_pid_lagrange_update(const double* window_sums, double pid_kp, double pid_ki, double pid_kd,
+                            int pid_d_delay, double pid_delta_p_ema_alpha, double pid_delta_d_ema_alpha,
+                            int sum_norm, int diff_norm, double penalty_max, double cost_limit,
+                            double* pid_state, float* lagrange_state, int* nan_flag, void* stream);
 /* kl = eval_out[0]/eval_out[4]; kl_state[4] = {last kl, passes done, stopped, 0}. */
 int osb_kl_check(const double* eval_out, float target_kl, int early_stop, int* stop_flag,
                  float* kl_state, void* stream);

@@ -1,5 +1,5 @@
-"""On-policy algorithms on the fused sm_100a path: PolicyGradient / PPO / PPOLag /
-NaturalPG / TRPO / TRPOLag / CPO / FOCOPS.
+"""On-policy algorithms on the fused sm_100a path: PolicyGradient / PPO / PPOLag / NaturalPG / RCPO /
+TRPO / TRPOLag / CPO / PCPO / FOCOPS / CPPOPID / TRPOPID / OnCRPO.
 
 Each class mirrors the override structure of the reference
 (omnisafe/algorithms/on_policy/base/{policy_gradient,ppo,natural_pg,trpo}.py,
@@ -22,6 +22,7 @@ from omnisafe_b200.algorithms.engine import (LOSS_COST, LOSS_FOCOPS, LOSS_PPO_CL
 from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 from omnisafe_b200.common.lagrange import Lagrange
 from omnisafe_b200.common.logger import Logger
+from omnisafe_b200.common.pid_lagrange import PIDLagrangian
 from omnisafe_b200.models.actor_critic import ConstraintActorCritic
 from omnisafe_b200.utils import distributed
 
@@ -214,6 +215,8 @@ class FOCOPS(_LagrangeMixin, PolicyGradient):
 class NaturalPG(PolicyGradient):
     """base/natural_pg.py:L30-230: one full-batch natural-gradient actor step, then critic passes."""
 
+    _kind = LOSS_RATIO
+
     def _init_log(self) -> None:
         super()._init_log()
         for key in ('Misc/Alpha', 'Misc/FinalStepNorm', 'Misc/gradient_norm', 'Misc/xHx', 'Misc/H_inv_g'):
@@ -227,6 +230,11 @@ class NaturalPG(PolicyGradient):
     def _adv_lagrange(self):
         return self._lagrange_ptr()
 
+    def _surrogate_kind(self) -> int:
+        """Which actor loss `_loss_pi(obs, act, logp, adv)` stands for this epoch: LOSS_RATIO with
+        adv = _compute_adv_surrogate(adv_r, adv_c), or LOSS_COST when the surrogate is -adv_c (OnCRPO)."""
+        return LOSS_RATIO
+
     def _natural_direction(self):
         """theta_old, g = -grad(loss), x = H^-1 g, xHx, alpha (natural_pg.py:L146-166)."""
         a, e, ac = self._cfgs.algo_cfgs, self._engine, self._actor_critic
@@ -234,7 +242,8 @@ class NaturalPG(PolicyGradient):
         e.snapshot_old_policy()
         theta_old = ac.theta[:Pa].clone()
         grads = torch.empty(Pa, dtype=torch.float32, device=self._device)
-        loss_before = e.actor_loss_grad(LOSS_RATIO, self._adv_lagrange(), grads, sign=-1.0)
+        self._kind = self._surrogate_kind()
+        loss_before = e.actor_loss_grad(self._kind, self._adv_lagrange(), grads, sign=-1.0)
         x = e.conjugate_gradients(grads, a.cg_iters, a.cg_damping, a.fvp_sample_freq)
         assert torch.isfinite(x).all(), 'x is not finite'
         e.fvp(x, e.cg_z, a.cg_damping, a.fvp_sample_freq)
@@ -278,8 +287,9 @@ class TRPO(NaturalPG):
         for step in range(total_steps):
             trial[: e.Pa] = theta_old + step_frac * step_direction
             ev = e.evaluate(trial, self._adv_lagrange())
-            loss_improve = loss_before - ev['loss']
-            if not math.isfinite(ev['loss']):
+            loss = ev['loss_c'] if self._kind == LOSS_COST else ev['loss']
+            loss_improve = loss_before - loss
+            if not math.isfinite(loss):
                 self._logger.log('WARNING: loss_pi not finite')
             elif loss_improve < 0:
                 self._logger.log('INFO: did not improve improve <0')
@@ -415,4 +425,84 @@ class CPO(TRPO):
             'Misc/q': q, 'Misc/r': r, 'Misc/s': s}
 
 
-ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'FOCOPS']
+@registry.register
+class PCPO(CPO):
+    """second_order/pcpo.py:L31-152: CPO's machinery with the projection step
+    sqrt(2 delta / q) H x - max(0, (sqrt(2 delta / q) r + c) / s) p, searched over up to 200 halvings."""
+
+    def _update_actor(self) -> None:
+        a, e = self._cfgs.algo_cfgs, self._engine
+        theta_old, grads, x, xHx, alpha, loss_reward_before = self._natural_direction()
+        h_inv_g = e.cg_z.clone()                     # the reference's `H_inv_g = self._fvp(x)` (pcpo.py:L80)
+        b_grads = torch.empty(e.Pa, dtype=torch.float32, device=self._device)
+        loss_cost_before = float(e.actor_loss_grad(LOSS_COST, None, b_grads, sign=1.0))
+        ep_costs = self._window_means()[1] - a.cost_limit
+        p = e.conjugate_gradients(b_grads, a.cg_iters, a.cg_damping, a.fvp_sample_freq)
+        q, r, s = xHx, e.dot(grads, p), e.dot(b_grads, p)
+        f32 = lambda v: torch.tensor(v, dtype=torch.float32)   # noqa: E731  (0-dim fp32 arithmetic as in the reference)
+        kl2 = 2 * a.target_kl
+        coef_h = float(torch.sqrt(kl2 / (f32(q) + 1e-8)))
+        coef_p = float(torch.clamp_min((torch.sqrt(kl2 / f32(q)) * f32(r) + ep_costs) / f32(s), 0.0))
+        step_direction = coef_h * h_inv_g - coef_p * p
+        step, accept = self._cpo_search_step(step_direction, theta_old, loss_reward_before, loss_cost_before,
+                                             total_steps=200, violation_c=ep_costs)
+        self._actor_critic.theta[: e.Pa] = theta_old + step
+        self._misc = {
+            'Misc/AcceptanceStep': accept, 'Misc/Alpha': alpha, 'Misc/FinalStepNorm': float(step.norm()),
+            'Misc/xHx': xHx, 'Misc/H_inv_g': float(x.norm()), 'Misc/gradient_norm': float(grads.norm()),
+            'Misc/cost_gradient_norm': float(b_grads.norm()), 'Misc/Lambda_star': 1.0, 'Misc/Nu_star': 1.0,
+            'Misc/OptimCase': 1, 'Misc/A': 1.0, 'Misc/B': 1.0, 'Misc/q': q, 'Misc/r': r, 'Misc/s': s}
+
+
+class _PIDLagrangeMixin(_LagrangeMixin):
+    """`_init` of CPPOPID / TRPOPID (pid_lagrange/cppo_pid.py:L36-43): the multiplier is driven by the PID
+    controller; `_update` (Jc -> pid_update -> super()._update()) and the surrogate
+    (adv_r - lambda adv_c) / (1 + lambda) are those of the Lagrange mixin."""
+
+    def _init(self) -> None:
+        super(_LagrangeMixin, self)._init()     # skip the Adam-multiplier constructor of the Lagrange mixin
+        self._lagrange = PIDLagrangian(**self._cfgs.lagrange_cfgs.todict(), device=self._device)
+
+
+@registry.register
+class CPPOPID(_PIDLagrangeMixin, PPO):
+    """pid_lagrange/cppo_pid.py:L27-103."""
+
+
+@registry.register
+class TRPOPID(_PIDLagrangeMixin, TRPO):
+    """pid_lagrange/trpo_pid.py:L26-103."""
+
+
+@registry.register
+class OnCRPO(TRPO):
+    """primal/crpo.py:L25-80: TRPO on adv_r while Jc <= cost_limit + distance, otherwise on -adv_c."""
+
+    def _init(self) -> None:
+        super()._init()
+        self._rew_update, self._cost_update = 0, 0
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Misc/RewUpdate')
+        self._logger.register_key('Misc/CostUpdate')
+
+    def _adv_lagrange(self):
+        return None
+
+    def _surrogate_kind(self) -> int:
+        a = self._cfgs.algo_cfgs
+        jc = self._window_means()[1]
+        if jc <= a.cost_limit + a.distance:
+            self._rew_update += 1
+            return LOSS_RATIO
+        self._cost_update += 1
+        return LOSS_COST
+
+    def _log_extra(self) -> None:
+        super()._log_extra()
+        self._logger.store({'Misc/RewUpdate': self._rew_update, 'Misc/CostUpdate': self._cost_update})
+
+
+ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO', 'FOCOPS',
+             'CPPOPID', 'TRPOPID', 'OnCRPO']

@@ -351,6 +351,39 @@ __global__ void lagrange_update_kernel(const double* __restrict__ window_sums, f
     state[0] = lam; state[1] = m; state[2] = v; state[3] = (float)t;
 }
 
+// PID-Lagrangian controller (common/pid_lagrange.py:L95-125), Python-float (fp64) arithmetic.
+// pid_state: [0] integral term, [1] EMA of delta, [2] EMA of Jc, [3] cost penalty, [4] deque length,
+// [5] deque head (oldest entry), [8 + i] ring buffer of the delayed cost EMAs (capacity d_delay <= 56).
+// lagrange_state[0] <- (float) cost penalty = the multiplier the update kernels read.
+__global__ void pid_lagrange_kernel(const double* __restrict__ window_sums, double kp, double ki, double kd,
+                                    int d_delay, double a_p, double a_d, int sum_norm, int diff_norm,
+                                    double penalty_max, double cost_limit, double* __restrict__ st,
+                                    float* __restrict__ lagrange_state, int* __restrict__ nan_flag) {
+    if (threadIdx.x != 0) return;
+    const double cnt = window_sums[3];
+    if (!(cnt > 0.0)) { *nan_flag = 1; return; }
+    const double jc = window_sums[1] / cnt;
+    // separately rounded fp64 operations (no FMA contraction): bit-identical to the Python floats
+    const double delta = __dadd_rn(jc, -cost_limit);
+    double pid_i = fmax(0.0, __dadd_rn(st[0], __dmul_rn(delta, ki)));
+    if (diff_norm) pid_i = fmax(0.0, fmin(1.0, pid_i));
+    double delta_p = __dmul_rn(st[1], a_p);
+    delta_p = __dadd_rn(delta_p, __dmul_rn(__dadd_rn(1.0, -a_p), delta));
+    double cost_d = __dmul_rn(st[2], a_d);
+    cost_d = __dadd_rn(cost_d, __dmul_rn(__dadd_rn(1.0, -a_d), jc));
+    int n = (int)st[4], head = (int)st[5];
+    const double oldest = st[8 + head];
+    const double pid_d = fmax(0.0, __dadd_rn(cost_d, -oldest));
+    const double pid_o = __dadd_rn(__dadd_rn(__dmul_rn(kp, delta_p), pid_i), __dmul_rn(kd, pid_d));
+    double pen = fmax(0.0, pid_o);
+    if (diff_norm) pen = fmin(1.0, pen);
+    if (!(diff_norm || sum_norm)) pen = fmin(pen, penalty_max);
+    if (n < d_delay) { st[8 + (head + n) % d_delay] = cost_d; ++n; }
+    else { st[8 + head] = cost_d; head = (head + 1) % d_delay; }
+    st[0] = pid_i; st[1] = delta_p; st[2] = cost_d; st[3] = pen; st[4] = (double)n; st[5] = (double)head;
+    lagrange_state[0] = (float)pen;
+}
+
 // KL early stop: eval_out[0] = sum KL (over samples and action dims), eval_out[4] = sample count.
 // kl_state[4] = {last kl, iterations executed, stopped flag as float, 0}
 __global__ void kl_check_kernel(const double* __restrict__ eval_out, float target_kl, int early_stop,
@@ -564,6 +597,20 @@ int osb_lagrange_update(const double* window_sums, float cost_limit, float lambd
                         float upper_bound, float* state, int* nan_flag, void* stream) {
     OSB_CHECK_ARG(window_sums && state && nan_flag, "null pointer");
     lagrange_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(window_sums, cost_limit, lambda_lr, upper_bound, state, nan_flag);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+int osb_pid_lagrange_update(const double* window_sums, double pid_kp, double pid_ki, double pid_kd,
+                            int pid_d_delay, double pid_delta_p_ema_alpha, double pid_delta_d_ema_alpha,
+                            int sum_norm, int diff_norm, double penalty_max, double cost_limit,
+                            double* pid_state, float* lagrange_state, int* nan_flag, void* stream) {
+    OSB_CHECK_ARG(window_sums && pid_state && lagrange_state && nan_flag, "null pointer");
+    OSB_CHECK_ARG(pid_d_delay >= 1 && pid_d_delay <= 56, "pid_d_delay must be in [1, 56]");
+    pid_lagrange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(window_sums, pid_kp, pid_ki, pid_kd, pid_d_delay,
+                                                           pid_delta_p_ema_alpha, pid_delta_d_ema_alpha, sum_norm,
+                                                           diff_norm, penalty_max, cost_limit, pid_state,
+                                                           lagrange_state, nan_flag);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }

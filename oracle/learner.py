@@ -237,3 +237,49 @@ def cpo_step_direction(case, xHx, x, A, B, q, p, r, s, ep_costs, target_kl):
         return 1.0 / (lam_star + 1e-8) * (x - nu_star * p), lam_star, nu_star
     nu_star = float(np.sqrt(2 * target_kl / (s + 1e-8)))
     return -nu_star * p, 0.0, nu_star
+
+
+def pcpo_step_direction(x_hx, hx, p, r, s, ep_costs, target_kl):
+    """PCPO projection step (second_order/pcpo.py:L99-106): sqrt(2 delta / (q + 1e-8)) * H x
+    - max(0, (sqrt(2 delta / q) * r + c) / s) * p, with q = xHx; hx, p torch vectors, scalars fp32."""
+    q = torch.tensor(x_hx, dtype=torch.float32)
+    r_, s_ = torch.tensor(r, dtype=torch.float32), torch.tensor(s, dtype=torch.float32)
+    return (torch.sqrt(2 * target_kl / (q + 1e-8)) * hx
+            - torch.clamp_min((torch.sqrt(2 * target_kl / q) * r_ + ep_costs) / s_, torch.tensor(0.0)) * p)
+
+
+class PIDLagrangian:
+    """PID controller of the multiplier (common/pid_lagrange.py:L54-125), Python floats throughout."""
+
+    def __init__(self, pid_kp, pid_ki, pid_kd, pid_d_delay, pid_delta_p_ema_alpha, pid_delta_d_ema_alpha,
+                 sum_norm, diff_norm, penalty_max, lagrangian_multiplier_init, cost_limit):
+        self.kp, self.ki, self.kd, self.delay = pid_kp, pid_ki, pid_kd, int(pid_d_delay)
+        self.a_p, self.a_d = pid_delta_p_ema_alpha, pid_delta_d_ema_alpha
+        self.sum_norm, self.diff_norm, self.penalty_max = bool(sum_norm), bool(diff_norm), penalty_max
+        self.cost_limit = cost_limit
+        self.pid_i = float(lagrangian_multiplier_init)
+        self.cost_ds = [0.0]          # deque(maxlen=delay): oldest first
+        self.delta_p, self.cost_d, self.cost_penalty = 0.0, 0.0, 0.0
+
+    @property
+    def lagrangian_multiplier(self) -> float:
+        return self.cost_penalty
+
+    def pid_update(self, ep_cost_avg: float) -> float:
+        delta = float(ep_cost_avg - self.cost_limit)
+        self.pid_i = max(0.0, self.pid_i + delta * self.ki)
+        if self.diff_norm:
+            self.pid_i = max(0.0, min(1.0, self.pid_i))
+        self.delta_p = self.delta_p * self.a_p + (1 - self.a_p) * delta
+        self.cost_d = self.cost_d * self.a_d + (1 - self.a_d) * float(ep_cost_avg)
+        pid_d = max(0.0, self.cost_d - self.cost_ds[0])
+        pid_o = self.kp * self.delta_p + self.pid_i + self.kd * pid_d
+        self.cost_penalty = max(0.0, pid_o)
+        if self.diff_norm:
+            self.cost_penalty = min(1.0, self.cost_penalty)
+        if not (self.diff_norm or self.sum_norm):
+            self.cost_penalty = min(self.cost_penalty, self.penalty_max)
+        self.cost_ds.append(self.cost_d)
+        if len(self.cost_ds) > self.delay:
+            self.cost_ds.pop(0)
+        return self.cost_penalty

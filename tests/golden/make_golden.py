@@ -284,12 +284,12 @@ def gen_update_focops():
              **{'data_' + k: v for k, v in data.items()})
 
 
-def gen_cpo():
-    """CPO: Fisher-vector product, CG solve and one full actor+critic update of the reference."""
+def gen_cpo(name='CPO', fname='update_cpo.npz', seed=7, cost_limit=2.0):
+    """CPO / PCPO: Fisher-vector product, CG solve and one full actor+critic update of the reference."""
     from omnisafe.utils.math import conjugate_gradients as ref_cg
 
-    N, T, O, A, seed = 8, 24, 12, 3, 7
-    algo = _build_algo('CPO', N, T, O, A, seed, extra_algo={'cost_limit': 2.0}, tmax=8, term_prob=0.05)
+    N, T, O, A = 8, 24, 12, 3
+    algo = _build_algo(name, N, T, O, A, seed, extra_algo={'cost_limit': cost_limit}, tmax=8, term_prob=0.05)
     theta0 = _flat_theta(algo._actor_critic)
     algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
     data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
@@ -310,11 +310,36 @@ def gen_cpo():
         'Misc/AcceptanceStep', 'Misc/Alpha', 'Misc/FinalStepNorm', 'Misc/xHx', 'Misc/H_inv_g',
         'Misc/gradient_norm', 'Misc/cost_gradient_norm', 'Misc/Lambda_star', 'Misc/Nu_star',
         'Misc/OptimCase', 'Misc/A', 'Misc/B', 'Misc/q', 'Misc/r', 'Misc/s')}
-    np.savez(os.path.join(OUT, 'update_cpo.npz'), N=N, T=T, O=O, A=A, theta0=theta0,
+    np.savez(os.path.join(OUT, fname), N=N, T=T, O=O, A=A, seed=seed, theta0=theta0,
              theta1=_flat_theta(algo._actor_critic), vec=vec.numpy(), fvp=fv, bvec=bvec.numpy(), xcg=xcg,
-             ep_cost=ep_cost, cost_limit=2.0, perms=perms, batch_size=32, update_iters=2,
+             ep_cost=ep_cost, cost_limit=cost_limit, perms=perms, batch_size=32, update_iters=2,
              cg_damping=0.1, cg_iters=15, target_kl=0.01, kl=_last(lg, 'Train/KL'),
              **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
+
+
+def gen_pid():
+    """PIDLagrangian.pid_update (common/pid_lagrange.py:L95-125) over cost sequences that exercise the
+    integral clamp, the delayed derivative (deque roll-over) and the three normalisation modes."""
+    from omnisafe.common.pid_lagrange import PIDLagrangian
+
+    rng = np.random.default_rng(5)
+    base = dict(pid_kp=0.1, pid_ki=0.01, pid_kd=0.01, pid_d_delay=10, pid_delta_p_ema_alpha=0.95,
+                pid_delta_d_ema_alpha=0.95, sum_norm=True, diff_norm=False, penalty_max=100.0,
+                lagrangian_multiplier_init=0.001, cost_limit=25.0)
+    cfgs = [base, dict(base, diff_norm=True), dict(base, sum_norm=False, penalty_max=0.3, pid_kd=0.5, pid_d_delay=3),
+            dict(base, pid_d_delay=1, pid_ki=0.1)]
+    costs = np.concatenate([np.linspace(0, 60, 25), 25 + 20 * rng.standard_normal(40), np.linspace(60, 0, 25)])
+    out = {'costs': costs, 'n_cfgs': len(cfgs)}
+    for i, cfg in enumerate(cfgs):
+        pid = PIDLagrangian(**cfg)
+        lam = []
+        for c in costs:
+            pid.pid_update(float(c))
+            lam.append(pid.lagrangian_multiplier)
+        out[f'lam_{i}'] = np.asarray(lam, np.float64)
+        for k, v in cfg.items():
+            out[f'cfg_{i}_{k}'] = v
+    np.savez(os.path.join(OUT, 'pid_lagrange.npz'), **out)
 
 
 if __name__ == '__main__':
@@ -326,4 +351,6 @@ if __name__ == '__main__':
     gen_update_ppolag(algo)
     gen_update_focops()
     gen_cpo()
+    gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)
+    gen_pid()
     print('golden fixtures written to', OUT)

@@ -19,7 +19,8 @@ def _custom(tmp, N=64, T=32, epochs=3, **algo):
     }
 
 
-@pytest.mark.parametrize('algo', ['PPOLag', 'TRPOLag', 'CPO', 'FOCOPS', 'PPO', 'TRPO', 'RCPO', 'NaturalPG', 'PolicyGradient'])
+@pytest.mark.parametrize('algo', ['PPOLag', 'TRPOLag', 'CPO', 'FOCOPS', 'PPO', 'TRPO', 'RCPO', 'NaturalPG', 'PolicyGradient',
+                                  'PCPO', 'CPPOPID', 'TRPOPID', 'OnCRPO'])
 def test_agent_trains_and_logs(cuda, tmp_path, algo):
     import omnisafe_b200
 
@@ -57,21 +58,22 @@ def test_ppolag_learning_signal(cuda, tmp_path):
     assert ret[-1] > ret[0] + 0.05, ret
 
 
-def test_cpo_update_golden(cuda, tmp_path, golden_dir):
-    """CPO._update of the unmodified reference vs ours on identical data: same case analysis,
-    same step, same parameters afterwards."""
+@pytest.mark.parametrize('name,fname', [('CPO', 'update_cpo.npz'), ('PCPO', 'update_pcpo.npz')])
+def test_cpo_update_golden(cuda, tmp_path, golden_dir, name, fname):
+    """CPO._update / PCPO._update of the unmodified reference vs ours on identical data: same case
+    analysis, same step, same parameters afterwards."""
     import omnisafe_b200
 
-    g = np.load(os.path.join(golden_dir, 'update_cpo.npz'))
+    g = np.load(os.path.join(golden_dir, fname))
     N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
     cfg = {
-        'seed': 7,
+        'seed': int(g['seed']) if 'seed' in g.files else 7,
         'train_cfgs': {'device': 'cuda', 'vector_env_nums': N, 'total_steps': N * T * 2},
-        'algo_cfgs': {'steps_per_epoch': N * T, 'batch_size': 32, 'update_iters': 2, 'cost_limit': 2.0},
+        'algo_cfgs': {'steps_per_epoch': N * T, 'batch_size': 32, 'update_iters': 2, 'cost_limit': float(g['cost_limit'])},
         'logger_cfgs': {'log_dir': str(tmp_path), 'window_lens': 10, 'use_tensorboard': False},
         'env_cfgs': {'obs_dim': O, 'act_dim': A, 'max_episode_steps': 8, 'term_prob': 0.05},
     }
-    algo = omnisafe_b200.Agent('CPO', 'SyntheticBox-v0', custom_cfgs=cfg).agent
+    algo = omnisafe_b200.Agent(name, 'SyntheticBox-v0', custom_cfgs=cfg).agent
     algo._actor_critic.load_flat(g['theta0'])
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
 
@@ -99,3 +101,29 @@ def test_cpo_update_golden(cuda, tmp_path, golden_dir):
     # by a few lr (1e-3) between two correct fp32 implementations: allow < 0.1 % such elements.
     bad = ~np.isclose(got, want, rtol=2e-3, atol=2e-5)
     assert bad.mean() < 1e-3 and np.abs(got - want).max() < 5e-3, (bad.sum(), np.abs(got - want).max())
+
+
+def test_pid_lagrange_kernel_golden(cuda, golden_dir):
+    """osb_pid_lagrange_update vs the reference PIDLagrangian over the recorded cost sequences: the
+    fp64 penalty bit-for-bit, the fp32 multiplier the kernels read = its rounding."""
+    from omnisafe_b200.common.pid_lagrange import PIDLagrangian
+
+    g = np.load(os.path.join(golden_dir, 'pid_lagrange.npz'))
+    keys = ('pid_kp', 'pid_ki', 'pid_kd', 'pid_d_delay', 'pid_delta_p_ema_alpha', 'pid_delta_d_ema_alpha',
+            'sum_norm', 'diff_norm', 'penalty_max', 'lagrangian_multiplier_init', 'cost_limit')
+    for i in range(int(g['n_cfgs'])):
+        pid = PIDLagrangian(**{k: g[f'cfg_{i}_{k}'].item() for k in keys}, device=cuda)
+        pens, lams = [], []
+        for c in g['costs']:
+            ws = torch.tensor([0.0, float(c) * 8.0, 0.0, 8.0], dtype=torch.float64, device=cuda)
+            pid.pid_update(ws)
+            pens.append(pid.pid_state[3].clone())
+            lams.append(pid.state[0].clone())
+        pens = torch.stack(pens).cpu().numpy()
+        lams = torch.stack(lams).cpu().numpy()
+        np.testing.assert_array_equal(pens, g[f'lam_{i}'])
+        np.testing.assert_array_equal(lams, g[f'lam_{i}'].astype(np.float32))
+        assert int(pid.nan_flag) == 0
+    empty = torch.zeros(4, dtype=torch.float64, device=cuda)
+    pid.pid_update(empty)
+    assert int(pid.nan_flag) == 1

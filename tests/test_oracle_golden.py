@@ -169,3 +169,48 @@ def test_focops_update_golden(golden_dir):
     np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(st['loss_pi'], g['loss_pi'], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7)
+
+
+def test_pid_lagrange_golden(golden_dir):
+    """oracle PIDLagrangian vs the reference class over the recorded cost sequences (bit-exact: both are
+    Python-float recurrences)."""
+    from oracle.learner import PIDLagrangian
+
+    g = np.load(os.path.join(golden_dir, 'pid_lagrange.npz'))
+    keys = ('pid_kp', 'pid_ki', 'pid_kd', 'pid_d_delay', 'pid_delta_p_ema_alpha', 'pid_delta_d_ema_alpha',
+            'sum_norm', 'diff_norm', 'penalty_max', 'lagrangian_multiplier_init', 'cost_limit')
+    for i in range(int(g['n_cfgs'])):
+        cfg = {k: g[f'cfg_{i}_{k}'].item() for k in keys}
+        pid = PIDLagrangian(**cfg)
+        lam = [pid.pid_update(float(c)) for c in g['costs']]
+        np.testing.assert_array_equal(np.asarray(lam), g[f'lam_{i}'])
+
+
+def test_pcpo_step_golden(golden_dir):
+    """oracle PCPO projection step on the golden data reproduces the reference's logged q, r, s and,
+    through the accepted line-search fraction, its final step norm."""
+    import torch
+
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_pcpo.npz')
+    O, A = int(g['O']), int(g['A'])
+    L = ol.Learner(g['theta0'], O, A, lr_actor=None, lr_critic=1e-3)
+    obs, act, logp = (torch.as_tensor(data[k]) for k in ('obs', 'act', 'logp'))
+    damping, iters, kl = float(g['cg_damping']), int(g['cg_iters']), float(g['target_kl'])
+    fvp = lambda v: L.fvp(v, obs, damping)   # noqa: E731
+    L.zero_grad('actor')
+    L.loss_pi_plain(obs, act, logp, torch.as_tensor(data['adv_r'])).backward()
+    grads = -L.flat_grad('actor')
+    x = ol.conjugate_gradients(fvp, grads.numpy(), iters)
+    hx = fvp(x)
+    xhx = float(x.dot(hx))
+    L.zero_grad('actor')
+    L.loss_pi_cost(obs, act, logp, torch.as_tensor(data['adv_c'])).backward()
+    b = L.flat_grad('actor')
+    p = ol.conjugate_gradients(fvp, b.numpy(), iters)
+    r, s = float(grads.dot(p)), float(b.dot(p))
+    np.testing.assert_allclose([xhx, r, s], [g['misc_q'][-1], g['misc_r'][-1], g['misc_s'][-1]], rtol=2e-3)
+    step = ol.pcpo_step_direction(xhx, hx, p, r, s, float(g['ep_cost']) - float(g['cost_limit']), kl)
+    frac = 0.8 ** (int(g['misc_AcceptanceStep'][-1]) - 1)
+    np.testing.assert_allclose(float((frac * step).norm()), g['misc_FinalStepNorm'][-1], rtol=5e-3)
