@@ -42,6 +42,17 @@ int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const 
                  double gamma, double lam, double lam_c, double penalty_coef, float* adv_r,
                  float* adv_c, float* tv_r, float* tv_c, float* disc_ret, double* workspace,
                  double* sums, void* stream);
+/* osb_gae_dual with the reference's other advantage estimators (onpolicy_buffer.py:L299-331):
+ * estimator 0 = 'gae', 1 = 'gae-rtg' (targets = discounted reward-to-go of the penalised path incl.
+ * its bootstrap slot), 2 = 'plain' (advantage = one-step delta, targets = reward-to-go), 3 = 'vtrace'
+ * (on-policy V-trace, rho = c = 1: targets v_t = V_t + delta_t + gamma (v_{t+1} - V_{t+1}), advantage
+ * r_t + gamma v_{t+1} - V_t; fp32 replay of the reference recurrence from an fp64 scan carry).
+ * For 1 / 2 disc_ret shares the reward-to-go scan: pass NULL unless penalty_coef == 0. */
+int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, const float* val_c,
+                     const uint8_t* flags, const float* boot_r, const float* boot_c, int T, int N,
+                     double gamma, double lam, double lam_c, double penalty_coef, int estimator,
+                     float* adv_r, float* adv_c, float* tv_r, float* tv_c, float* disc_ret,
+                     double* workspace, double* sums, void* stream);
 /* moments[4] <- {mean_r, std_r + 1e-8, mean_c, 1}: the statistics VectorOnPolicyBuffer.get()
  * standardises with (vector_onpolicy_buffer.py:L131-136, utils/distributed.py:L382-388). */
 int osb_adv_moments(const double* sums, int standardize_r, int standardize_c, float* moments,

@@ -20,9 +20,8 @@ class VectorOnPolicyBuffer:
                  num_envs: int = 1, device='cuda', keep_discounted_ret: bool = True) -> None:
         if num_envs < 1:
             raise ValueError('num_envs must be greater than 0.')
-        assert advantage_estimator == 'gae', (
-            "only adv_estimation_method='gae' is implemented on the B200 path "
-            "(gae-rtg / vtrace / plain are §8(f) 'next' rows)")
+        assert advantage_estimator in ('gae', 'gae-rtg', 'vtrace', 'plain')      # onpolicy_buffer.py:L122
+        self._estimator = {'gae': 0, 'gae-rtg': 1, 'plain': 2, 'vtrace': 3}[advantage_estimator]
         assert penalty_coefficient >= 0, 'penalty_coefficient must be non-negative!'
         T, N, O, A = int(size), int(num_envs), int(obs_dim), int(act_dim)
         dev = torch.device(device)
@@ -67,12 +66,14 @@ class VectorOnPolicyBuffer:
     def finish_paths(self) -> None:
         """All finish_path calls of one epoch (onpolicy_buffer.py:L148-203) in one launch."""
         d = self.data
-        lib().osb_gae_dual(ptr(d['reward']), ptr(d['cost']), ptr(d['value_r']), ptr(d['value_c']),
-                           ptr(d['flags']), ptr(d['boot_r']), ptr(d['boot_c']), self.T, self.N,
-                           self._gamma, self._lam, self._lam_c, self._penalty,
-                           ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']),
-                           ptr(d['target_value_c']), ptr(d['discounted_ret']), ptr(self._ws),
-                           ptr(self.adv_sums), current_stream())
+        # the reward-to-go estimators share their scan with discounted_ret: identical when penalty == 0
+        ret = d['discounted_ret'] if (self._estimator in (0, 3) or self._penalty == 0.0) else None
+        lib().osb_adv_estimate(ptr(d['reward']), ptr(d['cost']), ptr(d['value_r']), ptr(d['value_c']),
+                               ptr(d['flags']), ptr(d['boot_r']), ptr(d['boot_c']), self.T, self.N,
+                               self._gamma, self._lam, self._lam_c, self._penalty, self._estimator,
+                               ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']),
+                               ptr(d['target_value_c']), ptr(ret), ptr(self._ws),
+                               ptr(self.adv_sums), current_stream())
 
     def finalize_statistics(self) -> None:
         """Turn the (already all-reduced) fp64 sums into the moments the update kernels consume

@@ -79,11 +79,22 @@ __device__ __forceinline__ void gae_load_tile(const GaeArgs& p, int env, bool en
 
 // MULTI = more than one 128-step tile: prefetches the next tile (more registers, 1 CTA per SM);
 // the single-tile instantiation fits 64 registers so that two CTAs share an SM.
-template <bool MULTI>
-__global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeArgs p) {
-    __shared__ double sa[3 * GC * GPAD];
-    __shared__ double sb[3 * GC * GPAD];
-    __shared__ double carry[3 * GE];
+// EST = advantage estimator (onpolicy_buffer.py:L299-331):
+//   0 'gae'      adv = scan(delta, gamma*lam),  target = adv + V                    (L299-303)
+//   1 'gae-rtg'  adv = scan(delta, gamma*lam),  target = discount_cumsum(rewards)   (L305-310)
+//   2 'plain'    adv = delta,                   target = discount_cumsum(rewards)   (L328-331)
+//   3 'vtrace'   on-policy V-trace (behaviour == target policy, so rho = c = 1, L312-326, L338-405):
+//                v_t = V_t + delta_t + gamma (v_{t+1} - V_{t+1}),  adv_t = r_t + gamma v_{t+1} - V_t,
+//                target = v.  The scan carries e_t = v_t - V_t (the lambda = 1 GAE recurrence) in fp64;
+//                the replay pass redoes the reference's fp32 operations from that carry.
+// where `rewards` is the penalised reward path INCLUDING its bootstrap slot (finish_path subtracts
+// penalty * costs in place, L185) and the cost targets use the same gamma (L192-196).
+template <bool MULTI, int EST>
+__global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 : 2) gae_dual_kernel(GaeArgs p) {
+    constexpr int NQ = (EST == 0 || EST == 3) ? 3 : 4;    // scanned quantities: adv_r, adv_c, reward-to-go, cost-to-go
+    __shared__ double sa[NQ * GC * GPAD];
+    __shared__ double sb[NQ * GC * GPAD];
+    __shared__ double carry[NQ * GE];
     __shared__ double red[3 * (GTHREADS / 32)];
     __shared__ int s_last;
 
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
     const int N = p.N, T = p.T;
     const int ntiles = (T + GT - 1) / GT;
 
-    if (lin < 3 * GE) carry[lin] = 0.0;
+    if (lin < NQ * GE) carry[lin] = 0.0;
 
     double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
     GaeTile cur;
@@ -106,7 +117,7 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
         const int t0 = T - (k + 1) * GT + y * GL;  // first step of my chunk (may be < 0)
         if (!MULTI && k > 0) gae_load_tile(p, env, env_ok, t0, cur);   // no prefetch in the 2-CTA/SM variant
         // fp32 deltas with the reference's three separately rounded ops; bootstrap at path ends.
-        float dr[GL], dc[GL], bootr[GL], r[GL], vr[GL], vc[GL];
+        float dr[GL], dc[GL], bootr[GL], bootc[GL], r[GL], c[GL], vr[GL], vc[GL];
         bool end[GL], valid[GL];
 #pragma unroll
         for (int i = 0; i < GL; ++i) {
@@ -120,16 +131,23 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
                 nr = term ? 0.f : __ldg(p.boot_r + idx);
                 nc = term ? 0.f : __ldg(p.boot_c + idx);
             }
-            bootr[i] = nr;
             const float rp = __fadd_rn(cur.r[i], -__fmul_rn(p.pen, cur.c[i]));
+            // reward-to-go estimators run on the penalised path, bootstrap slot included
+            bootr[i] = (EST == 0 || EST == 3) ? nr : __fadd_rn(nr, -__fmul_rn(p.pen, nc));
+            bootc[i] = nc;
             dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -cur.vr[i]);
             dc[i] = __fadd_rn(__fadd_rn(cur.c[i], __fmul_rn(p.gamma_f, nc)), -cur.vc[i]);
-            r[i] = cur.r[i]; vr[i] = cur.vr[i]; vc[i] = cur.vc[i];
+            r[i] = (EST == 0 || EST == 3) ? cur.r[i] : rp; c[i] = cur.c[i]; vr[i] = cur.vr[i]; vc[i] = cur.vc[i];
         }
+        const float cur_vr_last = cur.vr[GL], cur_vc_last = cur.vc[GL];
+        float nvr[GL], nvc[GL];   // V_{t+1} inside the path (V-trace replay)
+#pragma unroll
+        for (int i = 0; i < GL; ++i) { nvr[i] = cur.vr[i + 1]; nvc[i] = cur.vc[i + 1]; }
         // prefetch the next (earlier) tile while this one is scanned
         if (MULTI && k + 1 < ntiles) gae_load_tile(p, env, env_ok, t0 - GT, cur);
         // pass 1: fold the chunk into affine maps (a, b) per quantity.
-        double ar = 1.0, br = 0.0, ac = 1.0, bc = 0.0, ag = 1.0, bg = 0.0;
+        const double glr = (EST == 3) ? p.g : p.gl_r, glc = (EST == 3) ? p.g : p.gl_c;
+        double ar = 1.0, br = 0.0, ac = 1.0, bc = 0.0, ag = 1.0, bg = 0.0, bh = 0.0;   // (ag, bh): cost-to-go
 #pragma unroll
         for (int i = GL - 1; i >= 0; --i) {
             if (valid[i]) {
@@ -137,20 +155,23 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
                     ar = 0.0; br = (double)dr[i];
                     ac = 0.0; bc = (double)dc[i];
                     ag = 0.0; bg = (double)r[i] + p.g * (double)bootr[i];
+                    if (EST != 0) bh = (double)c[i] + p.g * (double)bootc[i];
                 } else {
-                    br = (double)dr[i] + p.gl_r * br; ar = p.gl_r * ar;
-                    bc = (double)dc[i] + p.gl_c * bc; ac = p.gl_c * ac;
+                    br = (double)dr[i] + glr * br; ar = glr * ar;
+                    bc = (double)dc[i] + glc * bc; ac = glc * ac;
                     bg = (double)r[i] + p.g * bg;     ag = p.g * ag;
+                    if (EST != 0) bh = (double)c[i] + p.g * bh;
                 }
             }
         }
         sa[(0 * GC + y) * GPAD + x] = ar; sb[(0 * GC + y) * GPAD + x] = br;
         sa[(1 * GC + y) * GPAD + x] = ac; sb[(1 * GC + y) * GPAD + x] = bc;
         sa[(2 * GC + y) * GPAD + x] = ag; sb[(2 * GC + y) * GPAD + x] = bg;
+        if (EST != 0) { sa[(3 * GC + y) * GPAD + x] = ag; sb[(3 * GC + y) * GPAD + x] = bh; }
         __syncthreads();
         // transposed role: warp tw owns env tw of the block, lane tl = chunk index.
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = (EST == 2 ? 2 : 0); q < NQ; ++q) {
             double a = sa[(q * GC + tl) * GPAD + tw];
             double b = sb[(q * GC + tl) * GPAD + tw];
 #pragma unroll
@@ -172,24 +193,53 @@ __global__ void __launch_bounds__(GTHREADS, MULTI ? 1 : 2) gae_dual_kernel(GaeAr
         double Ar = sb[(0 * GC + y) * GPAD + x];
         double Ac = sb[(1 * GC + y) * GPAD + x];
         double Ag = sb[(2 * GC + y) * GPAD + x];
+        double Ah = (EST == 1 || EST == 2) ? sb[(3 * GC + y) * GPAD + x] : 0.0;
+        // V-trace replay state: v_{t+1} of the step after this chunk (fp32, = V + e from the scan)
+        float lv_r = 0.f, lv_c = 0.f;
+        if (EST == 3) {
+            lv_r = (float)((double)cur_vr_last + Ar);
+            lv_c = (float)((double)cur_vc_last + Ac);
+        }
 #pragma unroll
         for (int i = GL - 1; i >= 0; --i) {
-            if (valid[i]) {
+            if (EST == 3) {
+                if (valid[i]) {
+                    // values[index + 1] and last_v_s: the bootstrap slot at a path end, else V_{t+1} / v_{t+1}
+                    const float vnr = end[i] ? bootr[i] : nvr[i], vnc = end[i] ? bootc[i] : nvc[i];
+                    const float lr = end[i] ? bootr[i] : lv_r, lc = end[i] ? bootc[i] : lv_c;
+                    const size_t idx = (size_t)(t0 + i) * N + env;
+                    // policy_advantage = clip_rho * (r + gamma * v_{t+1} - V_t)        (L402-403)
+                    const float rp = __fadd_rn(r[i], -__fmul_rn(p.pen, c[i]));
+                    const float o_ar = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, lr)), -vr[i]);
+                    const float o_ac = __fadd_rn(__fadd_rn(c[i], __fmul_rn(p.gamma_f, lc)), -vc[i]);
+                    // v_s[t] += delta + gamma * c * (last_v_s - V_{t+1})                 (L394-397)
+                    lv_r = __fadd_rn(vr[i], __fadd_rn(dr[i], __fmul_rn(p.gamma_f, __fadd_rn(lr, -vnr))));
+                    lv_c = __fadd_rn(vc[i], __fadd_rn(dc[i], __fmul_rn(p.gamma_f, __fadd_rn(lc, -vnc))));
+                    Ag = end[i] ? __dadd_rn((double)r[i], __dmul_rn(p.g, (double)bootr[i]))
+                                : __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
+                    p.adv_r[idx] = o_ar; p.adv_c[idx] = o_ac;
+                    p.tv_r[idx] = lv_r;  p.tv_c[idx] = lv_c;
+                    if (p.disc_ret) p.disc_ret[idx] = (float)Ag;
+                    st_r += (double)o_ar; st_r2 += (double)o_ar * (double)o_ar; st_c += (double)o_ac;
+                }
+            } else if (valid[i]) {
                 if (end[i]) {
                     Ar = (double)dr[i];
                     Ac = (double)dc[i];
                     Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, (double)bootr[i]));
+                    if (EST != 0) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, (double)bootc[i]));
                 } else {
                     Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
                     Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
                     Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
+                    if (EST != 0) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, Ah));
                 }
                 const size_t idx = (size_t)(t0 + i) * N + env;
-                const float o_ar = (float)Ar, o_ac = (float)Ac;
+                const float o_ar = (EST == 2) ? dr[i] : (float)Ar, o_ac = (EST == 2) ? dc[i] : (float)Ac;
                 p.adv_r[idx] = o_ar;
                 p.adv_c[idx] = o_ac;
-                p.tv_r[idx] = (float)(Ar + (double)vr[i]);
-                p.tv_c[idx] = (float)(Ac + (double)vc[i]);
+                p.tv_r[idx] = (EST == 0) ? (float)(Ar + (double)vr[i]) : (float)Ag;
+                p.tv_c[idx] = (EST == 0) ? (float)(Ac + (double)vc[i]) : (float)Ah;
                 if (p.disc_ret) p.disc_ret[idx] = (float)Ag;
                 st_r += (double)o_ar;
                 st_r2 += (double)o_ar * (double)o_ar;
@@ -312,12 +362,15 @@ extern "C" {
 // partials [blocks][4] + one 8-byte ticket slot (zero-initialised by the caller, self-resetting)
 int osb_gae_workspace_doubles(int n_envs) { return ((n_envs + GE - 1) / GE) * 4 + 8; }
 
-int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const float* val_c,
-                 const uint8_t* flags, const float* boot_r, const float* boot_c, int T, int N,
-                 double gamma, double lam, double lam_c, double penalty_coef, float* adv_r,
-                 float* adv_c, float* tv_r, float* tv_c, float* disc_ret, double* workspace,
-                 double* sums, void* stream) {
+int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, const float* val_c,
+                     const uint8_t* flags, const float* boot_r, const float* boot_c, int T, int N,
+                     double gamma, double lam, double lam_c, double penalty_coef, int estimator,
+                     float* adv_r, float* adv_c, float* tv_r, float* tv_c, float* disc_ret,
+                     double* workspace, double* sums, void* stream) {
     OSB_CHECK_ARG(T > 0 && N > 0, "T, N must be positive");
+    OSB_CHECK_ARG(estimator >= 0 && estimator <= 3, "estimator: 0 gae, 1 gae-rtg, 2 plain, 3 vtrace");
+    OSB_CHECK_ARG(estimator == 0 || estimator == 3 || disc_ret == nullptr || penalty_coef == 0.0,
+                  "reward-to-go estimators share the scan with discounted_ret: needs penalty_coef == 0 or disc_ret == NULL");
     OSB_CHECK_ARG(rew && cost && val_r && val_c && flags && boot_r && boot_c, "null input slab");
     OSB_CHECK_ARG(adv_r && adv_c && tv_r && tv_c && workspace && sums, "null output");
     GaeArgs a;
@@ -335,12 +388,27 @@ int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const 
     // the 64-register instantiation (two CTAs per SM) wins at every T measured on B200: occupancy beats
     // the register-hungry prefetching variant, which is kept for experiments (OSB_GAE_PREFETCH=1)
     static const bool prefetch = getenv("OSB_GAE_PREFETCH") != nullptr;
-    if (prefetch && T > GT)
-        gae_dual_kernel<true><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    if (estimator == 1)
+        gae_dual_kernel<false, 1><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    else if (estimator == 2)
+        gae_dual_kernel<false, 2><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    else if (estimator == 3)
+        gae_dual_kernel<false, 3><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    else if (prefetch && T > GT)
+        gae_dual_kernel<true, 0><<<nblocks, dim3(GE, GC), 0, s>>>(a);
     else
-        gae_dual_kernel<false><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+        gae_dual_kernel<false, 0><<<nblocks, dim3(GE, GC), 0, s>>>(a);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
+}
+
+int osb_gae_dual(const float* rew, const float* cost, const float* val_r, const float* val_c,
+                 const uint8_t* flags, const float* boot_r, const float* boot_c, int T, int N,
+                 double gamma, double lam, double lam_c, double penalty_coef, float* adv_r,
+                 float* adv_c, float* tv_r, float* tv_c, float* disc_ret, double* workspace,
+                 double* sums, void* stream) {
+    return osb_adv_estimate(rew, cost, val_r, val_c, flags, boot_r, boot_c, T, N, gamma, lam, lam_c,
+                            penalty_coef, 0, adv_r, adv_c, tv_r, tv_c, disc_ret, workspace, sums, stream);
 }
 
 int osb_adv_moments(const double* sums, int standardize_r, int standardize_c, float* moments,

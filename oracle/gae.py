@@ -24,8 +24,9 @@ def discount_cumsum(x, discount: float) -> np.ndarray:
     return y
 
 
-def finish_path(rew, cost, val_r, val_c, last_r, last_c, gamma, lam, lam_c, pen=0.0):
-    """One path of OnPolicyBuffer.finish_path (onpolicy_buffer.py:L148-203, 'gae' L299-303).
+def finish_path(rew, cost, val_r, val_c, last_r, last_c, gamma, lam, lam_c, pen=0.0, estimator='gae'):
+    """One path of OnPolicyBuffer.finish_path (onpolicy_buffer.py:L148-203; estimators 'gae' L299-303,
+    'gae-rtg' L305-310, 'vtrace' L312-326, 'plain' L328-331).
 
     Inputs are float32 1-D arrays of one path; returns float32 (adv_r, tv_r, adv_c, tv_c, ret).
     """
@@ -37,9 +38,31 @@ def finish_path(rew, cost, val_r, val_c, last_r, last_c, gamma, lam, lam_c, pen=
     ret = discount_cumsum(rewards, gamma)[:-1].astype(f32)
     rewards = (rewards - f32(pen) * costs).astype(f32)
 
+    def vtrace(values, rews):
+        """_calculate_v_trace (onpolicy_buffer.py:L338-405) with policy == behaviour probabilities, so
+        rho = c = 1 exactly (L312-326): sequential fp32 arithmetic as torch executes it."""
+        n = len(rews) - 1
+        v_s = values[:-1].copy()
+        last = values[-1]
+        g32 = f32(gamma)
+        for i in range(n - 1, -1, -1):
+            delta = f32(f32(rews[i] + f32(g32 * values[i + 1])) - values[i])
+            v_s[i] = f32(v_s[i] + f32(delta + f32(g32 * f32(last - values[i + 1]))))
+            last = v_s[i]
+        v_next = np.concatenate([v_s[1:], values[-1:]])
+        adv = ((rews[:-1] + (g32 * v_next).astype(f32)).astype(f32) - values[:-1]).astype(f32)
+        return adv, v_s
+
     def adv_and_target(values, rews, lam_):
+        if estimator == 'vtrace':
+            return vtrace(values, rews)
         deltas = ((rews[:-1] + f32(gamma) * values[1:]).astype(f32) - values[:-1]).astype(f32)
+        if estimator == 'plain':
+            return deltas, discount_cumsum(rews, gamma)[:-1].astype(f32)
         adv = discount_cumsum(deltas, gamma * lam_)
+        if estimator == 'gae-rtg':
+            return adv.astype(f32), discount_cumsum(rews, gamma)[:-1].astype(f32)
+        assert estimator == 'gae'
         target = adv + values[:-1].astype(np.float64)
         return adv.astype(f32), target.astype(f32)
 
@@ -88,8 +111,9 @@ def dual_gae_slab(rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, la
     return {'adv_r': adv_r, 'adv_c': adv_c, 'tv_r': tv_r, 'tv_c': tv_c, 'disc_ret': ret}
 
 
-def dual_gae_per_path(rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, lam_c, pen=0.0):
-    """Slow cross-check: split every env column into paths and call finish_path on each."""
+def dual_gae_per_path(rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, lam_c, pen=0.0, estimator='gae'):
+    """Per-path restatement: split every env column into paths and call finish_path on each (the form the
+    reference executes; also the oracle of the 'gae-rtg' / 'plain' estimators)."""
     T, N = rew.shape
     out = {k: np.zeros((T, N), np.float32) for k in ('adv_r', 'adv_c', 'tv_r', 'tv_c', 'disc_ret')}
     for i in range(N):
@@ -102,7 +126,7 @@ def dual_gae_per_path(rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam
                 sl = slice(start, t + 1)
                 a_r, t_r, a_c, t_c, ret = finish_path(
                     rew[sl, i], cost[sl, i], val_r[sl, i], val_c[sl, i], lr, lc,
-                    gamma, lam, lam_c, pen)
+                    gamma, lam, lam_c, pen, estimator)
                 out['adv_r'][sl, i] = a_r; out['tv_r'][sl, i] = t_r
                 out['adv_c'][sl, i] = a_c; out['tv_c'][sl, i] = t_c
                 out['disc_ret'][sl, i] = ret

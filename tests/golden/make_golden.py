@@ -43,14 +43,14 @@ def gen_discount_cumsum():
     np.savez(os.path.join(OUT, 'discount_cumsum.npz'), **out)
 
 
-def gen_buffer_gae():
+def gen_buffer_gae(estimator='gae', fname='buffer_gae.npz', seed=2):
     """Drive the reference VectorOnPolicyBuffer with random data + random path ends."""
-    rng = np.random.default_rng(2)
+    rng = np.random.default_rng(seed)
     N, T, O, A = 6, 48, 3, 2
     gamma, lam, lam_c, pen = 0.99, 0.95, 0.9, 0.05
     buf = VectorOnPolicyBuffer(
         obs_space=Box(-1, 1, (O,)), act_space=Box(-1, 1, (A,)), size=T, gamma=gamma, lam=lam,
-        lam_c=lam_c, advantage_estimator='gae', penalty_coefficient=pen,
+        lam_c=lam_c, advantage_estimator=estimator, penalty_coefficient=pen,
         standardized_adv_r=True, standardized_adv_c=True, num_envs=N)
     rew = rng.random((T, N)).astype(np.float32)
     cost = (rng.random((T, N)) < 0.2).astype(np.float32)
@@ -78,7 +78,7 @@ def gen_buffer_gae():
     raw = {k: np.stack([b.data[k].numpy().copy() for b in buf.buffers], 1)  # -> [T, N]
            for k in ('adv_r', 'adv_c', 'target_value_r', 'target_value_c', 'discounted_ret')}
     data = buf.get()
-    np.savez(os.path.join(OUT, 'buffer_gae.npz'), rew=rew, cost=cost, val_r=val_r, val_c=val_c,
+    np.savez(os.path.join(OUT, fname), estimator=estimator, rew=rew, cost=cost, val_r=val_r, val_c=val_c,
              obs=obs, act=act, logp=logp, flags=flags, boot_r=boot_r, boot_c=boot_c,
              gamma=gamma, lam=lam, lam_c=lam_c, pen=pen,
              **{'raw_' + k: v for k, v in raw.items()},
@@ -346,6 +346,9 @@ if __name__ == '__main__':
     torch.set_num_threads(1)
     gen_discount_cumsum()
     gen_buffer_gae()
+    gen_buffer_gae('gae-rtg', 'buffer_gae_rtg.npz', seed=12)
+    gen_buffer_gae('plain', 'buffer_plain.npz', seed=13)
+    gen_buffer_gae('vtrace', 'buffer_vtrace.npz', seed=14)
     gen_normalizer()
     algo = gen_rollout()
     gen_update_ppolag(algo)

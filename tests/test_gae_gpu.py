@@ -10,11 +10,12 @@ from oracle import gae as ogae
 pytestmark = pytest.mark.gpu
 
 
-def _run_gae(dev, rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, lam_c, pen, std=(True, True)):
+def _run_gae(dev, rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, lam_c, pen, std=(True, True),
+             estimator='gae'):
     from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 
     T, N = rew.shape
-    buf = VectorOnPolicyBuffer(3, 2, T, gamma, lam, lam_c, 'gae', pen, std[0], std[1], num_envs=N, device=dev)
+    buf = VectorOnPolicyBuffer(3, 2, T, gamma, lam, lam_c, estimator, pen, std[0], std[1], num_envs=N, device=dev)
     for k, v in (('reward', rew), ('cost', cost), ('value_r', val_r), ('value_c', val_c),
                  ('flags', flags), ('boot_r', boot_r), ('boot_c', boot_c)):
         buf.data[k].copy_(torch.as_tensor(v))
@@ -62,6 +63,36 @@ def test_gae_golden_reference_buffer(cuda, golden_dir):
     np.testing.assert_allclose(got['adv_r'].cpu().numpy(), g['get_adv_r'], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(got['adv_c'].cpu().numpy(), g['get_adv_c'], rtol=1e-5, atol=1e-5)
     assert np.array_equal(got['obs'].shape, g['get_obs'].shape)
+
+
+@pytest.mark.parametrize('fname', ['buffer_gae_rtg.npz', 'buffer_plain.npz', 'buffer_vtrace.npz'])
+def test_other_estimators_golden_reference_buffer(cuda, golden_dir, fname):
+    """'gae-rtg' / 'plain' / 'vtrace' (onpolicy_buffer.py:L305-331, L338-405) vs the reference buffer
+    (penalty 0.05: the reward-to-go targets run on the penalised path, discounted_ret is not produced then)."""
+    g = np.load(os.path.join(golden_dir, fname))
+    buf = _run_gae(cuda, g['rew'], g['cost'], g['val_r'], g['val_c'], g['flags'], g['boot_r'], g['boot_c'],
+                   float(g['gamma']), float(g['lam']), float(g['lam_c']), float(g['pen']),
+                   estimator=str(g['estimator']))
+    for ours, ref in (('adv_r', 'raw_adv_r'), ('adv_c', 'raw_adv_c'), ('target_value_r', 'raw_target_value_r'),
+                      ('target_value_c', 'raw_target_value_c')):
+        a, b = buf.data[ours].cpu().numpy(), g[ref]
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-6, err_msg=ours)
+        # V-trace replays an fp32 recurrence from an fp64 scan carry: 1-ulp differences at chunk boundaries
+        assert (a == b).mean() > (0.7 if 'vtrace' in fname else 0.99), (ours, (a == b).mean())
+
+
+@pytest.mark.parametrize('estimator', ['gae-rtg', 'plain', 'vtrace'])
+@pytest.mark.parametrize('T,N', [(1, 1), (127, 40), (300, 97), (512, 256)])
+def test_other_estimators_vs_oracle(cuda, T, N, estimator):
+    rng = np.random.default_rng(T * 77 + N)
+    case = _rand_case(rng, T, N)
+    buf = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.0, estimator=estimator)
+    ref = ogae.dual_gae_per_path(*case, 0.99, 0.95, 0.9, 0.0, estimator=estimator)
+    for ours, r in (('adv_r', 'adv_r'), ('adv_c', 'adv_c'), ('target_value_r', 'tv_r'), ('target_value_c', 'tv_c'),
+                    ('discounted_ret', 'disc_ret')):
+        a, b = buf.data[ours].cpu().numpy(), ref[r]
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-6, err_msg=ours)
+        assert (a == b).mean() > (0.7 if estimator == 'vtrace' else 0.99), (ours, (a == b).mean())
 
 
 @pytest.mark.parametrize('T,N', [(1, 1), (4, 33), (127, 40), (128, 64), (129, 31), (300, 97), (512, 256)])

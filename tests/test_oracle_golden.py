@@ -43,6 +43,19 @@ def test_buffer_gae_golden_bit_exact(golden_dir):
     assert np.array_equal(em(g['obs']), g['get_obs'])
 
 
+def test_buffer_other_estimators_golden_bit_exact(golden_dir):
+    """'gae-rtg' / 'plain' / 'vtrace' (onpolicy_buffer.py:L305-331, L338-405) of the per-path oracle vs the
+    reference buffer."""
+    for fname in ('buffer_gae_rtg.npz', 'buffer_plain.npz', 'buffer_vtrace.npz'):
+        g = np.load(os.path.join(golden_dir, fname))
+        out = ogae.dual_gae_per_path(g['rew'], g['cost'], g['val_r'], g['val_c'], g['flags'], g['boot_r'],
+                                     g['boot_c'], float(g['gamma']), float(g['lam']), float(g['lam_c']),
+                                     float(g['pen']), estimator=str(g['estimator']))
+        for ours, ref in (('adv_r', 'raw_adv_r'), ('adv_c', 'raw_adv_c'), ('tv_r', 'raw_target_value_r'),
+                          ('tv_c', 'raw_target_value_c'), ('disc_ret', 'raw_discounted_ret')):
+            assert np.array_equal(out[ours], g[ref]), f'{fname}: {ours} differs from the reference buffer'
+
+
 def test_normalizer_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, 'normalizer.npz'))
     norm = Normalizer((5,))
