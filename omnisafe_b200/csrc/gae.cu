@@ -155,19 +155,19 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
                     ar = 0.0; br = (double)dr[i];
                     ac = 0.0; bc = (double)dc[i];
                     ag = 0.0; bg = (double)r[i] + p.g * (double)bootr[i];
-                    if (EST != 0) bh = (double)c[i] + p.g * (double)bootc[i];
+                    if (EST == 1 || EST == 2) bh = (double)c[i] + p.g * (double)bootc[i];
                 } else {
                     br = (double)dr[i] + glr * br; ar = glr * ar;
                     bc = (double)dc[i] + glc * bc; ac = glc * ac;
                     bg = (double)r[i] + p.g * bg;     ag = p.g * ag;
-                    if (EST != 0) bh = (double)c[i] + p.g * bh;
+                    if (EST == 1 || EST == 2) bh = (double)c[i] + p.g * bh;
                 }
             }
         }
         sa[(0 * GC + y) * GPAD + x] = ar; sb[(0 * GC + y) * GPAD + x] = br;
         sa[(1 * GC + y) * GPAD + x] = ac; sb[(1 * GC + y) * GPAD + x] = bc;
         sa[(2 * GC + y) * GPAD + x] = ag; sb[(2 * GC + y) * GPAD + x] = bg;
-        if (EST != 0) { sa[(3 * GC + y) * GPAD + x] = ag; sb[(3 * GC + y) * GPAD + x] = bh; }
+        if (EST == 1 || EST == 2) { sa[(3 * GC + y) * GPAD + x] = ag; sb[(3 * GC + y) * GPAD + x] = bh; }
         __syncthreads();
         // transposed role: warp tw owns env tw of the block, lane tl = chunk index.
 #pragma unroll
@@ -227,12 +227,12 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
                     Ar = (double)dr[i];
                     Ac = (double)dc[i];
                     Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, (double)bootr[i]));
-                    if (EST != 0) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, (double)bootc[i]));
+                    if (EST == 1 || EST == 2) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, (double)bootc[i]));
                 } else {
                     Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
                     Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
                     Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
-                    if (EST != 0) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, Ah));
+                    if (EST == 1 || EST == 2) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, Ah));
                 }
                 const size_t idx = (size_t)(t0 + i) * N + env;
                 const float o_ar = (EST == 2) ? dr[i] : (float)Ar, o_ac = (EST == 2) ? dc[i] : (float)Ac;
