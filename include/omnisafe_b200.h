@@ -117,6 +117,13 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
  * across epochs; window_sums[4] <- {sum EpRet, sum EpCost, sum EpLen, count} (fp64). */
 int osb_episode_window(const unsigned char* flags, const float* epfin, int T, int N, int W,
                        float* ring, int* meta, double* window_sums, void* stream);
+/* RewardNormalize / CostNormalize (envs/wrapper.py:L280-423; Normalizer(shape=(), clip=5),
+ * common/normalizer.py:L88-139) applied to one epoch's slab x[T][N] in place, after the rollout: row t
+ * is pushed into the running statistics (batch of N) and normalised with the statistics valid right
+ * after that push, exactly the reference's per-step sequence.  state: {mean, sumsq, std} (3 floats) and
+ * count[1] persist across epochs; workspace: 4 * T floats. */
+int osb_scalar_normalize_rows(float* x, int T, int N, float clip, float* state, long long* count,
+                              float* workspace, void* stream);
 
 /* ---- learner: fused minibatch forward + loss + backward ------------------------------------
  * replaces PolicyGradient._update minibatch body  algorithms/on_policy/base/policy_gradient.py:L369-381

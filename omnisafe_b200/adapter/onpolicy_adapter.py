@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from omnisafe_b200._lib import current_stream, lib, ptr
-from omnisafe_b200.common.normalizer import Normalizer
+from omnisafe_b200.common.normalizer import Normalizer, ScalarNormalizer
 from omnisafe_b200.envs.synthetic import SyntheticBoxEnv
 
 
@@ -26,8 +26,9 @@ class OnPolicyAdapter:
                                     env_id_offset=env_id_offset, **env_cfgs)
         self._env.set_seed(seed)
         algo = cfgs.algo_cfgs
-        assert not getattr(algo, 'reward_normalize', False) and not getattr(algo, 'cost_normalize', False), (
-            'reward_normalize / cost_normalize are not part of the fused step yet (SURVEY §8f rank 3)')
+        # RewardNormalize / CostNormalize wrappers (online_adapter.py:L98-101, wrapper.py:L280-423)
+        self._reward_normalizer = ScalarNormalizer(5.0, self._device) if getattr(algo, 'reward_normalize', False) else None
+        self._cost_normalizer = ScalarNormalizer(5.0, self._device) if getattr(algo, 'cost_normalize', False) else None
         self._obs_normalize = bool(getattr(algo, 'obs_normalize', True))
         self._obs_normalizer = Normalizer((self._env.obs_dim,), clip=5.0, device=self._device)
         W = int(getattr(cfgs.logger_cfgs, 'window_lens', 100))
@@ -57,7 +58,12 @@ class OnPolicyAdapter:
 
     def save(self) -> dict:
         """What OnlineAdapter.save() exposes for checkpoints (online_adapter.py:L222-231)."""
-        return {'obs_normalizer': self._obs_normalizer} if self._obs_normalize else {}
+        saved = {'obs_normalizer': self._obs_normalizer} if self._obs_normalize else {}
+        if self._reward_normalizer is not None:
+            saved['reward_normalizer'] = self._reward_normalizer
+        if self._cost_normalizer is not None:
+            saved['cost_normalizer'] = self._cost_normalizer
+        return saved
 
     def rollout(self, steps_per_epoch: int, agent, buffer, logger=None, eps=None) -> None:
         """Roll the envs for `steps_per_epoch` steps each and fill `buffer`.
@@ -74,6 +80,13 @@ class OnPolicyAdapter:
                    self.window_lens, ptr(self.ep_ring), ptr(self.ep_meta), ptr(self.window_sums),
                    int(self.precision), current_stream()])
         lib().osb_rollout_epoch(*args)
+        # the policy never sees rewards inside a rollout: the per-step reward / cost normalisation of the
+        # reference commutes with the rollout and runs on the finished slab (episode statistics stay raw,
+        # info['original_reward'] in the reference)
+        if self._reward_normalizer is not None:
+            self._reward_normalizer.normalize_rows_(buffer.data['reward'])
+        if self._cost_normalizer is not None:
+            self._cost_normalizer.normalize_rows_(buffer.data['cost'])
         self._epoch_index += 1
 
     def close(self) -> None:

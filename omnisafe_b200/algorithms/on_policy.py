@@ -1,5 +1,5 @@
 """On-policy algorithms on the fused sm_100a path: PolicyGradient / PPO / PPOLag / NaturalPG / RCPO /
-TRPO / TRPOLag / CPO / PCPO / FOCOPS / CPPOPID / TRPOPID / OnCRPO.
+TRPO / TRPOLag / CPO / PCPO / FOCOPS / CPPOPID / TRPOPID / OnCRPO / PDO / IPO.
 
 Each class mirrors the override structure of the reference
 (omnisafe/algorithms/on_policy/base/{policy_gradient,ppo,natural_pg,trpo}.py,
@@ -202,6 +202,44 @@ class _LagrangeMixin:
 @registry.register
 class PPOLag(_LagrangeMixin, PPO):
     """naive_lagrange/ppo_lag.py:L26-102."""
+
+
+@registry.register
+class PDO(_LagrangeMixin, PolicyGradient):
+    """naive_lagrange/pdo.py:L25-100: PolicyGradient on the Lagrangian surrogate (its YAML defaults switch
+    the reward / cost normalisers on)."""
+
+
+@registry.register
+class IPO(PPO):
+    """penalty_function/ipo.py:L24-74: PPO on (adv_r - penalty adv_c) / (1 + penalty) with the interior-point
+    penalty kappa / (cost_limit - Jc + 1e-8), replaced by penalty_max when negative or too large."""
+
+    def _init(self) -> None:
+        super()._init()
+        self._penalty_state = torch.zeros(4, dtype=torch.float32, device=self._device)
+        self._penalty = 0.0
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Misc/Penalty')
+
+    def _lagrange_ptr(self):
+        return self._penalty_state
+
+    def _update(self, *args, **kwargs) -> None:
+        a = self._cfgs.algo_cfgs
+        jc = self._window_means()[1]            # the reference reads the logger here too (ipo.py:L68)
+        penalty = a.kappa / (a.cost_limit - jc + 1e-8)
+        if penalty < 0 or penalty > a.penalty_max:
+            penalty = a.penalty_max
+        self._penalty = float(penalty)
+        self._penalty_state[0] = self._penalty
+        super()._update(*args, **kwargs)
+
+    def _log_extra(self) -> None:
+        super()._log_extra()
+        self._logger.store({'Misc/Penalty': self._penalty})
 
 
 @registry.register
@@ -504,5 +542,5 @@ class OnCRPO(TRPO):
         self._logger.store({'Misc/RewUpdate': self._rew_update, 'Misc/CostUpdate': self._cost_update})
 
 
-ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO', 'FOCOPS',
-             'CPPOPID', 'TRPOPID', 'OnCRPO']
+ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'PDO', 'IPO', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO',
+             'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO']

@@ -66,3 +66,11 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
                 window.append((float(ep_ret[i]), float(ep_cost[i]), float(ep_len[i])))
         ep_ret[fin] = 0; ep_cost[fin] = 0; ep_len[fin] = 0
     return sl
+
+
+def normalize_rows(norm, slab):
+    """RewardNormalize / CostNormalize (envs/wrapper.py:L280-423) over a finished [T, N] slab: row t is
+    pushed into `norm` (oracle Normalizer with shape ()) and normalised, step after step as the wrapper
+    does inside `env.step`."""
+    import numpy as np
+    return np.stack([norm.normalize(slab[t]) for t in range(slab.shape[0])]).astype(np.float32)

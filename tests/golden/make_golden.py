@@ -177,13 +177,14 @@ def _flat_theta(ac):
     return torch.cat(parts).numpy().copy()
 
 
-def gen_rollout():
-    """One epoch of the unmodified OnPolicyAdapter.rollout + buffer on the synthetic env."""
+def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled=1):
+    """Epoch(s) of the unmodified OnPolicyAdapter.rollout + buffer on the synthetic env.  PDO's defaults
+    switch RewardNormalize / CostNormalize on (PDO.yaml:L44-46): the slabs then hold normalised values."""
     import torch.distributions.normal as tdn
     import torch.distributions.utils as tdu
 
-    N, T, O, A, seed = 8, 24, 12, 3, 5
-    algo = _build_algo('PPOLag', N, T, O, A, seed)
+    N, T, O, A = 8, 24, 12, 3
+    algo = _build_algo(name, N, T, O, A, seed, epochs=2)
     theta = _flat_theta(algo._actor_critic)
     drawn = []
     orig = tdn._standard_normal
@@ -195,12 +196,15 @@ def gen_rollout():
 
     tdn._standard_normal = rec
     try:
-        algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf,
-                          logger=algo._logger)
+        for e in range(epochs_rolled):
+            if e > 0:
+                algo._buf.get()          # drain the buffer; normaliser states carry over to the next epoch
+            algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf,
+                              logger=algo._logger)
     finally:
         tdn._standard_normal = orig
     eps = np.stack([d.numpy() for d in drawn if tuple(d.shape) == (N, A)])
-    assert eps.shape[0] == T, eps.shape
+    assert eps.shape[0] == T * epochs_rolled, eps.shape
     bufs = algo._buf.buffers
     fields = ('obs', 'act', 'reward', 'cost', 'value_r', 'value_c', 'logp', 'adv_r', 'adv_c',
               'target_value_r', 'target_value_c', 'discounted_ret')
@@ -211,8 +215,16 @@ def gen_rollout():
     while not hasattr(norm, '_obs_normalizer'):
         norm = norm._env
     nz = norm._obs_normalizer
+    extra = {}
+    w = algo._env._env
+    while w is not None:
+        for key, attr in (('rnorm', '_reward_normalizer'), ('cnorm', '_cost_normalizer')):
+            if hasattr(w, attr):
+                z = getattr(w, attr)
+                extra.update({f'{key}_mean': z.mean.numpy(), f'{key}_std': z.std.numpy(), f'{key}_count': int(z._count)})
+        w = getattr(w, '_env', None)
     got = algo._buf.get()
-    np.savez(os.path.join(OUT, 'rollout_ppolag.npz'), N=N, T=T, O=O, A=A, seed=seed, theta=theta,
+    np.savez(os.path.join(OUT, fname), N=N, T=T, O=O, A=A, seed=seed, theta=theta, epochs_rolled=epochs_rolled, **extra,
              eps=eps, tmax=8, term_prob=0.05, gamma=0.99, lam=0.95, lam_c=0.95,
              norm_mean=nz.mean.numpy(), norm_std=nz.std.numpy(), norm_count=int(nz._count),
              win_ret=window['Metrics/EpRet'], win_cost=window['Metrics/EpCost'],
@@ -352,6 +364,7 @@ if __name__ == '__main__':
     gen_normalizer()
     algo = gen_rollout()
     gen_update_ppolag(algo)
+    gen_rollout('PDO', 'rollout_pdo.npz', seed=9, epochs_rolled=2)
     gen_update_focops()
     gen_cpo()
     gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)

@@ -99,6 +99,32 @@ def test_rollout_golden(golden_dir):
     np.testing.assert_allclose(w[:, 2], g['win_len'])
 
 
+def test_rollout_reward_cost_normalize_golden(golden_dir):
+    """Two epochs of the unmodified reference with RewardNormalize / CostNormalize on (PDO defaults) vs the
+    oracle rollout + the oracle scalar normalisers applied to the finished slabs (the wrappers commute
+    with the rollout: the policy never sees rewards)."""
+    g = np.load(os.path.join(golden_dir, 'rollout_pdo.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    env = SyntheticBoxEnv(N, O, A, max_episode_steps=int(g['tmax']), seed=int(g['seed']),
+                          term_prob=float(g['term_prob']))
+    norm, rnorm, cnorm = Normalizer((O,)), Normalizer(()), Normalizer(())
+    for e in range(int(g['epochs_rolled'])):
+        sl = orollout.rollout_epoch(env, norm, g['theta'], T, g['eps'][e * T:(e + 1) * T])
+        rew = orollout.normalize_rows(rnorm, sl['rew'])
+        cost = orollout.normalize_rows(cnorm, sl['cost'])
+    tol = dict(rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **tol)
+    np.testing.assert_allclose(rew, g['slab_reward'], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(cost, g['slab_cost'], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose([rnorm.mean, rnorm.std, cnorm.mean, cnorm.std],
+                               [g['rnorm_mean'], g['rnorm_std'], g['cnorm_mean'], g['cnorm_std']], rtol=1e-5)
+    assert rnorm.count == int(g['rnorm_count']) and cnorm.count == int(g['cnorm_count'])
+    out = ogae.dual_gae_slab(rew, cost, sl['val_r'], sl['val_c'], sl['flags'], sl['boot_r'], sl['boot_c'],
+                             float(g['gamma']), float(g['lam']), float(g['lam_c']))
+    np.testing.assert_allclose(out['adv_r'], g['slab_adv_r'], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(out['adv_c'], g['slab_adv_c'], rtol=1e-4, atol=5e-5)
+
+
 def _load_update(golden_dir, name):
     g = np.load(os.path.join(golden_dir, name))
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}

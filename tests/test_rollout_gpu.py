@@ -15,8 +15,8 @@ from oracle.synthetic_env import SyntheticBoxEnv as OEnv
 pytestmark = pytest.mark.gpu
 
 
-def _cfgs(obs_normalize=True, window=100, **env_cfgs):
-    return NS(algo_cfgs=NS(obs_normalize=obs_normalize, reward_normalize=False, cost_normalize=False),
+def _cfgs(obs_normalize=True, window=100, rc_normalize=False, **env_cfgs):
+    return NS(algo_cfgs=NS(obs_normalize=obs_normalize, reward_normalize=rc_normalize, cost_normalize=rc_normalize),
               logger_cfgs=NS(window_lens=window), env_cfgs=env_cfgs)
 
 
@@ -26,12 +26,13 @@ def _model_cfgs():
               weight_initialization_mode='kaiming_uniform')
 
 
-def _gpu_rollout(dev, N, T, O, A, seed, theta, eps, tmax, term_prob, obs_normalize=True, window=100, epochs=1):
+def _gpu_rollout(dev, N, T, O, A, seed, theta, eps, tmax, term_prob, obs_normalize=True, window=100, epochs=1,
+                 rc_normalize=False):
     from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
     from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
     from omnisafe_b200.models import ConstraintActorCritic
 
-    cfgs = _cfgs(obs_normalize, window, obs_dim=O, act_dim=A, max_episode_steps=tmax, term_prob=term_prob)
+    cfgs = _cfgs(obs_normalize, window, rc_normalize, obs_dim=O, act_dim=A, max_episode_steps=tmax, term_prob=term_prob)
     ad = OnPolicyAdapter('SyntheticBox-v0', N, seed, cfgs, device=dev)
     agent = ConstraintActorCritic(O, A, _model_cfgs(), epochs=1, device=dev)
     agent.load_flat(theta)
@@ -95,6 +96,59 @@ def test_rollout_golden_reference(cuda, golden_dir):
     np.testing.assert_allclose(ring[2][order], g['win_len'])
     ws = ad.window_sums.cpu().numpy()
     np.testing.assert_allclose(ws[1] / ws[3], g['win_cost'].mean(), rtol=1e-6)
+
+
+def test_rollout_reward_cost_normalize_golden(cuda, golden_dir):
+    """RewardNormalize / CostNormalize (wrapper.py:L280-423) as the slab post-pass vs two epochs of the
+    unmodified reference with PDO's defaults (normalisers on); then GAE on the normalised slabs."""
+    g = np.load(os.path.join(golden_dir, 'rollout_pdo.npz'))
+    N, T, O, A, E = int(g['N']), int(g['T']), int(g['O']), int(g['A']), int(g['epochs_rolled'])
+    ad, buf, outs = _gpu_rollout(cuda, N, T, O, A, int(g['seed']), g['theta'], g['eps'].reshape(E, T, N, A),
+                                 int(g['tmax']), float(g['term_prob']), window=10, epochs=E, rc_normalize=True)
+    sl = outs[-1]
+    t = dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **t)
+    np.testing.assert_allclose(sl['reward'], g['slab_reward'], rtol=5e-5, atol=5e-5)
+    np.testing.assert_allclose(sl['cost'], g['slab_cost'], rtol=5e-5, atol=5e-5)
+    rn, cn = ad.save()['reward_normalizer'], ad.save()['cost_normalizer']
+    np.testing.assert_allclose([float(rn.mean), float(rn.std), float(cn.mean), float(cn.std)],
+                               [g['rnorm_mean'], g['rnorm_std'], g['cnorm_mean'], g['cnorm_std']], rtol=2e-5)
+    assert int(rn.count[0]) == int(g['rnorm_count']) and int(cn.count[0]) == int(g['cnorm_count'])
+    assert set(rn.state_dict()) == {'_mean', '_sumsq', '_var', '_std', '_count', '_clip'}
+    buf.finish_paths()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(buf.data['adv_r'].cpu().numpy(), g['slab_adv_r'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(buf.data['adv_c'].cpu().numpy(), g['slab_adv_c'], rtol=1e-4, atol=1e-4)
+    # episode statistics stay raw (info['original_reward'], onpolicy_adapter.py:L141-146)
+    meta, ring = ad.ep_meta.cpu().numpy(), ad.ep_ring.cpu().numpy()
+    cnt, head = int(meta[0]), int(meta[1])
+    order = [(head - cnt + i) % 10 for i in range(cnt)]
+    np.testing.assert_allclose(ring[0][order], g['win_ret'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ring[1][order], g['win_cost'])
+
+
+def test_scalar_normalizer_large_rows(cuda):
+    """Slab post-pass vs the oracle Normalizer(()) at a headline-sized row (N = 4096) over several epochs."""
+    from omnisafe_b200.common.normalizer import ScalarNormalizer
+    from oracle.normalizer import Normalizer as ONorm
+    from oracle.rollout import normalize_rows
+
+    rng = np.random.default_rng(4)
+    sn, on = ScalarNormalizer(5.0, cuda), ONorm(())
+    for e in range(3):
+        x = (rng.standard_normal((16, 4096)) * (1 + e) + 0.3 * e).astype(np.float32)
+        want = normalize_rows(on, x)
+        got = torch.as_tensor(x).to(cuda)
+        sn.normalize_rows_(got)
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose([float(sn.mean), float(sn.std)], [on.mean, on.std], rtol=1e-5)
+    assert int(sn.count[0]) == on.count
+    one = ScalarNormalizer(5.0, cuda)      # N == 1: count <= 1 after the first push -> passthrough
+    y = torch.tensor([[2.0], [4.0], [9.0]], device=cuda)
+    o1 = ONorm(())
+    want = normalize_rows(o1, np.array([[2.0], [4.0], [9.0]], np.float32))
+    one.normalize_rows_(y)
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-6)
 
 
 @pytest.mark.parametrize('N,T,O,A,tmax,term_prob,norm', [
