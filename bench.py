@@ -204,7 +204,9 @@ def run_b200(args) -> dict:
     gae_gbs = 33.0 * total / (ms_gae * 1e-3) / 1e9
     roofline = {'kernel': 'minibatch_grad_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf,
                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': ach_tf / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'frac': ach_tf / peaks['bf16_tflops_sustained'],
+                'traffic': 14.57e6,   # dram bytes read + written per launch, ncu --set full (profiles/r01_ncu_minibatch_grad_tc.md)
+                'algorithmic_bytes': 292.0 * w['batch_size'] + 147 * 24850 * 4.0,   # sample rows read + per-CTA partial gradients written
                 'peak_source': peaks['source'] + ' (cuBLAS bf16 sustained; kernel runs tcgen05 kind::tf32, nominal tf32 peak = half of bf16)',
                 'us_per_launch': ms_grad * 1e3,
                 'gae': {'kernel': 'gae_dual_kernel', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],

@@ -135,7 +135,9 @@ int osb_scalar_normalize_rows(float* x, int T, int N, float clip, float* state, 
  * RAW GAE outputs and are standardised on the fly with moments[4] (osb_adv_moments).  A minibatch is
  * the window [mb_start, mb_start+mb_count) of a permutation of [0,total): perm (slab rows, parity
  * mode) or NULL (in-kernel keyed Feistel bijection).  loss_kind: 0 PPO-clip, 1 plain ratio*adv,
- * 2 FOCOPS, 3 cost surrogate.  lagrange: device scalar lambda or NULL (0).  net_mask bit0 actor,
+ * 2 FOCOPS, 3 cost surrogate, 5 P3O (PPO-clip + kappa * relu(mean(ratio*adv_c) + Jc - limit),
+ * penalty_function/p3o.py:L48-125; kappa is passed as focops_lam, Jc - limit as focops_eta; like
+ * FOCOPS it runs a forward-only pass first for the minibatch mean).  lagrange: device scalar lambda or NULL (0).  net_mask bit0 actor,
  * bit1 reward critic, bit2 cost critic.  gpart: osb_update_grid_blocks(mb_count) * P floats;
  * stats_part: that many * 3 * 8 floats.  stop_flag (device int, may be NULL): non-zero = no-op. */
 int osb_update_grid_blocks(int mb_count);

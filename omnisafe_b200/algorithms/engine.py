@@ -9,7 +9,7 @@ import torch
 from omnisafe_b200._lib import current_stream, lib, ptr
 from omnisafe_b200.utils import distributed
 
-LOSS_PPO_CLIP, LOSS_RATIO, LOSS_FOCOPS, LOSS_COST = 0, 1, 2, 3
+LOSS_PPO_CLIP, LOSS_RATIO, LOSS_FOCOPS, LOSS_COST, LOSS_P3O = 0, 1, 2, 3, 5
 NET_ACTOR, NET_CRITIC_R, NET_CRITIC_C = 1, 2, 4
 
 

@@ -1,5 +1,5 @@
 """On-policy algorithms on the fused sm_100a path: PolicyGradient / PPO / PPOLag / NaturalPG / RCPO /
-TRPO / TRPOLag / CPO / PCPO / FOCOPS / CPPOPID / TRPOPID / OnCRPO / PDO / IPO.
+TRPO / TRPOLag / CPO / PCPO / FOCOPS / CPPOPID / TRPOPID / OnCRPO / PDO / IPO / P3O.
 
 Each class mirrors the override structure of the reference
 (omnisafe/algorithms/on_policy/base/{policy_gradient,ppo,natural_pg,trpo}.py,
@@ -17,7 +17,7 @@ import torch
 from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
 from omnisafe_b200.algorithms import registry
 from omnisafe_b200.algorithms.base_algo import BaseAlgo
-from omnisafe_b200.algorithms.engine import (LOSS_COST, LOSS_FOCOPS, LOSS_PPO_CLIP, LOSS_RATIO,
+from omnisafe_b200.algorithms.engine import (LOSS_COST, LOSS_FOCOPS, LOSS_P3O, LOSS_PPO_CLIP, LOSS_RATIO,
                                              NET_ACTOR, UpdateEngine)
 from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 from omnisafe_b200.common.lagrange import Lagrange
@@ -240,6 +240,35 @@ class IPO(PPO):
     def _log_extra(self) -> None:
         super()._log_extra()
         self._logger.store({'Misc/Penalty': self._penalty})
+
+
+@registry.register
+class P3O(PPO):
+    """penalty_function/p3o.py:L29-125: the PPO clipped surrogate on adv_r plus the exact penalty
+    kappa * relu(mean(ratio adv_c) + Jc - cost_limit) in the actor loss."""
+
+    _loss_kind = LOSS_P3O
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Loss/Loss_pi_cost', delta=True)
+
+    def _update(self, net_mask: int = 7, perm=None) -> None:
+        a = self._cfgs.algo_cfgs
+        jc = self._window_means()[1] - a.cost_limit        # the reference reads the logger per minibatch (p3o.py:L88)
+        self._engine.ppo_epoch(
+            loss_kind=LOSS_P3O, lagrange=None, net_mask=net_mask if a.use_cost else net_mask & ~4,
+            batch_size=a.batch_size, update_iters=a.update_iters, clip=a.clip, entropy_coef=a.entropy_coef,
+            focops_lam=a.kappa, focops_eta=jc,
+            critic_norm_coef=a.critic_norm_coef if a.use_critic_norm else 0.0,
+            max_grad_norm=a.max_grad_norm if a.use_max_grad_norm else 0.0,
+            lr_actor=self._actor_critic.actor_lr, lr_critic=self._actor_critic.critic_lr,
+            target_kl=a.target_kl, kl_early_stop=a.kl_early_stop, perm=perm)
+
+    def _log_extra(self) -> None:
+        super()._log_extra()
+        ts = self._engine.train_stats[:8].tolist()      # actor slots: loss, ratio, penalty term, minibatch steps
+        self._logger.store({'Loss/Loss_pi_cost': ts[2] / max(ts[3], 1.0)})
 
 
 @registry.register
@@ -542,5 +571,5 @@ class OnCRPO(TRPO):
         self._logger.store({'Misc/RewUpdate': self._rew_update, 'Misc/CostUpdate': self._cost_update})
 
 
-ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'PDO', 'IPO', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO',
+ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'PDO', 'IPO', 'P3O', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO',
              'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO']

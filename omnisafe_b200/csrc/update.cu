@@ -24,7 +24,7 @@ namespace osb {
 
 constexpr int UT = 128;  // samples per tile
 
-enum LossKind { LOSS_PPO_CLIP = 0, LOSS_RATIO = 1, LOSS_FOCOPS = 2, LOSS_COST = 3 };
+enum LossKind { LOSS_PPO_CLIP = 0, LOSS_RATIO = 1, LOSS_FOCOPS = 2, LOSS_COST = 3, LOSS_P3O = 5 };   // 4 = FVP (tensor-core kernel)
 
 struct Batch {
     const float* obs;     // [rows][O]
@@ -225,11 +225,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
                     const float adv_c = __ldg(p.b.adv_c + row) - m_c;
                     float adv = (adv_r - lam * adv_c) / (1.f + lam);
                     float dlogp = 0.f, loss = 0.f, dmask = 0.f;
-                    if (p.lc.kind == LOSS_PPO_CLIP) {
+                    if (p.lc.kind == LOSS_PPO_CLIP || p.lc.kind == LOSS_P3O) {
                         const float rc = fminf(fmaxf(ratio, 1.f - p.lc.clip), 1.f + p.lc.clip);
                         const float s1 = ratio * adv, s2 = rc * adv;
                         loss = -fminf(s1, s2);
                         dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
+                        if (p.lc.kind == LOSS_P3O) {
+                            // P3O (penalty_function/p3o.py:L48-91): + kappa * relu(mean_j(ratio_j adv_c_j) + Jc - limit).
+                            // gate = kappa when the minibatch mean (forward-only pass 1) makes the relu active.
+                            // Statistic slot 2: pass 1 -> ratio * adv_c; pass 2 -> the penalty term (Loss/Loss_pi_cost),
+                            // slot 0 stays the PPO part as the reference logs Loss/Loss_pi (ppo.py:L80-86).
+                            const bool pass2 = p.lc.focops_mask_mean != nullptr;
+                            const float gate = pass2 ? __ldg(p.lc.focops_mask_mean) : 0.f;
+                            dlogp += gate * adv_c * ratio * inv_b;
+                            kl = pass2 ? gate * (ratio * adv_c + p.lc.focops_eta) : ratio * adv_c;
+                        }
                     } else if (p.lc.kind == LOSS_RATIO) {
                         loss = -ratio * adv;
                         dlogp = -adv * ratio * inv_b;
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) minibatch_grad_kernel(GradArgs p)
             float g = sLs[2 * OUTP + threadIdx.x];
             // entropy bonus: loss -= coef * mean(entropy); d entropy / d log_std_a = 1 (mean over A)
             // (only PPO._loss_pi / FOCOPS._loss_pi carry the entropy term)
-            if (blockIdx.x == 0 && (p.lc.kind == LOSS_PPO_CLIP || p.lc.kind == LOSS_FOCOPS))
+            if (blockIdx.x == 0 && (p.lc.kind == LOSS_PPO_CLIP || p.lc.kind == LOSS_FOCOPS || p.lc.kind == LOSS_P3O))
                 g -= p.lc.entropy_coef / (float)A;
             gout[L.off_logstd + threadIdx.x] = g;
         }
@@ -781,13 +791,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fvp_kernel(FvpArgs p) {
     }
 }
 
-// FOCOPS pass 1 -> mean_i mask_i of the minibatch: stats slot 4 / slot 3 of the actor, fixed order.
+// Pass 1 of the two-pass losses, fixed order over the actor's per-CTA statistics:
+//   FOCOPS: out = mean_i mask_i                      (slot 4 / slot 3)
+//   P3O:    out = kappa if mean_i(ratio_i adv_c_i) + (Jc - limit) > 0 else 0   (slot 2 / slot 3; F.relu gate)
 __global__ void focops_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
-                                        const int* __restrict__ stop_flag) {
+                                        const int* __restrict__ stop_flag, int kind, float kappa, float jc_minus_limit) {
     if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    const int slot = (kind == LOSS_P3O) ? 2 : 4;
     float m = 0.f, n = 0.f;
-    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * ST_N + 4]; n += stats_part[((size_t)b * 3) * ST_N + 3]; }
-    out[0] = n > 0.f ? m / n : 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * ST_N + slot]; n += stats_part[((size_t)b * 3) * ST_N + 3]; }
+    const float mean = n > 0.f ? m / n : 0.f;
+    out[0] = (kind == LOSS_P3O) ? ((mean + jc_minus_limit > 0.f) ? kappa : 0.f) : mean;
 }
 
 }  // namespace osb
@@ -845,14 +859,16 @@ int osb_minibatch_grad(const float* theta, int O, int A, const float* obs, const
         attr = true;
     }
     dim3 grid(osb_update_grid_blocks(mb_count), 3);
-    if (loss_kind == LOSS_FOCOPS && (net_mask & 1)) {
-        // pass 1: actor forward only -> mean mask of the minibatch (the reference's [b,1] x [b] broadcast)
+    if ((loss_kind == LOSS_FOCOPS || loss_kind == LOSS_P3O) && (net_mask & 1)) {
+        // pass 1: actor forward only -> mean mask of the minibatch (FOCOPS: the reference's [b,1] x [b]
+        // broadcast) or the relu gate of the minibatch-mean cost surrogate (P3O)
         if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
         GradArgs q = p;
         q.forward_only = 1; q.net_mask = 1;
         minibatch_grad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(q);
         OSB_LAUNCH_CHECK();
-        focops_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, (int)grid.x, d_mask_mean, stop_flag);
+        focops_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, (int)grid.x, d_mask_mean, stop_flag,
+                                                                    loss_kind, focops_lam, focops_eta);
         OSB_LAUNCH_CHECK();
         p.lc.focops_mask_mean = d_mask_mean;
     }

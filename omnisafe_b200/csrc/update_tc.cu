@@ -29,7 +29,7 @@ using namespace umma;
 constexpr int TT = 128;                 // samples per tile
 constexpr uint32_t BUF = TT * 64 * 4;   // 32 KB activation buffer ([128][64] or [64][128] fp32)
 
-enum TcLoss { TC_PPO_CLIP = 0, TC_RATIO = 1, TC_FOCOPS = 2, TC_COST = 3, TC_FVP = 4 };   // TC_FVP: dOUT supplied (Fisher-vector product)
+enum TcLoss { TC_PPO_CLIP = 0, TC_RATIO = 1, TC_FOCOPS = 2, TC_COST = 3, TC_FVP = 4, TC_P3O = 5 };   // TC_FVP: dOUT supplied (Fisher-vector product)
 
 struct TcBatch {
     const float* obs; const float* act; const float* logp; const float* adv_r; const float* adv_c;
@@ -417,11 +417,17 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                         loss = kl * dmask - mbar * ratio * adv / p.focops_lam;
                         dlogp = -mbar * adv * ratio / p.focops_lam * inv_b;
                         st[2] = kl; st[4] = dmask;
-                    } else if (p.kind == TC_PPO_CLIP) {
+                    } else if (p.kind == TC_PPO_CLIP || p.kind == TC_P3O) {
                         const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
                         const float s1 = ratio * adv, s2 = rc * adv;
                         loss = -fminf(s1, s2);
                         dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
+                        if (p.kind == TC_P3O) {   // + kappa * relu(mean(ratio adv_c) + Jc - limit), gate from pass 1
+                            const bool pass2 = p.focops_mask_mean != nullptr;
+                            const float gate = pass2 ? __ldg(p.focops_mask_mean) : 0.f;
+                            dlogp += gate * adv_c * ratio * inv_b;
+                            st[2] = pass2 ? gate * (ratio * adv_c + p.focops_eta) : ratio * adv_c;   // Loss/Loss_pi_cost
+                        }
                     } else if (p.kind == TC_RATIO) {
                         loss = -ratio * adv; dlogp = -adv * ratio * inv_b;
                     } else {
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         if (tid < L.out) gout[L.off_b3 + tid] = sB3acc[tid];
         if (net == 0 && tid < A) {
             float g = sLs[32 + tid];
-            if (blockIdx.x == 0 && (p.kind == TC_PPO_CLIP || is_focops)) g -= p.entropy_coef / (float)A;
+            if (blockIdx.x == 0 && (p.kind == TC_PPO_CLIP || p.kind == TC_P3O || is_focops)) g -= p.entropy_coef / (float)A;
             // log_std block of the Fisher matrix: (2/A) v, counted once (natural_pg.py:L74-119, analytic form)
             if (is_fvp) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + tid) : 0.f;
             gout[L.off_logstd + tid] = g;
@@ -862,12 +868,15 @@ int osb_tc_grid_blocks(long long rows, int net_mask) {
 }
 
 // FOCOPS pass 1 -> mean_i mask_i of the minibatch (stats slot 4 / slot 3 of the actor), fixed order.
+//   P3O:    out = kappa if mean_i(ratio_i adv_c_i) + (Jc - limit) > 0 else 0   (slot 2 / slot 3)
 __global__ void tc_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
-                                    const int* __restrict__ stop_flag) {
+                                    const int* __restrict__ stop_flag, int kind, float kappa, float jc_minus_limit) {
     if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    const int slot = (kind == TC_P3O) ? 2 : 4;
     float m = 0.f, n = 0.f;
-    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + 4]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
-    out[0] = n > 0.f ? m / n : 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + slot]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
+    const float mean = n > 0.f ? m / n : 0.f;
+    out[0] = (kind == TC_P3O) ? ((mean + jc_minus_limit > 0.f) ? kappa : 0.f) : mean;
 }
 
 // Tensor-core (TF32 tcgen05) variant of osb_minibatch_grad: same arguments, O <= 64, A <= 16.
@@ -884,7 +893,7 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
     OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
     OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "tensor-core path needs O <= 64, A <= 16");
     OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
-    OSB_CHECK_ARG(loss_kind >= 0 && loss_kind <= 3, "loss kind");
+    OSB_CHECK_ARG((loss_kind >= 0 && loss_kind <= 3) || loss_kind == TC_P3O, "loss kind");
     OSB_CHECK_ARG(loss_kind != TC_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old/logstd_old");
     OSB_CHECK_ARG(net_mask > 0 && net_mask < 8, "net_mask");
     TcArgs p;
@@ -896,7 +905,7 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
     p.mu_old = mu_old; p.logstd_old = logstd_old; p.focops_lam = focops_lam; p.focops_eta = focops_eta;
     p.focops_mask_mean = nullptr; p.forward_only = 0;
     const int nb = osb_tc_grid_blocks(mb_count, net_mask);
-    if (loss_kind == TC_FOCOPS && (net_mask & 1)) {
+    if ((loss_kind == TC_FOCOPS || loss_kind == TC_P3O) && (net_mask & 1)) {
         // pass 1: actor forward only -> mean mask of the minibatch (the reference's [b,1] x [b] broadcast)
         if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
         TcArgs q = p;
@@ -904,7 +913,8 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
         const int nb1 = osb_tc_grid_blocks(mb_count, 1);
         int rc = launch_grad_tc(q, nb1, (cudaStream_t)stream);
         if (rc) return rc;
-        tc_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag);
+        tc_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag, loss_kind,
+                                                                focops_lam, focops_eta);
         OSB_LAUNCH_CHECK();
         p.focops_mask_mean = d_mask_mean;
     }

@@ -98,6 +98,13 @@ class Learner:
         ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
         return (ratio * adv_c).mean()
 
+    def loss_pi_p3o(self, obs, act, logp, adv_r, adv_c, clip, kappa, jc_minus_limit, entropy_coef=0.0):
+        """P3O._update_actor (penalty_function/p3o.py:L48-125): PPO clipped surrogate on adv_r +
+        kappa * relu(mean(ratio * adv_c) + Jc - cost_limit)."""
+        loss_reward, ratio = self.loss_pi_ppo(obs, act, logp, adv_r, clip, entropy_coef)
+        surr_cadv = (ratio * adv_c).mean()
+        return loss_reward + kappa * torch.relu(surr_cadv + jc_minus_limit), ratio
+
     def loss_pi_focops(self, obs, act, logp, adv, old_mean, old_std, lam_f, eta, entropy_coef=0.0):
         # NB: as in the reference, kl is [b, 1] while ratio * adv is [b]: the difference broadcasts
         # to [b, b] before the mean (first_order/focops.py:L85-89).  Kept verbatim for parity.
@@ -126,7 +133,7 @@ class Learner:
 
     def update_ppo(self, data, perms, lam, *, batch_size, clip=0.2, entropy_coef=0.0, use_cost=True,
                    critic_norm_coef=0.001, max_grad_norm=40.0, target_kl=0.02, kl_early_stop=True,
-                   focops=None):
+                   focops=None, p3o=None):
         """PolicyGradient._update / FOCOPS._update.  `data` holds env-major tensors as returned by
         VectorOnPolicyBuffer.get(); `perms[i]` is the sample order of pass i (DataLoader shuffle)."""
         t = {k: torch.as_tensor(v) for k, v in data.items()}
@@ -145,7 +152,10 @@ class Learner:
                 if use_cost:
                     stats['loss_c'].append(self.critic_step('cost_critic', obs, t['target_value_c'][idx], critic_norm_coef, max_grad_norm))
                 adv = (t['adv_r'][idx] - lam * t['adv_c'][idx]) / (1 + lam)
-                if focops is None:
+                if p3o is not None:
+                    loss, _ = self.loss_pi_p3o(obs, t['act'][idx], t['logp'][idx], t['adv_r'][idx], t['adv_c'][idx],
+                                               clip, p3o['kappa'], p3o['jc_minus_limit'], entropy_coef)
+                elif focops is None:
                     loss, _ = self.loss_pi_ppo(obs, t['act'][idx], t['logp'][idx], adv, clip, entropy_coef)
                 else:
                     loss, _ = self.loss_pi_focops(obs, t['act'][idx], t['logp'][idx], adv, old_mean[idx],

@@ -296,6 +296,25 @@ def gen_update_focops():
              **{'data_' + k: v for k, v in data.items()})
 
 
+def gen_update_p3o():
+    """P3O._update of the unmodified reference with the relu penalty active (cost_limit below Jc)."""
+    N, T, O, A, seed = 8, 24, 12, 3, 13
+    algo = _build_algo('P3O', N, T, O, A, seed, extra_algo={'cost_limit': 1.0, 'kappa': 0.5}, tmax=8, term_prob=0.05)
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    Jc = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    np.savez(os.path.join(OUT, 'update_p3o.npz'), N=N, T=T, O=O, A=A, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), Jc=Jc, perms=perms, batch_size=32, update_iters=2,
+             cost_limit=1.0, kappa=0.5, kl=_last(lg, 'Train/KL'), stop_iter=_last(lg, 'Train/StopIter'),
+             loss_pi=_last(lg, 'Loss/Loss_pi'), loss_pi_cost=_last(lg, 'Loss/Loss_pi_cost'),
+             **{'data_' + k: v for k, v in data.items()})
+
+
 def gen_cpo(name='CPO', fname='update_cpo.npz', seed=7, cost_limit=2.0):
     """CPO / PCPO: Fisher-vector product, CG solve and one full actor+critic update of the reference."""
     from omnisafe.utils.math import conjugate_gradients as ref_cg
@@ -366,6 +385,7 @@ if __name__ == '__main__':
     gen_update_ppolag(algo)
     gen_rollout('PDO', 'rollout_pdo.npz', seed=9, epochs_rolled=2)
     gen_update_focops()
+    gen_update_p3o()
     gen_cpo()
     gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)
     gen_pid()

@@ -20,7 +20,7 @@ def _custom(tmp, N=64, T=32, epochs=3, **algo):
 
 
 @pytest.mark.parametrize('algo', ['PPOLag', 'TRPOLag', 'CPO', 'FOCOPS', 'PPO', 'TRPO', 'RCPO', 'NaturalPG', 'PolicyGradient',
-                                  'PCPO', 'CPPOPID', 'TRPOPID', 'OnCRPO', 'PDO', 'IPO'])
+                                  'PCPO', 'CPPOPID', 'TRPOPID', 'OnCRPO', 'PDO', 'IPO', 'P3O'])
 def test_agent_trains_and_logs(cuda, tmp_path, algo):
     import omnisafe_b200
 

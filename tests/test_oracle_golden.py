@@ -210,6 +210,21 @@ def test_focops_update_golden(golden_dir):
     np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7)
 
 
+def test_p3o_update_golden(golden_dir):
+    """Oracle P3O update (PPO clip + kappa * relu(mean(ratio adv_c) + Jc - limit)) == unmodified P3O._update."""
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_p3o.npz')
+    O, A = int(g['O']), int(g['A'])
+    L = ol.Learner(g['theta0'], O, A)
+    st = L.update_ppo(data, g['perms'][::2], 0.0, batch_size=int(g['batch_size']),
+                      p3o={'kappa': float(g['kappa']), 'jc_minus_limit': float(g['Jc']) - float(g['cost_limit'])})
+    np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
+    # the reference logs the PPO part and the penalty separately (Loss/Loss_pi, Loss/Loss_pi_cost)
+    np.testing.assert_allclose(st['loss_pi'], g['loss_pi'] + g['loss_pi_cost'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7)
+
+
 def test_pid_lagrange_golden(golden_dir):
     """oracle PIDLagrangian vs the reference class over the recorded cost sequences (bit-exact: both are
     Python-float recurrences)."""

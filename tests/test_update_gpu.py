@@ -233,3 +233,62 @@ def test_focops_update_epoch_golden(cuda, golden_dir):
     np.testing.assert_allclose(float(eng.kl_state[0]), g['kl'][-1], rtol=2e-3, atol=1e-6)
     ts = eng.train_stats.cpu().numpy().reshape(3, 8)
     np.testing.assert_allclose(ts[0, 0] / ts[0, 3], g['loss_pi'].mean(), rtol=2e-3, atol=1e-5)
+
+
+def test_p3o_update_epoch_golden(cuda, golden_dir):
+    """P3O on the device (forward-only pass for the minibatch-mean relu gate) vs the unmodified
+    P3O._update: same parameters afterwards."""
+    g = np.load(os.path.join(golden_dir, 'update_p3o.npz'))
+    data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, g['theta0'])
+    perms = torch.as_tensor(np.stack([_rows(p_, N, T) for p_ in g['perms'][::2]])).to(cuda)
+    eng.ppo_epoch(loss_kind=5, lagrange=None, net_mask=7, batch_size=int(g['batch_size']),
+                  update_iters=int(g['update_iters']), clip=0.2, entropy_coef=0.0, focops_lam=float(g['kappa']),
+                  focops_eta=float(g['Jc']) - float(g['cost_limit']), critic_norm_coef=0.001, max_grad_norm=40.0,
+                  lr_actor=3e-4, lr_critic=3e-4, target_kl=0.02, kl_early_stop=True, perm=perms)
+    torch.cuda.synchronize()
+    got, want = agent.theta.cpu().numpy(), g['theta1']
+    bad = ~np.isclose(got, want, rtol=2e-4, atol=2e-6)
+    assert bad.mean() < 1e-3 and np.abs(got - want).max() < 2e-3, (bad.sum(), np.abs(got - want).max())
+    np.testing.assert_allclose(float(eng.kl_state[0]), g['kl'][-1], rtol=2e-3, atol=1e-6)
+    ts = eng.train_stats.cpu().numpy().reshape(3, 8)
+    np.testing.assert_allclose(ts[0, 0] / ts[0, 3], g['loss_pi'].mean(), rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(ts[0, 2] / ts[0, 3], g['loss_pi_cost'].mean(), rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize('jc_minus_limit', [-5.0, 0.3])
+@pytest.mark.parametrize('tc', [0, 1])
+def test_p3o_gate_vs_autograd(cuda, jc_minus_limit, tc):
+    """Both states of the relu gate (inactive: plain PPO-clip gradient; active: + kappa d mean(ratio adv_c)),
+    fp32 tiles and tcgen05 tiles, against autograd of the oracle loss."""
+    from omnisafe_b200._lib import current_stream, lib, ptr
+
+    N, T, O, A = 40, 25, 60, 8
+    rng = np.random.default_rng(17)
+    theta = oac.init_theta(O, A, seed=6)
+    data = _rand_data(rng, N, T, O, A, theta)
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+    B = N * T
+    perm_em = rng.permutation(B)
+    perm = torch.as_tensor(_rows(perm_em, N, T)).to(cuda)
+    kappa = 0.7
+    d = buf.data
+    fn = lib().osb_minibatch_grad_tc if tc else lib().osb_minibatch_grad
+    nb = lib().osb_tc_grid_blocks(B, 1) if tc else lib().osb_update_grid_blocks(B)
+    fn(ptr(agent.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']),
+       ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(eng.mu_old), ptr(buf.adv_moments), ptr(perm), B, 0,
+       0, B, 5, 0.2, 0.0, kappa, jc_minus_limit, 0, ptr(eng.logstd_old), 1, ptr(eng.gpart), ptr(eng.stats_part), 0,
+       current_stream())
+    lib().osb_grad_reduce(ptr(eng.gpart), ptr(eng.stats_part), nb, O, A, ptr(agent.theta), ptr(agent.grad), 0.0, 1,
+                          ptr(eng.sumsq_part), ptr(agent.adam_step), ptr(eng.train_stats), 0, current_stream())
+    torch.cuda.synchronize()
+    got = agent.grad.cpu().numpy()[: eng.Pa]
+    L = ol.Learner(theta, O, A)
+    t = {k: torch.as_tensor(v) for k, v in data.items()}
+    loss, _ = L.loss_pi_p3o(t['obs'], t['act'], t['logp'], t['adv_r'], t['adv_c'], 0.2, kappa, jc_minus_limit)
+    loss.backward()
+    want = L.flat_grad('actor').numpy()
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel < (2e-2 if tc else 1e-4), rel
+    np.testing.assert_allclose(float(eng.train_stats[0] + eng.train_stats[2]), float(loss), rtol=5e-3 if tc else 1e-4, atol=1e-5)
