@@ -111,7 +111,8 @@ class RefSyntheticBox(CMDP):
     def __init__(self, env_id, num_envs=1, device='cpu', **kw):
         super().__init__(env_id)
         self._num_envs = num_envs
-        self._kw = dict(kw)
+        # keep the env-spec keys only (the Evaluator also passes render_mode / camera / size kwargs)
+        self._kw = {k: v for k, v in kw.items() if k in ('obs_dim', 'act_dim', 'max_episode_steps', 'term_prob', 'cost_threshold')}
         self._env = None
         O, A = kw.get('obs_dim', 60), kw.get('act_dim', 8)
         self._observation_space = Box(-10.0, 10.0, (O,))
@@ -128,6 +129,8 @@ class RefSyntheticBox(CMDP):
         return torch.as_tensor(self._env.reset()), {}
 
     def step(self, action):
+        if action.dim() == 1:      # the Evaluator drives a single env with an unbatched action
+            action = action.unsqueeze(0)
         nobs, rew, cost, term, trunc, final, fin = self._env.step(action.numpy())
         info = {}
         if fin.any():
