@@ -46,7 +46,7 @@ class UpdateEngine:
 
     # ---- helpers ----------------------------------------------------------------------------
     def _tc(self) -> bool:
-        return self.precision == 1 and self.O <= 64
+        return self.precision == 1 and self.O <= 512      # obs dims > 64: layer 1 K-chunked (rollout stays on fp32 tiles)
 
     def _eval_fn(self):
         return lib().osb_actor_eval_tc if self._tc() else lib().osb_actor_eval

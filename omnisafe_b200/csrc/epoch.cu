@@ -169,7 +169,7 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     OSB_CUDA(cudaMemsetAsync(train_stats, 0, 3 * 8 * sizeof(float), s));
     int rc;
     // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
-    const bool use_tc = precision == 1 && O <= 64;
+    const bool use_tc = precision == 1 && O <= 512;
     const bool train_actor = (net_mask & 1) != 0;
     if (train_actor) {
         OSB_CHECK_ARG(mu_old && logstd_old && eval_ws && eval_out, "actor update needs mu_old/logstd_old/eval buffers");

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) actor_eval_tc_kernel(EvalTcArgs p
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int n = (tid >> 6) + 4 * j;
-            w1v[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
+            w1v[j] = (k < O && O <= 64) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
             w2v[j] = __ldg(theta + L.off_w2 + n * 64 + k);
         }
 #pragma unroll
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) actor_eval_tc_kernel(EvalTcArgs p
     constexpr uint32_t C_Z = 0, C_OUT = 64;
     uint32_t phase = 0;
 
+    const int nchunks = (O + 63) >> 6;
     const long long nrows = (p.total + p.stride - 1) / p.stride;
     const long long ntiles = (nrows + ET - 1) / ET;
     const float lam = p.lagrange ? __ldg(p.lagrange) : 0.f;
@@ -93,25 +94,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) actor_eval_tc_kernel(EvalTcArgs p
             sRow[tid] = (k < nrows) ? k * p.stride : -1;
         }
         __syncthreads();
-        {
-            const int k = tid & 63;
+        for (int c = 0; c < nchunks; ++c) {     // layer 1 as a K loop over 64-column chunks of X / W1 (one chunk if O <= 64)
+            const int k = tid & 63, col = c * 64 + k;
+            if (nchunks > 1) {
+                float w1c[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w1c[j] = (col < O) ? __ldg(theta + L.off_w1 + ((tid >> 6) + 4 * j) * O + col) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sts(tile_addr(sW1, (tid >> 6) + 4 * j, k, 64), tf32r(w1c[j]));
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float xv[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const long long row = sRow[(tid >> 6) + 4 * (16 * half + j)];
-                    xv[j] = (row >= 0 && k < O) ? __ldg(p.obs + row * O + k) : 0.f;
+                    xv[j] = (row >= 0 && col < O) ? __ldg(p.obs + row * O + col) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sts(tile_addr(B0, (tid >> 6) + 4 * (16 * half + j), k, ET), tf32r(xv[j]));
             }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B0, ET, sW1, 64, 128, 64, 64, c > 0); mma_commit(&bar); }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B0, ET, sW1, 64, 128, 64, 64, false); mma_commit(&bar); }
-        mbar_wait(&bar, phase); phase ^= 1;
-        tc_fence_after();
         {
             float v[32];
             tmem_ld32(tmem + lane_base + C_Z + 32 * h, v);
@@ -195,7 +203,7 @@ using namespace osb;
 
 extern "C" {
 
-// Tensor-core variant of osb_actor_eval (O <= 64); same arguments and outputs.
+// Tensor-core variant of osb_actor_eval (O <= 512; layer 1 K-chunked above 64); same arguments and outputs.
 int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, const float* act,
                       const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
                       const float* logstd_old, const float* moments, const float* lagrange,
@@ -214,7 +222,7 @@ int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, 
                       const float* logstd_old, const float* moments, const float* lagrange,
                       long long total, int stride, float* mu_store, double* workspace, double* out,
                       void* stream) {
-    OSB_CHECK_ARG(theta_actor && obs && total > 0 && stride > 0 && O > 0 && O <= 64 && A > 0 && A <= 16, "bad argument (O <= 64)");
+    OSB_CHECK_ARG(theta_actor && obs && total > 0 && stride > 0 && O > 0 && O <= 512 && A > 0 && A <= 16, "bad argument (O <= 512)");
     OSB_CHECK_ARG(mu_store || (act && logp && adv_r && adv_c && mu_old && logstd_old && workspace && out), "null input");
     EvalTcArgs p{obs, act, logp, adv_r, adv_c, mu_old, logstd_old, moments, lagrange, theta_actor, mu_store, workspace, total, stride, O, A};
     const size_t smem = 1024 + 2 * (size_t)EBUF + 2 * 16384 + 4096 + (64 + 64 + 16 + 64) * 4 + 32 * 8 + 128 * 8 + 64;

@@ -100,6 +100,9 @@ __device__ __forceinline__ void load_row16(uint32_t base, int r, int c0, int R, 
                      : "r"(row + (uint32_t)(((ch0 + i) ^ (r & 7)) << 4)));
 }
 
+// CHUNKED = obs dim > 64: layer 1 runs as a K loop over 64-column chunks of X / W1 (forward: Z1 and Z1^T
+// accumulate over chunks; backward: one dW1 chunk per MMA, flushed from TMEM into this CTA's partial gradient).
+template <bool CHUNKED>
 __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     if (p.stop_flag && *p.stop_flag) return;
     // one network selected: grid.y == 1 and all of grid.x (up to one CTA per SM) works on that network
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = (tid >> 6) + 8 * j;
-            w1v[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
+            w1v[j] = (!CHUNKED && k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
             w2v[j] = __ldg(theta + L.off_w2 + n * 64 + k);
         }
 #pragma unroll
@@ -225,10 +228,68 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
+    // CHUNKED: one 64-column chunk of this thread's X elements in flight (global -> registers -> tile)
+    const int nchunks = (O + 63) >> 6;
+    float xr[16];
+    auto load_chunk = [&](const long long* rows, int c) {
+        if (vec) {
+            const int col = c * 64 + ((tid & 15) << 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long row = rows[(tid >> 4) + 32 * j];
+                const float4 v = (row >= 0 && col < O) ? __ldg(reinterpret_cast<const float4*>(p.b.obs + row * O + col))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
+            }
+        } else {
+            const int col = c * 64 + (tid & 63);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long row = rows[(tid >> 6) + 8 * j];
+                xr[j] = (row >= 0 && col < O) ? __ldg(p.b.obs + row * O + col) : 0.f;
+            }
+        }
+    };
+    auto store_chunk = [&](uint32_t dst, bool transposed) {     // dst: [128 s][64 k] K-major, or its transpose [64 k][128 s]
+        if (vec) {
+            const int k4 = (tid & 15) << 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = (tid >> 4) + 32 * j;
+                const float a = tf32r(xr[4 * j]), b = tf32r(xr[4 * j + 1]), c = tf32r(xr[4 * j + 2]), d = tf32r(xr[4 * j + 3]);
+                if (!transposed) {
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(dst, m, k4, TT)), "f"(a), "f"(b),
+                                 "f"(c), "f"(d)
+                                 : "memory");
+                } else {
+                    sts(tile_addr(dst, k4 + 0, m, 64), a); sts(tile_addr(dst, k4 + 1, m, 64), b);
+                    sts(tile_addr(dst, k4 + 2, m, 64), c); sts(tile_addr(dst, k4 + 3, m, 64), d);
+                }
+            }
+        } else {
+            const int k = tid & 63;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int m = (tid >> 6) + 8 * j;
+                const float v = tf32r(xr[j]);
+                if (!transposed) sts(tile_addr(dst, m, k, TT), v);
+                else sts(tile_addr(dst, k, m, 64), v);
+            }
+        }
+    };
+    auto load_w1_chunk = [&](int c) {                            // W1[:, 64c : 64c+64] -> sW1 (zero padded)
+        const int k = tid & 63, col = c * 64 + k;
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = (col < O) ? __ldg(theta + L.off_w1 + ((tid >> 6) + 8 * j) * O + col) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts(tile_addr(sW1, (tid >> 6) + 8 * j, k, 64), tf32r(w[j]));
+    };
     int rpar = 0;
     tile_rows(blockIdx.x, sRowBuf);
     __syncthreads();
-    if (vec) prefetch_x(sRowBuf);
+    if (CHUNKED) load_chunk(sRowBuf, 0);
+    else if (vec) prefetch_x(sRowBuf);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- P0: X and X^T tiles (data of this tile was prefetched into registers) ---------------
@@ -236,7 +297,9 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         long long* sRowNext = sRowBuf + (rpar ^ 1) * TT;
         const bool has_next = tile + (int)gridDim.x < ntiles;
         if (has_next) tile_rows(tile + gridDim.x, sRowNext);     // visible after the next barrier
-        if (vec) {
+        if (CHUNKED) {
+            // X is staged chunk by chunk inside P1 (and again, transposed, inside P6)
+        } else if (vec) {
             const int k4 = (tid & 15) << 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -269,14 +332,32 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         fence_async_smem();
         __syncthreads();
         // ---- P1: Z1 and Z1^T ---------------------------------------------------------------------
-        if (tid == 0) {
+        if (CHUNKED) {
+            for (int c = 0; c < nchunks; ++c) {
+                load_w1_chunk(c);                     // the previous chunk's MMAs completed: B0 / sW1 are free
+                store_chunk(B0, false);
+                fence_async_smem();
+                __syncthreads();
+                if (c + 1 < nchunks) load_chunk(sRow, c + 1);      // next chunk's rows fly during the MMAs
+                if (tid == 0) {
+                    tc_fence_after();
+                    tc_gemm(tmem + C_Z, B0, TT, sW1, 64, 128, 64, 64, c > 0);
+                    tc_gemm(tmem + C_ZT, sW1, 64, B0, TT, 64, 128, 64, c > 0);
+                    mma_commit(&bar);
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
+                tc_fence_after();
+            }
+        } else {
+            if (tid == 0) {
+                tc_fence_after();
+                tc_gemm(tmem + C_Z, B0, TT, sW1, 64, 128, 64, 64, false);
+                tc_gemm(tmem + C_ZT, sW1, 64, B0, TT, 64, 128, 64, false);
+                mma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            tc_gemm(tmem + C_Z, B0, TT, sW1, 64, 128, 64, 64, false);
-            tc_gemm(tmem + C_ZT, sW1, 64, B0, TT, 64, 128, 64, false);
-            mma_commit(&bar);
         }
-        mbar_wait(&bar, phase); phase ^= 1;
-        tc_fence_after();
         {   // plain epilogue only: H1 is all that layer 2 needs
             float v[16];
             tmem_ld16(tmem + lane_base + C_Z + c16, v);
@@ -481,8 +562,9 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             const int a = tid - 64;
             sB3acc[a] += sRed[96 + a] + sRed[112 + a] + sRed[128 + a] + sRed[144 + a];
         }
-        if (p.forward_only) {   // FOCOPS pass 1: statistics only
-            if (vec && has_next) prefetch_x(sRowNext);
+        if (p.forward_only) {   // FOCOPS / P3O pass 1: statistics only
+            if (CHUNKED) { if (has_next) load_chunk(sRowNext, 0); }
+            else if (vec && has_next) prefetch_x(sRowNext);
             first_tile = false;
             rpar ^= 1;
             __syncthreads();
@@ -521,7 +603,8 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         tc_fence_before();
         __syncthreads();
         // ---- P5: dW2 += dZ2^T H1 ; dZ1^T = W2^T dZ2^T --------------------------------------------
-        if (vec && has_next) prefetch_x(sRowNext);    // global loads of the next tile fly during P5 / P6
+        if (CHUNKED) load_chunk(sRow, 0);             // chunk 0 of THIS tile again: P6 needs X^T chunk by chunk
+        else if (vec && has_next) prefetch_x(sRowNext);    // global loads of the next tile fly during P5 / P6
         if (tid == 0) {
             tc_fence_after();
             tc_gemm(tmem + C_DW2, B4, 64, B3, 64, 64, 64, 128, !first_tile);
@@ -554,6 +637,43 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         tc_fence_before();
         __syncthreads();
         // ---- P6: dW1 += dZ1^T X --------------------------------------------------------------------
+        if (CHUNKED) {
+            for (int c = 0; c < nchunks; ++c) {
+                store_chunk(B1, true);               // X^T chunk [64 k][128 s]
+                fence_async_smem();
+                tc_fence_before();                   // (c > 0) every read of the previous chunk's accumulator is done
+                __syncthreads();
+                if (c + 1 < nchunks) load_chunk(sRow, c + 1);
+                if (tid == 0) {
+                    tc_fence_after();
+                    tc_gemm(tmem + C_DW1, B0, 64, B1, 64, 64, 64, 128, false);
+                    mma_commit(&bar);
+                }
+                if (c == 0 && tid < 64) {   // db1[j] = sum_s dZ1^T[j][s]
+                    float cs = 0.f, v[32];
+#pragma unroll 1
+                    for (int a4 = 0; a4 < 4; ++a4) {
+                        load_row32(B0, tid, 32 * a4, 64, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) cs += v[i];
+                    }
+                    ab1 += cs;
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
+                tc_fence_after();
+                {   // flush this chunk of dW1 into the CTA's partial gradient (each element owned by one thread)
+                    float v[16];
+                    tmem_ld16(tmem + lane_base + C_DW1 + c16, v);
+                    if (lane < 16) {
+                        float* qrow = gout + L.off_w1 + t_row * O + c * 64 + c16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c * 64 + c16 + i < O) qrow[i] = first_tile ? v[i] : qrow[i] + v[i];
+                    }
+                }
+            }
+            if (has_next) load_chunk(sRowNext, 0);
+        } else {
         if (tid == 0) {
             tc_fence_after();
             tc_gemm(tmem + C_DW1, B0, 64, B1, 64, 64, 64, 128, !first_tile);
@@ -571,6 +691,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         }
         mbar_wait(&bar, phase); phase ^= 1;      // B0 / B1 are rewritten by the next tile's gather
         tc_fence_after();
+        }
         first_tile = false;
         rpar ^= 1;
         __syncthreads();
@@ -586,10 +707,12 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         if (lane < 16)
 #pragma unroll
             for (int i = 0; i < 16; ++i) stage[t_row * 65 + c16 + i] = v[i];
-        tmem_ld16(tmem + lane_base + C_DW1 + c16, v);
-        if (lane < 16)
+        if (!CHUNKED) {
+            tmem_ld16(tmem + lane_base + C_DW1 + c16, v);
+            if (lane < 16)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) stage[64 * 65 + t_row * 65 + c16 + i] = v[i];
+                for (int i = 0; i < 16; ++i) stage[64 * 65 + t_row * 65 + c16 + i] = v[i];
+        }
         if (h == 0) {   // dW3^T [k][o] accumulator (M = 64 layout)
             tmem_ld16(tmem + lane_base + C_DW3, v);
             if (lane < 16)
@@ -598,7 +721,8 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         }
         __syncthreads();
         for (int i = tid; i < 64 * 64; i += NTC) gout[L.off_w2 + i] = stage[(i >> 6) * 65 + (i & 63)];
-        for (int i = tid; i < 64 * O; i += NTC) gout[L.off_w1 + i] = stage[64 * 65 + (i / O) * 65 + (i % O)];
+        if (!CHUNKED)
+            for (int i = tid; i < 64 * O; i += NTC) gout[L.off_w1 + i] = stage[64 * 65 + (i / O) * 65 + (i % O)];
         for (int i = tid; i < L.out * 64; i += NTC) gout[L.off_w3 + i] = stage[2 * 64 * 65 + (i >> 6) * 65 + (i & 63)];
         if (tid < 64) { gout[L.off_b1 + tid] = ab1; gout[L.off_b2 + tid] = ab2; }
         if (tid < L.out) gout[L.off_b3 + tid] = sB3acc[tid];
@@ -631,6 +755,7 @@ struct FvpTanArgs {
 };
 constexpr uint32_t F_Z1 = 0, F_Z2 = 128, F_DMU = 256;
 
+template <bool CHUNKED>     // obs dim > 64: K loop over 64-column chunks of X / [W1;V1]
 __global__ void __launch_bounds__(NTC, 1) fvp_tangent_tc_kernel(FvpTanArgs p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -662,8 +787,8 @@ __global__ void __launch_bounds__(NTC, 1) fvp_tangent_tc_kernel(FvpTanArgs p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = (tid >> 6) + 8 * j;
-            w1v[j] = (k < O) ? __ldg(p.theta + L.off_w1 + n * O + k) : 0.f;
-            v1v[j] = (k < O) ? __ldg(p.vec + L.off_w1 + n * O + k) : 0.f;
+            w1v[j] = (!CHUNKED && k < O) ? __ldg(p.theta + L.off_w1 + n * O + k) : 0.f;
+            v1v[j] = (!CHUNKED && k < O) ? __ldg(p.vec + L.off_w1 + n * O + k) : 0.f;
             w2v[j] = __ldg(p.theta + L.off_w2 + n * 64 + k);
             v2v[j] = __ldg(p.vec + L.off_w2 + n * 64 + k);
         }
@@ -720,17 +845,71 @@ __global__ void __launch_bounds__(NTC, 1) fvp_tangent_tc_kernel(FvpTanArgs p) {
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
+    const int nchunks = (O + 63) >> 6;
+    float xr[16];
+    auto load_chunk = [&](const long long* rows, int c) {
+        if (vec4) {
+            const int col = c * 64 + ((tid & 15) << 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long row = rows[(tid >> 4) + 32 * j];
+                const float4 v = (row >= 0 && col < O) ? __ldg(reinterpret_cast<const float4*>(p.obs + row * O + col))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
+            }
+        } else {
+            const int col = c * 64 + (tid & 63);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long row = rows[(tid >> 6) + 8 * j];
+                xr[j] = (row >= 0 && col < O) ? __ldg(p.obs + row * O + col) : 0.f;
+            }
+        }
+    };
+    auto store_chunk = [&]() {
+        if (vec4) {
+            const int k4 = (tid & 15) << 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, (tid >> 4) + 32 * j, k4, TT)),
+                             "f"(tf32r(xr[4 * j])), "f"(tf32r(xr[4 * j + 1])), "f"(tf32r(xr[4 * j + 2])), "f"(tf32r(xr[4 * j + 3]))
+                             : "memory");
+        } else {
+            const int k = tid & 63;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sts(tile_addr(B0, (tid >> 6) + 8 * j, k, TT), tf32r(xr[j]));
+        }
+    };
+    auto load_wv1_chunk = [&](int c) {                 // [W1 ; V1][:, 64c : 64c+64] -> sWV1 (zero padded)
+        const int k = tid & 63, col = c * 64 + k;
+        float w[8], v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
+            w[j] = (col < O) ? __ldg(p.theta + L.off_w1 + n * O + col) : 0.f;
+            v[j] = (col < O) ? __ldg(p.vec + L.off_w1 + n * O + col) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = (tid >> 6) + 8 * j;
+            sts(tile_addr(sWV1, n, k, 128), tf32r(w[j]));
+            sts(tile_addr(sWV1, 64 + n, k, 128), tf32r(v[j]));
+        }
+    };
     int rpar = 0;
     tile_rows(blockIdx.x, sRowBuf);
     __syncthreads();
-    if (vec4) prefetch_x(sRowBuf);
+    if (CHUNKED) load_chunk(sRowBuf, 0);
+    else if (vec4) prefetch_x(sRowBuf);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         long long* sRow = sRowBuf + rpar * TT;
         long long* sRowNext = sRowBuf + (rpar ^ 1) * TT;
         const bool has_next = tile + (int)gridDim.x < ntiles;
         if (has_next) tile_rows(tile + gridDim.x, sRowNext);
-        if (vec4) {
+        if (CHUNKED) {
+            // staged chunk by chunk below
+        } else if (vec4) {
             const int k4 = (tid & 15) << 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -752,15 +931,33 @@ __global__ void __launch_bounds__(NTC, 1) fvp_tangent_tc_kernel(FvpTanArgs p) {
         }
         fence_async_smem();
         __syncthreads();
-        if (vec4 && has_next) prefetch_x(sRowNext);      // next tile's rows fly during the three layers
         // ---- layer 1: [Z1 | X V1^T] ----------------------------------------------------------------
-        if (tid == 0) {
+        if (CHUNKED) {
+            for (int c = 0; c < nchunks; ++c) {
+                load_wv1_chunk(c);
+                store_chunk();
+                fence_async_smem();
+                __syncthreads();
+                if (c + 1 < nchunks) load_chunk(sRow, c + 1);
+                else if (has_next) load_chunk(sRowNext, 0);
+                if (tid == 0) {
+                    tc_fence_after();
+                    tc_gemm(tmem + F_Z1, B0, TT, sWV1, 128, 128, 128, 64, c > 0);
+                    mma_commit(&bar);
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
+                tc_fence_after();
+            }
+        } else {
+            if (vec4 && has_next) prefetch_x(sRowNext);      // next tile's rows fly during the three layers
+            if (tid == 0) {
+                tc_fence_after();
+                tc_gemm(tmem + F_Z1, B0, TT, sWV1, 128, 128, 128, 64, false);
+                mma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            tc_gemm(tmem + F_Z1, B0, TT, sWV1, 128, 128, 128, 64, false);
-            mma_commit(&bar);
         }
-        mbar_wait(&bar, phase); phase ^= 1;
-        tc_fence_after();
         {
             float z[16], dz[16];
             tmem_ld16(tmem + lane_base + F_Z1 + c16, z);
@@ -845,12 +1042,14 @@ static int launch_grad_tc(const TcArgs& p, int nblocks, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes();
     static bool attr = false;
     if (!attr) {
-        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     const bool single = (p.net_mask & (p.net_mask - 1)) == 0;     // one network: it gets every CTA
     dim3 grid(nblocks, single ? 1 : 3);
-    minibatch_grad_tc_kernel<<<grid, NTC, smem, stream>>>(p);
+    if (p.O > 64) minibatch_grad_tc_kernel<true><<<grid, NTC, smem, stream>>>(p);
+    else minibatch_grad_tc_kernel<false><<<grid, NTC, smem, stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
@@ -891,7 +1090,7 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
                           float* stats_part, const int* stop_flag, void* stream) {
     static float* d_mask_mean = nullptr;   // FOCOPS scratch scalar
     OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
-    OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "tensor-core path needs O <= 64, A <= 16");
+    OSB_CHECK_ARG(O > 0 && O <= 512 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "tensor-core path needs O <= 512, A <= 16");
     OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
     OSB_CHECK_ARG((loss_kind >= 0 && loss_kind <= 3) || loss_kind == TC_P3O, "loss kind");
     OSB_CHECK_ARG(loss_kind != TC_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old/logstd_old");
@@ -928,7 +1127,7 @@ int osb_fvp_partials_tc(const float* theta_actor, const float* vec, int O, int A
                         long long total, int stride, float* dmu, float* gpart, float* stats_scratch,
                         void* stream) {
     OSB_CHECK_ARG(theta_actor && vec && obs && dmu && gpart && stats_scratch && total > 0 && stride > 0, "bad argument");
-    OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16, "tensor-core path needs O <= 64, A <= 16");
+    OSB_CHECK_ARG(O > 0 && O <= 512 && A > 0 && A <= 16, "tensor-core path needs O <= 512, A <= 16");
     const long long nrows = (total + stride - 1) / stride;
     OSB_CHECK_ARG(nrows < (1ll << 31), "too many rows");
     const int nb = osb_tc_grid_blocks(nrows, 1);
@@ -938,10 +1137,12 @@ int osb_fvp_partials_tc(const float* theta_actor, const float* vec, int O, int A
         const size_t smem = fvp_tan_smem_bytes();
         static bool attr = false;
         if (!attr) {
-            OSB_CUDA(cudaFuncSetAttribute(fvp_tangent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            OSB_CUDA(cudaFuncSetAttribute(fvp_tangent_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            OSB_CUDA(cudaFuncSetAttribute(fvp_tangent_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = true;
         }
-        fvp_tangent_tc_kernel<<<nb, NTC, smem, s>>>(t);
+        if (O > 64) fvp_tangent_tc_kernel<true><<<nb, NTC, smem, s>>>(t);
+        else fvp_tangent_tc_kernel<false><<<nb, NTC, smem, s>>>(t);
         OSB_LAUNCH_CHECK();
     }
     TcArgs p;

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize('O,A,N,T,loss_kind', [(60, 8, 20, 13, 0), (60, 8, 64, 40, 0), (17, 6, 9, 31, 3), (64, 16, 16, 24, 1), (60, 8, 512, 80, 0)])
+@pytest.mark.parametrize('O,A,N,T,loss_kind', [(60, 8, 20, 13, 0), (60, 8, 64, 40, 0), (17, 6, 9, 31, 3), (64, 16, 16, 24, 1), (60, 8, 512, 80, 0),
+                                                (111, 8, 40, 30, 1), (376, 8, 33, 12, 3), (128, 4, 300, 9, 1), (65, 8, 20, 7, 0)])   # obs dims > 64: K-chunked layer 1
 def test_tc_grad_vs_autograd(cuda, O, A, N, T, loss_kind):
     from omnisafe_b200._lib import current_stream, lib, ptr
 
@@ -97,9 +98,10 @@ def test_tc_epoch_close_to_fp32_epoch(cuda):
 
 
 @pytest.mark.timeout(120)
-def test_tc_actor_eval_matches_fp32_eval(cuda):
+@pytest.mark.parametrize('O', [60, 111, 376])
+def test_tc_actor_eval_matches_fp32_eval(cuda, O):
     rng = np.random.default_rng(9)
-    N, T, O, A = 96, 50, 60, 8
+    N, T, A = 96, 50, 8
     theta = oac.init_theta(O, A, seed=4)
     data = _rand_data(rng, N, T, O, A, theta)
     agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
@@ -121,7 +123,8 @@ def test_tc_actor_eval_matches_fp32_eval(cuda):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize('O,A,N,T,stride', [(60, 8, 64, 40, 1), (17, 6, 9, 31, 1), (64, 16, 100, 50, 3), (60, 8, 512, 80, 1)])
+@pytest.mark.parametrize('O,A,N,T,stride', [(60, 8, 64, 40, 1), (17, 6, 9, 31, 1), (64, 16, 100, 50, 3), (60, 8, 512, 80, 1),
+                                             (111, 8, 40, 30, 1), (376, 8, 64, 40, 2)])
 def test_tc_fvp_vs_fp32_fvp(cuda, O, A, N, T, stride):
     """Tensor-core Fisher-vector product (tangent kernel + TC backward) vs the exact-fp32 FVP kernel
     (itself checked against double-backward autograd in test_update_gpu).  Tolerance 5e-3 l2-relative."""

@@ -31,7 +31,8 @@ def run(algo, O, epochs=4, N=4096, T=128):
     gae_us = g0.elapsed_time(g1) / 20 * 1e3
     out = {'algo': algo, 'obs_dim': O, 'ms_per_epoch': round(ms, 2), 'env_steps_per_s': round(N * T / ms * 1e3),
            'gae_us': round(gae_us, 2), 'gae_GBps': round(33 * N * T / gae_us / 1e3, 1),
-           'tensor_core_tiles': bool(algo_obj._engine.precision == 1 and O <= 64)}
+           'tensor_core_update': bool(algo_obj._engine.precision == 1 and O <= 512),
+           'tensor_core_rollout': bool(algo_obj._engine.precision == 1 and O <= 64)}
     print(json.dumps(out), flush=True)
     del algo_obj
     torch.cuda.empty_cache()
