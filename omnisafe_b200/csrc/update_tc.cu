@@ -666,9 +666,17 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                     tmem_ld16(tmem + lane_base + C_DW1 + c16, v);
                     if (lane < 16) {
                         float* qrow = gout + L.off_w1 + t_row * O + c * 64 + c16;
+                        const int nvalid = O - (c * 64 + c16);          // columns of this 16-group inside [0, O)
+                        if (!first_tile) {                              // all loads first (independent), then the stores
+                            float old[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) old[i] = (i < nvalid) ? __ldcg(qrow + i) : 0.f;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += old[i];
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c * 64 + c16 + i < O) qrow[i] = first_tile ? v[i] : qrow[i] + v[i];
+                            if (i < nvalid) __stcg(qrow + i, v[i]);
                     }
                 }
             }
