@@ -89,7 +89,8 @@ __device__ __forceinline__ void gae_load_tile(const GaeArgs& p, int env, bool en
 //                the replay pass redoes the reference's fp32 operations from that carry.
 // where `rewards` is the penalised reward path INCLUDING its bootstrap slot (finish_path subtracts
 // penalty * costs in place, L185) and the cost targets use the same gamma (L192-196).
-template <bool MULTI, int EST>
+// RET = produce discounted_ret (third scan); training keeps no discounted_ret, so the hot instantiation drops it.
+template <bool MULTI, int EST, bool RET>
 __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 : 2) gae_dual_kernel(GaeArgs p) {
     constexpr int NQ = (EST == 0 || EST == 3) ? 3 : 4;    // scanned quantities: adv_r, adv_c, reward-to-go, cost-to-go
     __shared__ double sa[NQ * GC * GPAD];
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
     const int ntiles = (T + GT - 1) / GT;
 
     if (lin < NQ * GE) carry[lin] = 0.0;
+    constexpr bool want_g = (EST == 1 || EST == 2) || RET;
 
     double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
     GaeTile cur;
@@ -154,24 +156,25 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
                 if (end[i]) {
                     ar = 0.0; br = (double)dr[i];
                     ac = 0.0; bc = (double)dc[i];
-                    ag = 0.0; bg = (double)r[i] + p.g * (double)bootr[i];
+                    if (want_g) { ag = 0.0; bg = (double)r[i] + p.g * (double)bootr[i]; }
                     if (EST == 1 || EST == 2) bh = (double)c[i] + p.g * (double)bootc[i];
                 } else {
                     br = (double)dr[i] + glr * br; ar = glr * ar;
                     bc = (double)dc[i] + glc * bc; ac = glc * ac;
-                    bg = (double)r[i] + p.g * bg;     ag = p.g * ag;
+                    if (want_g) { bg = (double)r[i] + p.g * bg; ag = p.g * ag; }
                     if (EST == 1 || EST == 2) bh = (double)c[i] + p.g * bh;
                 }
             }
         }
         sa[(0 * GC + y) * GPAD + x] = ar; sb[(0 * GC + y) * GPAD + x] = br;
         sa[(1 * GC + y) * GPAD + x] = ac; sb[(1 * GC + y) * GPAD + x] = bc;
-        sa[(2 * GC + y) * GPAD + x] = ag; sb[(2 * GC + y) * GPAD + x] = bg;
+        if (want_g) { sa[(2 * GC + y) * GPAD + x] = ag; sb[(2 * GC + y) * GPAD + x] = bg; }
         if (EST == 1 || EST == 2) { sa[(3 * GC + y) * GPAD + x] = ag; sb[(3 * GC + y) * GPAD + x] = bh; }
         __syncthreads();
         // transposed role: warp tw owns env tw of the block, lane tl = chunk index.
 #pragma unroll
         for (int q = (EST == 2 ? 2 : 0); q < NQ; ++q) {
+            if (q == 2 && !want_g) continue;
             double a = sa[(q * GC + tl) * GPAD + tw];
             double b = sb[(q * GC + tl) * GPAD + tw];
 #pragma unroll
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
         // pass 2: replay sequentially from the exact carry-in with the reference's roundings.
         double Ar = sb[(0 * GC + y) * GPAD + x];
         double Ac = sb[(1 * GC + y) * GPAD + x];
-        double Ag = sb[(2 * GC + y) * GPAD + x];
+        double Ag = want_g ? sb[(2 * GC + y) * GPAD + x] : 0.0;
         double Ah = (EST == 1 || EST == 2) ? sb[(3 * GC + y) * GPAD + x] : 0.0;
         // V-trace replay state: v_{t+1} of the step after this chunk (fp32, = V + e from the scan)
         float lv_r = 0.f, lv_c = 0.f;
@@ -219,19 +222,19 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
                                 : __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
                     p.adv_r[idx] = o_ar; p.adv_c[idx] = o_ac;
                     p.tv_r[idx] = lv_r;  p.tv_c[idx] = lv_c;
-                    if (p.disc_ret) p.disc_ret[idx] = (float)Ag;
+                    if (RET && p.disc_ret) p.disc_ret[idx] = (float)Ag;
                     st_r += (double)o_ar; st_r2 += (double)o_ar * (double)o_ar; st_c += (double)o_ac;
                 }
             } else if (valid[i]) {
                 if (end[i]) {
                     Ar = (double)dr[i];
                     Ac = (double)dc[i];
-                    Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, (double)bootr[i]));
+                    if (want_g) Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, (double)bootr[i]));
                     if (EST == 1 || EST == 2) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, (double)bootc[i]));
                 } else {
                     Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
                     Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
-                    Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
+                    if (want_g) Ag = __dadd_rn((double)r[i], __dmul_rn(p.g, Ag));
                     if (EST == 1 || EST == 2) Ah = __dadd_rn((double)c[i], __dmul_rn(p.g, Ah));
                 }
                 const size_t idx = (size_t)(t0 + i) * N + env;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
                 p.adv_c[idx] = o_ac;
                 p.tv_r[idx] = (EST == 0) ? (float)(Ar + (double)vr[i]) : (float)Ag;
                 p.tv_c[idx] = (EST == 0) ? (float)(Ac + (double)vc[i]) : (float)Ah;
-                if (p.disc_ret) p.disc_ret[idx] = (float)Ag;
+                if (RET && p.disc_ret) p.disc_ret[idx] = (float)Ag;
                 st_r += (double)o_ar;
                 st_r2 += (double)o_ar * (double)o_ar;
                 st_c += (double)o_ac;
@@ -388,16 +391,24 @@ int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, co
     // the 64-register instantiation (two CTAs per SM) wins at every T measured on B200: occupancy beats
     // the register-hungry prefetching variant, which is kept for experiments (OSB_GAE_PREFETCH=1)
     static const bool prefetch = getenv("OSB_GAE_PREFETCH") != nullptr;
-    if (estimator == 1)
-        gae_dual_kernel<false, 1><<<nblocks, dim3(GE, GC), 0, s>>>(a);
-    else if (estimator == 2)
-        gae_dual_kernel<false, 2><<<nblocks, dim3(GE, GC), 0, s>>>(a);
-    else if (estimator == 3)
-        gae_dual_kernel<false, 3><<<nblocks, dim3(GE, GC), 0, s>>>(a);
-    else if (prefetch && T > GT)
-        gae_dual_kernel<true, 0><<<nblocks, dim3(GE, GC), 0, s>>>(a);
-    else
-        gae_dual_kernel<false, 0><<<nblocks, dim3(GE, GC), 0, s>>>(a);
+    const bool ret = disc_ret != nullptr;
+    const dim3 blk(GE, GC);
+    if (estimator == 1) {
+        if (ret) gae_dual_kernel<false, 1, true><<<nblocks, blk, 0, s>>>(a);
+        else gae_dual_kernel<false, 1, false><<<nblocks, blk, 0, s>>>(a);
+    } else if (estimator == 2) {
+        if (ret) gae_dual_kernel<false, 2, true><<<nblocks, blk, 0, s>>>(a);
+        else gae_dual_kernel<false, 2, false><<<nblocks, blk, 0, s>>>(a);
+    } else if (estimator == 3) {
+        if (ret) gae_dual_kernel<false, 3, true><<<nblocks, blk, 0, s>>>(a);
+        else gae_dual_kernel<false, 3, false><<<nblocks, blk, 0, s>>>(a);
+    } else if (prefetch && T > GT) {
+        gae_dual_kernel<true, 0, true><<<nblocks, blk, 0, s>>>(a);
+    } else if (ret) {
+        gae_dual_kernel<false, 0, true><<<nblocks, blk, 0, s>>>(a);
+    } else {
+        gae_dual_kernel<false, 0, false><<<nblocks, blk, 0, s>>>(a);
+    }
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
