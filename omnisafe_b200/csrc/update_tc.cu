@@ -102,7 +102,9 @@ __device__ __forceinline__ void load_row16(uint32_t base, int r, int c0, int R, 
 
 // CHUNKED = obs dim > 64: layer 1 runs as a K loop over 64-column chunks of X / W1 (forward: Z1 and Z1^T
 // accumulate over chunks; backward: one dW1 chunk per MMA, flushed from TMEM into this CTA's partial gradient).
-template <bool CHUNKED>
+// EXT = the two-pass / supplied-dOUT loss kinds (FOCOPS, P3O, FVP); the plain instantiation (PPO-clip, ratio,
+// cost surrogate: the headline path) carries none of their registers or branches.
+template <bool CHUNKED, bool EXT>
 __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     if (p.stop_flag && *p.stop_flag) return;
     // one network selected: grid.y == 1 and all of grid.x (up to one CTA per SM) works on that network
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     const float lam = (p.lagrange != nullptr) ? __ldg(p.lagrange) : 0.f;
     float m_r = 0.f, s_r = 1.f, m_c = 0.f;
     if (p.b.moments) { m_r = __ldg(p.b.moments + 0); s_r = __ldg(p.b.moments + 1); m_c = __ldg(p.b.moments + 2); }
-    const bool is_fvp = p.kind == TC_FVP, is_focops = p.kind == TC_FOCOPS;
+    const bool is_fvp = EXT && p.kind == TC_FVP, is_focops = EXT && p.kind == TC_FOCOPS, is_p3o = EXT && p.kind == TC_P3O;
     float ab1 = 0.f, ab2 = 0.f;
     bool first_tile = true;
     const int s_row = 32 * q + lane;       // sample row of this thread in [s][.] accumulators
@@ -498,12 +500,12 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
                         loss = kl * dmask - mbar * ratio * adv / p.focops_lam;
                         dlogp = -mbar * adv * ratio / p.focops_lam * inv_b;
                         st[2] = kl; st[4] = dmask;
-                    } else if (p.kind == TC_PPO_CLIP || p.kind == TC_P3O) {
+                    } else if (p.kind == TC_PPO_CLIP || is_p3o) {
                         const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
                         const float s1 = ratio * adv, s2 = rc * adv;
                         loss = -fminf(s1, s2);
                         dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
-                        if (p.kind == TC_P3O) {   // + kappa * relu(mean(ratio adv_c) + Jc - limit), gate from pass 1
+                        if (is_p3o) {   // + kappa * relu(mean(ratio adv_c) + Jc - limit), gate from pass 1
                             const bool pass2 = p.focops_mask_mean != nullptr;
                             const float gate = pass2 ? __ldg(p.focops_mask_mean) : 0.f;
                             dlogp += gate * adv_c * ratio * inv_b;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
             const int a = tid - 64;
             sB3acc[a] += sRed[96 + a] + sRed[112 + a] + sRed[128 + a] + sRed[144 + a];
         }
-        if (p.forward_only) {   // FOCOPS / P3O pass 1: statistics only
+        if (EXT && p.forward_only) {   // FOCOPS / P3O pass 1: statistics only
             if (CHUNKED) { if (has_next) load_chunk(sRowNext, 0); }
             else if (vec && has_next) prefetch_x(sRowNext);
             first_tile = false;
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
     }
 
     // ---- write this CTA's partial gradient segment (staged through smem so that stores coalesce) ----
-    if (p.forward_only) {
+    if (EXT && p.forward_only) {
         if (tid < 8) p.stats_part[((size_t)blockIdx.x * 3 + net) * 8 + tid] = sStat[tid];
     } else {
         float v[16];
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(NTC, 1) minibatch_grad_tc_kernel(TcArgs p) {
         if (tid < L.out) gout[L.off_b3 + tid] = sB3acc[tid];
         if (net == 0 && tid < A) {
             float g = sLs[32 + tid];
-            if (blockIdx.x == 0 && (p.kind == TC_PPO_CLIP || p.kind == TC_P3O || is_focops)) g -= p.entropy_coef / (float)A;
+            if (blockIdx.x == 0 && (p.kind == TC_PPO_CLIP || is_p3o || is_focops)) g -= p.entropy_coef / (float)A;
             // log_std block of the Fisher matrix: (2/A) v, counted once (natural_pg.py:L74-119, analytic form)
             if (is_fvp) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + tid) : 0.f;
             gout[L.off_logstd + tid] = g;
@@ -1050,14 +1052,22 @@ static int launch_grad_tc(const TcArgs& p, int nblocks, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes();
     static bool attr = false;
     if (!attr) {
-        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     const bool single = (p.net_mask & (p.net_mask - 1)) == 0;     // one network: it gets every CTA
     dim3 grid(nblocks, single ? 1 : 3);
-    if (p.O > 64) minibatch_grad_tc_kernel<true><<<grid, NTC, smem, stream>>>(p);
-    else minibatch_grad_tc_kernel<false><<<grid, NTC, smem, stream>>>(p);
+    const bool ext = p.kind == TC_FOCOPS || p.kind == TC_FVP || p.kind == TC_P3O;
+    if (p.O > 64) {
+        if (ext) minibatch_grad_tc_kernel<true, true><<<grid, NTC, smem, stream>>>(p);
+        else minibatch_grad_tc_kernel<true, false><<<grid, NTC, smem, stream>>>(p);
+    } else {
+        if (ext) minibatch_grad_tc_kernel<false, true><<<grid, NTC, smem, stream>>>(p);
+        else minibatch_grad_tc_kernel<false, false><<<grid, NTC, smem, stream>>>(p);
+    }
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
