@@ -210,10 +210,17 @@ int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, 
                       long long total, int stride, float* mu_store, double* workspace, double* out,
                       void* stream);
 __global__ void eval_tc_reduce_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
+    // 32 groups x 8 statistics: group g sums CTAs g, g+32, ... ; the 32 group sums fold in a fixed order
+    __shared__ double sh[32][8];
+    const int q = threadIdx.x & 7, g = threadIdx.x >> 3;
+    double s = 0.0;
+    for (int b = g; b < nblocks; b += 32) s += part[(size_t)b * 8 + q];
+    sh[g][q] = s;
+    __syncthreads();
     if (threadIdx.x < 8) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * 8 + threadIdx.x];
-        out[threadIdx.x] = (threadIdx.x < 6) ? s : 0.0;
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += sh[i][threadIdx.x];
+        out[threadIdx.x] = (threadIdx.x < 6) ? t : 0.0;
     }
 }
 
@@ -238,7 +245,7 @@ int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, 
     actor_eval_tc_kernel<<<blocks, NTHREADS, smem, s>>>(p);
     OSB_LAUNCH_CHECK();
     if (!mu_store) {
-        eval_tc_reduce_kernel<<<1, 32, 0, s>>>(workspace, blocks, out);
+        eval_tc_reduce_kernel<<<1, 256, 0, s>>>(workspace, blocks, out);
         OSB_LAUNCH_CHECK();
     }
     return OSB_OK;
