@@ -11,11 +11,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_gae(dev, rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, lam_c, pen, std=(True, True),
-             estimator='gae'):
+             estimator='gae', keep_ret=True):
     from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 
     T, N = rew.shape
-    buf = VectorOnPolicyBuffer(3, 2, T, gamma, lam, lam_c, estimator, pen, std[0], std[1], num_envs=N, device=dev)
+    # keep_ret=False is the training configuration: 'gae' then runs the segment-sequential kernel
+    buf = VectorOnPolicyBuffer(3, 2, T, gamma, lam, lam_c, estimator, pen, std[0], std[1], num_envs=N, device=dev,
+                               keep_discounted_ret=keep_ret)
     for k, v in (('reward', rew), ('cost', cost), ('value_r', val_r), ('value_c', val_c),
                  ('flags', flags), ('boot_r', boot_r), ('boot_c', boot_c)):
         buf.data[k].copy_(torch.as_tensor(v))
@@ -43,6 +45,8 @@ def _check(buf, ref, rtol=1e-6):
              ('target_value_c', 'tv_c'), ('discounted_ret', 'disc_ret'))
     exact = []
     for ours, theirs in names:
+        if buf.data[ours] is None:          # training configuration: no discounted_ret slab
+            continue
         a = buf.data[ours].cpu().numpy()
         b = ref[theirs]
         # north_star tolerance: fp32 advantages / returns within 1e-5 rtol; we hold 1e-6
@@ -51,10 +55,11 @@ def _check(buf, ref, rtol=1e-6):
     return exact
 
 
-def test_gae_golden_reference_buffer(cuda, golden_dir):
+@pytest.mark.parametrize('keep_ret', [True, False])
+def test_gae_golden_reference_buffer(cuda, golden_dir, keep_ret):
     g = np.load(os.path.join(golden_dir, 'buffer_gae.npz'))
     buf = _run_gae(cuda, g['rew'], g['cost'], g['val_r'], g['val_c'], g['flags'], g['boot_r'], g['boot_c'],
-                   float(g['gamma']), float(g['lam']), float(g['lam_c']), float(g['pen']))
+                   float(g['gamma']), float(g['lam']), float(g['lam_c']), float(g['pen']), keep_ret=keep_ret)
     ref = {'adv_r': g['raw_adv_r'], 'adv_c': g['raw_adv_c'], 'tv_r': g['raw_target_value_r'],
            'tv_c': g['raw_target_value_c'], 'disc_ret': g['raw_discounted_ret']}
     exact = _check(buf, ref)
@@ -98,11 +103,12 @@ def test_other_estimators_vs_oracle(cuda, T, N, estimator):
         assert estimator == 'vtrace' or (a == b).mean() > 0.99, (ours, (a == b).mean())
 
 
+@pytest.mark.parametrize('keep_ret', [True, False])
 @pytest.mark.parametrize('T,N', [(1, 1), (4, 33), (127, 40), (128, 64), (129, 31), (300, 97), (512, 256)])
-def test_gae_vs_oracle_shapes(cuda, T, N):
+def test_gae_vs_oracle_shapes(cuda, T, N, keep_ret):
     rng = np.random.default_rng(T * 1000 + N)
     case = _rand_case(rng, T, N)
-    buf = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.1)
+    buf = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.1, keep_ret=keep_ret)
     ref = ogae.dual_gae_slab(*case, 0.99, 0.95, 0.9, 0.1)
     exact = _check(buf, ref)
     assert min(exact) > 0.99, exact
@@ -186,3 +192,23 @@ def test_buffer_argument_checks(cuda):
     got = buf.get()                      # standardisation off: raw advantages come back
     assert got['obs'].shape == (16, 3) and got['adv_r'].shape == (16,)
     np.testing.assert_allclose(got['adv_r'].cpu().numpy().reshape(2, 8), buf.data['adv_r'].cpu().numpy().T)
+
+
+@pytest.mark.parametrize('T,N', [(128, 4096), (2048, 512), (300, 97), (16, 32), (129, 33)])
+def test_gae_segment_kernel_matches_scan_kernel(cuda, T, N):
+    """Training configuration (no discounted_ret slab -> segment-sequential kernel) vs the chunk-scan kernel:
+    both replay the reference's roundings from an fp64 carry, so they agree to the bit almost everywhere;
+    sampled env columns are checked against the oracle as well."""
+    rng = np.random.default_rng(T + N)
+    case = _rand_case(rng, T, N, p_end=0.02)
+    a = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.05, keep_ret=False)
+    b = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.05, keep_ret=True)
+    for k in ('adv_r', 'adv_c', 'target_value_r', 'target_value_c'):
+        x, y = a.data[k].cpu().numpy(), b.data[k].cpu().numpy()
+        np.testing.assert_allclose(x, y, rtol=1e-6, atol=1e-6, err_msg=k)
+        assert (x == y).mean() > 0.99, (k, (x == y).mean())
+    np.testing.assert_allclose(a.adv_moments.cpu().numpy(), b.adv_moments.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    cols = rng.choice(N, min(N, 24), replace=False)
+    ref = ogae.dual_gae_slab(*[c[:, cols] for c in case], 0.99, 0.95, 0.9, 0.05)
+    np.testing.assert_allclose(a.data['adv_r'].cpu().numpy()[:, cols], ref['adv_r'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(a.data['target_value_c'].cpu().numpy()[:, cols], ref['tv_c'], rtol=1e-6, atol=1e-6)
