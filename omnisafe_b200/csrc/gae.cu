@@ -282,148 +282,6 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Segment-sequential variant for the training path ('gae', no discounted_ret).  A warp = 32 consecutive
-// envs (every load / store is one 128-byte request), a block = 8 warps = 8 time segments of 16 steps
-// (tile = 128 steps).  Each thread folds its 16 steps sequentially into the affine maps of the two
-// advantages (fp64), the 8 segment maps of an env are composed through shared memory (<= 7 serial
-// steps, no shuffles, one barrier), and the replay pass redoes the reference's separately rounded
-// recurrence from the carry-in.  The tile carry is the REPLAYED value of segment 0, so rounding never
-// accumulates across tiles.  4x fewer scan steps per sample than gae_dual_kernel and 2 barriers per tile.
-constexpr int SE = 32, SS = 8, SL = 16, STILE = SS * SL, STHREADS = SE * SS;
-
-__global__ void __launch_bounds__(STHREADS, 2) gae_seg_kernel(GaeArgs p) {
-    __shared__ double sa[2][SS][SE], sb[2][SS][SE];
-    __shared__ double carry[2][SE];
-    __shared__ double red[3 * SS];
-    __shared__ int s_last;
-
-    const int x = threadIdx.x, y = threadIdx.y;      // env lane, time segment (higher y = later)
-    const int lin = y * SE + x;
-    const int env = blockIdx.x * SE + x;
-    const bool env_ok = env < p.N;
-    const int N = p.N, T = p.T;
-    const int ntiles = (T + STILE - 1) / STILE;
-    if (y == 0) { carry[0][x] = 0.0; carry[1][x] = 0.0; }
-    double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
-    __syncthreads();
-
-    for (int k = 0; k < ntiles; ++k) {
-        const int t0 = T - (k + 1) * STILE + y * SL;  // first step of my segment (may be < 0)
-        float dr[SL], dc[SL], vr[SL + 1], vc[SL + 1];
-        unsigned endmask = 0u, validmask = 0u;
-        {
-            float r[SL], c[SL];
-            unsigned f[SL];
-            const size_t ecol = (size_t)(env_ok ? env : 0);
-#pragma unroll
-            for (int i = 0; i < SL; ++i) {        // all loads of the segment are independent: issue them together
-                const int t = t0 + i;
-                const bool ok = env_ok && t >= 0;
-                const size_t idx = (size_t)(ok ? t : 0) * N + ecol;
-                r[i] = ok ? __ldg(p.rew + idx) : 0.f;
-                c[i] = ok ? __ldg(p.cost + idx) : 0.f;
-                vr[i] = ok ? __ldg(p.val_r + idx) : 0.f;
-                vc[i] = ok ? __ldg(p.val_c + idx) : 0.f;
-                f[i] = ok ? (unsigned)__ldg(p.flags + idx) : 0u;
-            }
-            {
-                const int t = t0 + SL;
-                const bool ok = env_ok && t >= 0 && t < T;
-                const size_t idx = (size_t)(ok ? t : 0) * N + ecol;
-                vr[SL] = ok ? __ldg(p.val_r + idx) : 0.f;
-                vc[SL] = ok ? __ldg(p.val_c + idx) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < SL; ++i) {
-                const int t = t0 + i;
-                const bool valid = env_ok && t >= 0;
-                const bool end = valid && (f[i] != 0u || t == T - 1);
-                float nr = vr[i + 1], nc = vc[i + 1];
-                if (end) {
-                    const bool term = (f[i] & OSB_FLAG_TERMINATED) != 0u;
-                    const size_t idx = (size_t)t * N + env;
-                    nr = term ? 0.f : __ldg(p.boot_r + idx);
-                    nc = term ? 0.f : __ldg(p.boot_c + idx);
-                }
-                // fp32 deltas with the reference's separately rounded operations (onpolicy_buffer.py:L185, L301)
-                const float rp = __fadd_rn(r[i], -__fmul_rn(p.pen, c[i]));
-                dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -vr[i]);
-                dc[i] = __fadd_rn(__fadd_rn(c[i], __fmul_rn(p.gamma_f, nc)), -vc[i]);
-                if (valid) validmask |= 1u << i;
-                if (end) endmask |= 1u << i;
-            }
-        }
-        // pass 1: fold the segment into A_in -> b + a * A_in
-        double ar = 1.0, br = 0.0, ac = 1.0, bc = 0.0;
-#pragma unroll
-        for (int i = SL - 1; i >= 0; --i) {
-            if ((validmask >> i) & 1u) {
-                if ((endmask >> i) & 1u) { ar = 0.0; br = (double)dr[i]; ac = 0.0; bc = (double)dc[i]; }
-                else { br = (double)dr[i] + p.gl_r * br; ar = p.gl_r * ar; bc = (double)dc[i] + p.gl_c * bc; ac = p.gl_c * ac; }
-            }
-        }
-        sa[0][y][x] = ar; sb[0][y][x] = br; sa[1][y][x] = ac; sb[1][y][x] = bc;
-        __syncthreads();
-        // carry-in of my segment: compose the later segments of this tile on top of the tile carry
-        double Ar = carry[0][x], Ac = carry[1][x];
-        for (int yy = SS - 1; yy > y; --yy) {
-            Ar = sb[0][yy][x] + sa[0][yy][x] * Ar;
-            Ac = sb[1][yy][x] + sa[1][yy][x] * Ac;
-        }
-        // pass 2: replay sequentially from the carry-in with the reference's roundings (utils/math.py:L77-80)
-#pragma unroll
-        for (int i = SL - 1; i >= 0; --i) {
-            if ((validmask >> i) & 1u) {
-                if ((endmask >> i) & 1u) { Ar = (double)dr[i]; Ac = (double)dc[i]; }
-                else {
-                    Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
-                    Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
-                }
-                const size_t idx = (size_t)(t0 + i) * N + env;
-                const float o_ar = (float)Ar, o_ac = (float)Ac;
-                p.adv_r[idx] = o_ar;
-                p.adv_c[idx] = o_ac;
-                p.tv_r[idx] = (float)(Ar + (double)vr[i]);
-                p.tv_c[idx] = (float)(Ac + (double)vc[i]);
-                st_r += (double)o_ar;
-                st_r2 += (double)o_ar * (double)o_ar;
-                st_c += (double)o_ac;
-            }
-        }
-        __syncthreads();                 // every thread has read carry / sa / sb of this tile
-        if (y == 0) { carry[0][x] = Ar; carry[1][x] = Ac; }     // exact (replayed) value at the tile's first step
-        __syncthreads();
-    }
-    st_r = warp_sum(st_r); st_r2 = warp_sum(st_r2); st_c = warp_sum(st_c);
-    if (x == 0) { red[y] = st_r; red[SS + y] = st_r2; red[2 * SS + y] = st_c; }
-    __syncthreads();
-    if (lin == 0) {
-        double a = 0, b = 0, c = 0;
-        for (int w = 0; w < SS; ++w) { a += red[w]; b += red[SS + w]; c += red[2 * SS + w]; }
-        double* o = p.partials + (size_t)blockIdx.x * 4;
-        o[0] = a; o[1] = b; o[2] = c;
-        const int nenv = min(SE, N - (int)blockIdx.x * SE);
-        o[3] = (double)nenv * (double)T;
-        __threadfence();
-        s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_last && lin < 32) {
-        __threadfence();
-        double acc[4] = {0, 0, 0, 0};
-        for (int bb = lin; bb < (int)gridDim.x; bb += 32)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] += __ldcg(p.partials + (size_t)bb * 4 + q);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
-        if (lin == 0) {
-            for (int q = 0; q < 4; ++q) p.sums[q] = acc[q];
-            *p.ticket = 0u;
-        }
-    }
-}
-
 // sums[4] = {sum adv_r, sum adv_r^2, sum adv_c, count}; one warp, fixed order.
 __global__ void gae_stats_reduce_kernel(const double* __restrict__ partials, int nblocks,
                                         double* __restrict__ sums) {
@@ -549,10 +407,10 @@ int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, co
     } else if (ret) {
         gae_dual_kernel<false, 0, true><<<nblocks, blk, 0, s>>>(a);
     } else {
-        // training path: segment-sequential kernel (OSB_GAE_SCAN=1 selects the chunk-scan kernel for A/B timing)
-        static const bool scan = getenv("OSB_GAE_SCAN") != nullptr;
-        if (scan) gae_dual_kernel<false, 0, false><<<nblocks, blk, 0, s>>>(a);
-        else gae_seg_kernel<<<(N + SE - 1) / SE, dim3(SE, SS), 0, s>>>(a);
+        // training path (no discounted_ret slab): two scans instead of three.  A segment-sequential variant
+        // (32-env warps, 16-step segments composed through shared memory) was measured slower at every
+        // horizon (12.7 vs 11.5 us at T=128, 1.4 vs 2.8 TB/s at T=2048): too few warps, too long chains.
+        gae_dual_kernel<false, 0, false><<<nblocks, blk, 0, s>>>(a);
     }
     OSB_LAUNCH_CHECK();
     return OSB_OK;

@@ -15,7 +15,7 @@ def _run_gae(dev, rew, cost, val_r, val_c, flags, boot_r, boot_c, gamma, lam, la
     from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 
     T, N = rew.shape
-    # keep_ret=False is the training configuration: 'gae' then runs the segment-sequential kernel
+    # keep_ret=False is the training configuration: the instantiation without the discounted-return scan
     buf = VectorOnPolicyBuffer(3, 2, T, gamma, lam, lam_c, estimator, pen, std[0], std[1], num_envs=N, device=dev,
                                keep_discounted_ret=keep_ret)
     for k, v in (('reward', rew), ('cost', cost), ('value_r', val_r), ('value_c', val_c),
@@ -195,10 +195,10 @@ def test_buffer_argument_checks(cuda):
 
 
 @pytest.mark.parametrize('T,N', [(128, 4096), (2048, 512), (300, 97), (16, 32), (129, 33)])
-def test_gae_segment_kernel_matches_scan_kernel(cuda, T, N):
-    """Training configuration (no discounted_ret slab -> segment-sequential kernel) vs the chunk-scan kernel:
-    both replay the reference's roundings from an fp64 carry, so they agree to the bit almost everywhere;
-    sampled env columns are checked against the oracle as well."""
+def test_gae_training_instantiation_matches_full_one(cuda, T, N):
+    """Training configuration (no discounted_ret slab -> two-scan instantiation) vs the three-scan one: the
+    advantage scans are the same arithmetic, so they agree to the bit; sampled env columns are checked
+    against the oracle as well (incl. the headline size and a 16-tile horizon)."""
     rng = np.random.default_rng(T + N)
     case = _rand_case(rng, T, N, p_end=0.02)
     a = _run_gae(cuda, *case, 0.99, 0.95, 0.9, 0.05, keep_ret=False)

@@ -1,11 +1,10 @@
-"""CUDA-event timing of the dual-GAE launch (training configuration) at several horizons; run once as is and once
-with OSB_GAE_SCAN=1 to compare the segment-sequential kernel with the chunk-scan kernel."""
+"""CUDA-event timing of the dual-GAE launch (training configuration: no discounted_ret slab) at several horizons."""
 import json, os, sys
 import torch
 sys.path.insert(0, '.')
 from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
 
-out = {'kernel': 'chunk-scan' if os.environ.get('OSB_GAE_SCAN') else 'segment-sequential'}
+out = {'kernel': 'gae_dual_kernel<false, 0, false>'}
 for T, N in ((128, 4096), (512, 4096), (2048, 4096), (128, 32768)):
     buf = VectorOnPolicyBuffer(4, 2, T, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=N, device='cuda', keep_discounted_ret=False)
     for k in ('reward', 'cost', 'value_r', 'value_c', 'boot_r', 'boot_c'):
