@@ -138,6 +138,57 @@ struct FusedOptArgs {
     float lr[3];
 };
 
+// Fixed-order sum of the per-CTA partial gradients of one parameter, 16 loads in flight at a time
+// (the in-order issue would otherwise serialise one L2 round trip per small batch).
+__device__ __forceinline__ float reduce_partials16(const float* __restrict__ gpart, int nblocks, int P, int q) {
+    float g = 0.f;
+    for (int b = 0; b < nblocks; b += 16) {
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = (b + u < nblocks) ? __ldcg(gpart + (size_t)(b + u) * P + q) : 0.f;
+        g += (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) +
+             (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
+    }
+    return g;
+}
+
+// After the grid barrier: warp 0 of every CTA folds the per-CTA squared norms (lanes stride over CTAs, fixed
+// butterfly) into the clip scale and the Adam step sizes; in CTA 0 warp 1 folds the loss statistics.
+__device__ __forceinline__ void clip_scale_and_stats(const FusedOptArgs& p, int net, int step_t, float* s_scale,
+                                                     float* s_step, float* s_bc2) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+    if (warp == 0 || (warp == 1 && blockIdx.x == 0)) {
+        float tot = 0.f, t2 = 0.f;
+        for (int b = lane; b < G; b += 32) { tot += __ldcg(p.r.sumsq_part + net * G + b); t2 += __ldcg(p.r.sumsq_part + (3 + net) * G + b); }
+        tot = warp_sum(tot); t2 = warp_sum(t2);
+        if (warp == 0) {
+            if (lane == 0) {
+                *s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
+                const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
+                *s_step = (float)((double)p.lr[net] / bc1);
+                *s_bc2 = (float)sqrt(bc2);
+            }
+        } else {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int b = lane; b < p.r.nblocks; b += 32)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] += __ldcg(p.r.stats_part + ((size_t)b * 3 + net) * 8 + i);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane == 0) {
+                p.r.adam_step[net] = step_t;                   // every CTA read it before the grid barrier
+                const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
+                float* ts = p.r.train_stats + net * 8;
+                ts[0] += acc[0] * inv + ((net != 0) ? p.r.critic_norm_coef * t2 : 0.f);
+                ts[1] += acc[1] * inv;
+                ts[2] += acc[2] * inv;
+                ts[3] += 1.f;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
     namespace cg = cooperative_groups;
     if (p.r.stop_flag && *p.r.stop_flag) return;          // uniform across the grid
@@ -154,14 +205,7 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
     if (active) {
         step_t = p.r.adam_step[net] + 1;                   // read before the grid barrier, bumped after it
         if (pl < L.size) {
-            // fixed-order reduction with 7 independent accumulators (loads in flight together)
-            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int b = 0;
-            for (; b + 7 <= p.r.nblocks; b += 7)
-#pragma unroll
-                for (int u = 0; u < 7; ++u) acc[u] += p.r.gpart[(size_t)(b + u) * p.r.P + q];
-            for (; b < p.r.nblocks; ++b) acc[0] += p.r.gpart[(size_t)b * p.r.P + q];
-            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + acc[6]);
+            g = reduce_partials16(p.r.gpart, p.r.nblocks, p.r.P, q);
             th = p.r.theta[q];
             if (net != 0 && p.r.critic_norm_coef > 0.f) g += 2.f * p.r.critic_norm_coef * th;
         }
@@ -176,26 +220,7 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
         }
     }
     cg::this_grid().sync();
-    if (active && threadIdx.x == 0) {
-        float tot = 0.f, t2 = 0.f;
-        for (int b = 0; b < (int)gridDim.x; ++b) { tot += p.r.sumsq_part[net * gridDim.x + b]; t2 += p.r.sumsq_part[(3 + net) * gridDim.x + b]; }
-        s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
-        const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
-        s_step = (float)((double)p.lr[net] / bc1);
-        s_bc2 = (float)sqrt(bc2);
-        if (blockIdx.x == 0) {
-            p.r.adam_step[net] = step_t;                   // every CTA read it before the grid barrier
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int b = 0; b < p.r.nblocks; ++b)
-                for (int i = 0; i < 4; ++i) acc[i] += p.r.stats_part[((size_t)b * 3 + net) * 8 + i];
-            const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
-            float* ts = p.r.train_stats + net * 8;
-            ts[0] += acc[0] * inv + ((net != 0) ? p.r.critic_norm_coef * t2 : 0.f);
-            ts[1] += acc[1] * inv;
-            ts[2] += acc[2] * inv;
-            ts[3] += 1.f;
-        }
-    }
+    if (active) clip_scale_and_stats(p, net, step_t, &s_scale, &s_step, &s_bc2);
     __syncthreads();
     if (active && pl < L.size) {
         g *= s_scale;
@@ -251,13 +276,7 @@ __global__ void __launch_bounds__(OT) optim_fused_p2p_kernel(P2POptArgs a) {
     if (active) {
         step_t = p.r.adam_step[net] + 1;
         if (pl < L.size) {
-            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int b = 0;
-            for (; b + 7 <= p.r.nblocks; b += 7)
-#pragma unroll
-                for (int u = 0; u < 7; ++u) acc[u] += p.r.gpart[(size_t)(b + u) * p.r.P + q];
-            for (; b < p.r.nblocks; ++b) acc[0] += p.r.gpart[(size_t)b * p.r.P + q];
-            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + acc[6]);
+            g = reduce_partials16(p.r.gpart, p.r.nblocks, p.r.P, q);
             th = p.r.theta[q];
             if (net != 0 && p.r.critic_norm_coef > 0.f) g += 2.f * p.r.critic_norm_coef * th;
         }
@@ -272,26 +291,7 @@ __global__ void __launch_bounds__(OT) optim_fused_p2p_kernel(P2POptArgs a) {
         }
     }
     cg::this_grid().sync();
-    if (active && threadIdx.x == 0) {
-        float tot = 0.f, t2 = 0.f;
-        for (int b = 0; b < (int)gridDim.x; ++b) { tot += p.r.sumsq_part[net * gridDim.x + b]; t2 += p.r.sumsq_part[(3 + net) * gridDim.x + b]; }
-        s_scale = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
-        const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
-        s_step = (float)((double)p.lr[net] / bc1);
-        s_bc2 = (float)sqrt(bc2);
-        if (blockIdx.x == 0) {
-            p.r.adam_step[net] = step_t;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int b = 0; b < p.r.nblocks; ++b)
-                for (int i = 0; i < 4; ++i) acc[i] += p.r.stats_part[((size_t)b * 3 + net) * 8 + i];
-            const float inv = acc[3] > 0.f ? 1.f / acc[3] : 0.f;
-            float* ts = p.r.train_stats + net * 8;
-            ts[0] += acc[0] * inv + ((net != 0) ? p.r.critic_norm_coef * t2 : 0.f);
-            ts[1] += acc[1] * inv;
-            ts[2] += acc[2] * inv;
-            ts[3] += 1.f;
-        }
-    }
+    if (active) clip_scale_and_stats(p, net, step_t, &s_scale, &s_step, &s_bc2);
     __syncthreads();
     // ---- publish the clipped gradient, exchange flags over NVLink, sum the peers ---------------------
     float* mine = a.peer_buf[a.rank] + (size_t)par * p.r.P;
