@@ -189,28 +189,6 @@ __device__ __forceinline__ void clip_scale_and_stats(const FusedOptArgs& p, int 
     }
 }
 
-// Software grid barrier for optim_fused_kernel: its <= 3 x 34 CTAs of 256 threads are always co-resident (the
-// stream serialises it behind the gradient kernel, nothing else shares the device), so a sense-reversing
-// counter in global memory replaces the cooperative launch and its launch overhead.  One use per launch.
-__device__ unsigned int g_bar_count = 0;
-__device__ volatile unsigned int g_bar_sense = 0;
-__device__ __forceinline__ void soft_grid_barrier(unsigned int total) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int s = g_bar_sense;
-        __threadfence();
-        if (atomicAdd(&g_bar_count, 1u) == total - 1u) {
-            g_bar_count = 0u;
-            __threadfence();
-            g_bar_sense = s ^ 1u;
-        } else {
-            while (g_bar_sense == s) { }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
     namespace cg = cooperative_groups;
     if (p.r.stop_flag && *p.r.stop_flag) return;          // uniform across the grid
@@ -241,7 +219,7 @@ __global__ void __launch_bounds__(OT) optim_fused_kernel(FusedOptArgs p) {
             p.r.sumsq_part[(3 + net) * gridDim.x + blockIdx.x] = t2;
         }
     }
-    soft_grid_barrier(gridDim.x * gridDim.y);
+    cg::this_grid().sync();
     if (active) clip_scale_and_stats(p, net, step_t, &s_scale, &s_step, &s_bc2);
     __syncthreads();
     if (active && pl < L.size) {
@@ -559,10 +537,9 @@ int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, in
     p.r.sumsq_part = sumsq_part; p.r.adam_step = adam_step; p.r.train_stats = train_stats; p.r.stop_flag = stop_flag;
     p.m = adam_m; p.v = adam_v; p.max_grad_norm = max_grad_norm;
     p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
-    // the software grid barrier needs every CTA resident at once: 8 CTAs of 256 threads fit an SM
-    OSB_CHECK_ARG(osb_optim_blocks(O, A) * 3 <= 148 * 6, "network too large for the single-launch optimiser");
-    optim_fused_kernel<<<dim3(osb_optim_blocks(O, A), 3), dim3(OT), 0, (cudaStream_t)stream>>>(p);
-    OSB_LAUNCH_CHECK();
+    void* args[] = {&p};
+    OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
+                                         (cudaStream_t)stream));
     return OSB_OK;
 }
 
