@@ -6,6 +6,9 @@
  * are DEVICE pointers to contiguous row-major arrays the caller owns; `stream` is a cudaStream_t
  * (NULL = default stream).  Every function returns 0 on success, non-zero on failure;
  * osb_last_error() returns the reason.  No function synchronises the host unless stated.
+ * Host-side state (kernel attributes set once, the FOCOPS / P3O scratch scalar, the P2P step counter, the
+ * last-error string) is per process: call the entry points from ONE host thread per device, one
+ * process per GPU -- the way the reference's `distributed.fork` runs it.
  *
  * Slab layout ("time-major"): per-step scalars are [T][N] (env index contiguous), observations
  * [T][N][O], actions [T][N][A].  Sample k of the reference's env-major order
