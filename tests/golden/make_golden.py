@@ -351,6 +351,30 @@ def gen_cpo(name='CPO', fname='update_cpo.npz', seed=7, cost_limit=2.0):
              **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
 
 
+def gen_update_trpo(name='TRPOLag', fname='update_trpolag.npz', seed=17, extra=None):
+    """TRPOLag / OnCRPO / RCPO ._update of the unmodified reference: natural direction, line search, critics."""
+    N, T, O, A = 8, 24, 12, 3
+    algo = _build_algo(name, N, T, O, A, seed, extra_algo=extra, tmax=8, term_prob=0.05)
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    ep_cost = algo._logger.get_stats('Metrics/EpCost')[0]
+    lam0 = float(algo._lagrange.lagrangian_multiplier.item()) if hasattr(algo, '_lagrange') else 0.0
+    _, perms = _record_randperm(algo._update)
+    lam1 = float(algo._lagrange.lagrangian_multiplier.item()) if hasattr(algo, '_lagrange') else 0.0
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    keys = ['Misc/Alpha', 'Misc/FinalStepNorm', 'Misc/xHx', 'Misc/H_inv_g', 'Misc/gradient_norm']
+    if name != 'RCPO':
+        keys.append('Misc/AcceptanceStep')
+    misc = {k.split('/')[1]: _last(lg, k) for k in keys}
+    np.savez(os.path.join(OUT, fname), name=name, N=N, T=T, O=O, A=A, seed=seed, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), ep_cost=ep_cost, lam0=lam0, lam1=lam1, perms=perms, batch_size=32,
+             update_iters=2, kl=_last(lg, 'Train/KL'), **{'extra_' + k: v for k, v in (extra or {}).items()},
+             **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
+
+
 def gen_pid():
     """PIDLagrangian.pid_update (common/pid_lagrange.py:L95-125) over cost sequences that exercise the
     integral clamp, the delayed derivative (deque roll-over) and the three normalisation modes."""
@@ -391,5 +415,7 @@ if __name__ == '__main__':
     gen_update_p3o()
     gen_cpo()
     gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)
+    gen_update_trpo('TRPOLag', 'update_trpolag.npz', seed=17)
+    gen_update_trpo('OnCRPO', 'update_oncrpo.npz', seed=19, extra={'cost_limit': 1.0, 'distance': 0.5})
     gen_pid()
     print('golden fixtures written to', OUT)
