@@ -293,3 +293,41 @@ class PIDLagrangian:
         if len(self.cost_ds) > self.delay:
             self.cost_ds.pop(0)
         return self.cost_penalty
+
+
+def trpo_actor_step(L: 'Learner', obs, act, logp, adv, *, cost_surrogate=False, damping=0.1, cg_iters=15,
+                    target_kl=0.01, total_steps=15, decay=0.8):
+    """NaturalPG._update_actor direction (natural_pg.py:L146-166) + TRPO._search_step_size
+    (trpo.py:L56-138) on the oracle Learner.  `cost_surrogate`: the loss is mean(ratio * adv) instead of
+    -mean(ratio * adv) (OnCRPO's -adv_c surrogate, crpo.py:L55-80, passes adv = adv_c with this flag).
+    Sets the actor parameters to theta_old + accepted step; returns (accept_step, final_kl, step, x, xHx, alpha)."""
+    loss_fn = (lambda: L.loss_pi_cost(obs, act, logp, adv)) if cost_surrogate else (lambda: L.loss_pi_plain(obs, act, logp, adv))
+    theta_old = torch.as_tensor(L.flat('actor')).clone()
+    with torch.no_grad():
+        p = L.dist(obs)
+        p_dist = Normal(p.loc.clone(), p.scale.clone())
+    L.zero_grad('actor')
+    loss_before = loss_fn()
+    loss_before.backward()
+    grads = -L.flat_grad('actor')
+    fvp = lambda v: L.fvp(v, obs, damping)   # noqa: E731
+    x = conjugate_gradients(fvp, grads.numpy(), cg_iters)
+    x_hx = float(x.dot(fvp(x)))
+    alpha = float(np.sqrt(2 * target_kl / (x_hx + 1e-8)))
+    step_direction = alpha * x
+    step_frac, accept, final_kl = 1.0, 0, 0.0
+    for step in range(total_steps):
+        L.set_flat('actor', theta_old + step_frac * step_direction)
+        with torch.no_grad():
+            loss = loss_fn()
+            kl = float(kl_divergence(p_dist, L.dist(obs)).mean())
+        improve = float(loss_before.detach() - loss)
+        if np.isfinite(float(loss)) and improve >= 0 and kl <= target_kl:
+            accept, final_kl = step + 1, kl
+            break
+        step_frac *= decay
+    else:
+        step_direction = torch.zeros_like(step_direction)
+    step = step_frac * step_direction
+    L.set_flat('actor', theta_old + step)
+    return accept, final_kl, step, x, x_hx, alpha

@@ -268,3 +268,34 @@ def test_pcpo_step_golden(golden_dir):
     step = ol.pcpo_step_direction(xhx, hx, p, r, s, float(g['ep_cost']) - float(g['cost_limit']), kl)
     frac = 0.8 ** (int(g['misc_AcceptanceStep'][-1]) - 1)
     np.testing.assert_allclose(float((frac * step).norm()), g['misc_FinalStepNorm'][-1], rtol=5e-3)
+
+
+def test_trpo_family_actor_step_golden(golden_dir):
+    """oracle natural direction + TRPO line search vs the unmodified TRPOLag._update / OnCRPO._update
+    (cost-surrogate branch): same xHx, alpha, accepted step, step norm, KL and actor parameters."""
+    import torch
+
+    from oracle import actor_critic as oac
+    from oracle import learner as ol
+
+    for fname in ('update_trpolag.npz', 'update_oncrpo.npz'):
+        g, data = _load_update(golden_dir, fname)
+        O, A = int(g['O']), int(g['A'])
+        L = ol.Learner(g['theta0'], O, A, lr_actor=None, lr_critic=1e-3)
+        obs, act, logp = (torch.as_tensor(data[k]) for k in ('obs', 'act', 'logp'))
+        adv_r, adv_c = torch.as_tensor(data['adv_r']), torch.as_tensor(data['adv_c'])
+        if str(g['name']) == 'OnCRPO':
+            jc, limit, dist_ = float(g['ep_cost']), float(g['extra_cost_limit']), float(g['extra_distance'])
+            assert jc > limit + dist_            # the fixture exercises the cost branch
+            adv, cost_mode = adv_c, True
+        else:
+            lam = float(g['lam1'])               # the multiplier is updated before the actor (trpo_lag.py:L67-73)
+            adv, cost_mode = (adv_r - lam * adv_c) / (1 + lam), False
+        accept, kl, step, x, x_hx, alpha = ol.trpo_actor_step(L, obs, act, logp, adv, cost_surrogate=cost_mode)
+        assert accept == int(g['misc_AcceptanceStep'][-1])
+        np.testing.assert_allclose([x_hx, alpha, float(step.norm()), float(x.norm())],
+                                   [g['misc_xHx'][-1], g['misc_Alpha'][-1], g['misc_FinalStepNorm'][-1], g['misc_H_inv_g'][-1]],
+                                   rtol=2e-3)
+        np.testing.assert_allclose(kl, g['kl'][-1], rtol=2e-3, atol=1e-7)
+        na = oac.layout(O, A)['actor']['size']
+        np.testing.assert_allclose(L.flat('actor'), g['theta1'][:na], rtol=2e-3, atol=2e-5)
