@@ -133,7 +133,7 @@ class Learner:
 
     def update_ppo(self, data, perms, lam, *, batch_size, clip=0.2, entropy_coef=0.0, use_cost=True,
                    critic_norm_coef=0.001, max_grad_norm=40.0, target_kl=0.02, kl_early_stop=True,
-                   focops=None, p3o=None):
+                   focops=None, p3o=None, plain=False):
         """PolicyGradient._update / FOCOPS._update.  `data` holds env-major tensors as returned by
         VectorOnPolicyBuffer.get(); `perms[i]` is the sample order of pass i (DataLoader shuffle)."""
         t = {k: torch.as_tensor(v) for k, v in data.items()}
@@ -155,6 +155,10 @@ class Learner:
                 if p3o is not None:
                     loss, _ = self.loss_pi_p3o(obs, t['act'][idx], t['logp'][idx], t['adv_r'][idx], t['adv_c'][idx],
                                                clip, p3o['kappa'], p3o['jc_minus_limit'], entropy_coef)
+                elif plain:      # PolicyGradient._loss_pi (policy_gradient.py:L483-524): no clipping
+                    loss = self.loss_pi_plain(obs, t['act'][idx], t['logp'][idx], adv)
+                    if entropy_coef:
+                        loss = loss - entropy_coef * self.dist(obs).entropy().mean()
                 elif focops is None:
                     loss, _ = self.loss_pi_ppo(obs, t['act'][idx], t['logp'][idx], adv, clip, entropy_coef)
                 else:

@@ -150,7 +150,7 @@ class RefSyntheticBox(CMDP):
         return self._kw.get('max_episode_steps', 64)
 
 
-def _build_algo(algo, N, T, O, A, seed, extra_algo=None, tmax=8, term_prob=0.05, epochs=2):
+def _build_algo(algo, N, T, O, A, seed, extra_algo=None, tmax=8, term_prob=0.05, epochs=2, extra_lagrange=None):
     from omnisafe.utils.config import get_default_kwargs_yaml
     from omnisafe.utils.tools import recursive_check_config
     from omnisafe.algorithms import registry
@@ -164,6 +164,8 @@ def _build_algo(algo, N, T, O, A, seed, extra_algo=None, tmax=8, term_prob=0.05,
                         'window_lens': 10},
         'env_cfgs': {'obs_dim': O, 'act_dim': A, 'max_episode_steps': tmax, 'term_prob': term_prob},
     }
+    if extra_lagrange:
+        custom['lagrange_cfgs'] = dict(extra_lagrange)
     env_cfgs = custom.pop('env_cfgs')   # CPO.yaml has no env_cfgs default block: bypass the key check
     recursive_check_config(custom, cfgs)
     cfgs.recurisve_update(custom)
@@ -375,6 +377,30 @@ def gen_update_trpo(name='TRPOLag', fname='update_trpolag.npz', seed=17, extra=N
              **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
 
 
+def gen_update_first_order(name, fname, seed, extra=None, lagrange=None):
+    """IPO / CPPOPID / PDO ._update of the unmodified reference (penalty resp. multiplier from the logged Jc)."""
+    N, T, O, A = 8, 24, 12, 3
+    algo = _build_algo(name, N, T, O, A, seed, extra_algo=extra, tmax=8, term_prob=0.05, extra_lagrange=lagrange)
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    ep_cost = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    if name == 'IPO':
+        lam1 = float(_last(lg, 'Misc/Penalty')[-1])
+    else:
+        lam = algo._lagrange.lagrangian_multiplier
+        lam1 = float(lam.item() if hasattr(lam, 'item') else lam)
+    np.savez(os.path.join(OUT, fname), name=name, N=N, T=T, O=O, A=A, seed=seed, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), ep_cost=ep_cost, lam1=lam1, perms=perms, batch_size=32,
+             update_iters=2, kl=_last(lg, 'Train/KL'), stop_iter=_last(lg, 'Train/StopIter'),
+             loss_pi=_last(lg, 'Loss/Loss_pi'), **{'extra_' + k: v for k, v in (extra or {}).items()},
+             **{'lagrange_' + k: v for k, v in (lagrange or {}).items()}, **{'data_' + k: v for k, v in data.items()})
+
+
 def gen_pid():
     """PIDLagrangian.pid_update (common/pid_lagrange.py:L95-125) over cost sequences that exercise the
     integral clamp, the delayed derivative (deque roll-over) and the three normalisation modes."""
@@ -417,5 +443,8 @@ if __name__ == '__main__':
     gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)
     gen_update_trpo('TRPOLag', 'update_trpolag.npz', seed=17)
     gen_update_trpo('OnCRPO', 'update_oncrpo.npz', seed=19, extra={'cost_limit': 1.0, 'distance': 0.5})
+    gen_update_first_order('IPO', 'update_ipo.npz', 21, {'cost_limit': 6.0, 'kappa': 0.5})
+    gen_update_first_order('CPPOPID', 'update_cppopid.npz', 22, lagrange={'cost_limit': 1.0})
+    gen_update_first_order('PDO', 'update_pdo.npz', 23, lagrange={'cost_limit': 1.0})
     gen_pid()
     print('golden fixtures written to', OUT)

@@ -299,3 +299,28 @@ def test_trpo_family_actor_step_golden(golden_dir):
         np.testing.assert_allclose(kl, g['kl'][-1], rtol=2e-3, atol=1e-7)
         na = oac.layout(O, A)['actor']['size']
         np.testing.assert_allclose(L.flat('actor'), g['theta1'][:na], rtol=2e-3, atol=2e-5)
+
+
+def test_first_order_family_update_golden(golden_dir):
+    """Oracle update with the penalty / multiplier each class derives from Jc == unmodified IPO / CPPOPID /
+    PDO ._update: IPO's interior-point penalty (ipo.py:L68-74), CPPOPID's PID controller
+    (pid_lagrange.py:L95-125), PDO's Adam multiplier on the unclipped policy-gradient loss."""
+    from oracle import learner as ol
+
+    for fname in ('update_ipo.npz', 'update_cppopid.npz', 'update_pdo.npz'):
+        g, data = _load_update(golden_dir, fname)
+        name, O, A, jc = str(g['name']), int(g['O']), int(g['A']), float(g['ep_cost'])
+        if name == 'IPO':
+            lam = float(g['extra_kappa']) / (float(g['extra_cost_limit']) - jc + 1e-8)
+            lam = lam if 0 <= lam <= 1.0 else 1.0                      # penalty_max = 1.0 (IPO.yaml)
+        elif name == 'CPPOPID':
+            pid = ol.PIDLagrangian(0.1, 0.01, 0.01, 10, 0.95, 0.95, True, False, 100.0, 0.001, float(g['lagrange_cost_limit']))
+            lam = pid.pid_update(jc)
+        else:
+            lag = ol.Lagrange(float(g['lagrange_cost_limit']), 0.001, 0.035)
+            lam = lag.update(jc)
+        np.testing.assert_allclose(lam, float(g['lam1']), rtol=1e-5, atol=1e-7, err_msg=name)
+        L = ol.Learner(g['theta0'], O, A)
+        st = L.update_ppo(data, g['perms'][::2], float(lam), batch_size=int(g['batch_size']), plain=(name == 'PDO'))
+        np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6, err_msg=name)
+        np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7, err_msg=name)
