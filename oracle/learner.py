@@ -300,9 +300,9 @@ class PIDLagrangian:
 
 
 def trpo_actor_step(L: 'Learner', obs, act, logp, adv, *, cost_surrogate=False, damping=0.1, cg_iters=15,
-                    target_kl=0.01, total_steps=15, decay=0.8):
+                    target_kl=0.01, total_steps=15, decay=0.8, search=True):
     """NaturalPG._update_actor direction (natural_pg.py:L146-166) + TRPO._search_step_size
-    (trpo.py:L56-138) on the oracle Learner.  `cost_surrogate`: the loss is mean(ratio * adv) instead of
+    (trpo.py:L56-138; `search=False`: plain NaturalPG step) on the oracle Learner.  `cost_surrogate`: the loss is mean(ratio * adv) instead of
     -mean(ratio * adv) (OnCRPO's -adv_c surrogate, crpo.py:L55-80, passes adv = adv_c with this flag).
     Sets the actor parameters to theta_old + accepted step; returns (accept_step, final_kl, step, x, xHx, alpha)."""
     loss_fn = (lambda: L.loss_pi_cost(obs, act, logp, adv)) if cost_surrogate else (lambda: L.loss_pi_plain(obs, act, logp, adv))
@@ -319,6 +319,9 @@ def trpo_actor_step(L: 'Learner', obs, act, logp, adv, *, cost_surrogate=False, 
     x_hx = float(x.dot(fvp(x)))
     alpha = float(np.sqrt(2 * target_kl / (x_hx + 1e-8)))
     step_direction = alpha * x
+    if not search:      # NaturalPG / RCPO: the natural step is taken as is (natural_pg.py:L166-170)
+        L.set_flat('actor', theta_old + step_direction)
+        return 0, 0.0, step_direction, x, x_hx, alpha
     step_frac, accept, final_kl = 1.0, 0, 0.0
     for step in range(total_steps):
         L.set_flat('actor', theta_old + step_frac * step_direction)

@@ -353,10 +353,10 @@ def gen_cpo(name='CPO', fname='update_cpo.npz', seed=7, cost_limit=2.0):
              **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
 
 
-def gen_update_trpo(name='TRPOLag', fname='update_trpolag.npz', seed=17, extra=None):
+def gen_update_trpo(name='TRPOLag', fname='update_trpolag.npz', seed=17, extra=None, lagrange=None):
     """TRPOLag / OnCRPO / RCPO ._update of the unmodified reference: natural direction, line search, critics."""
     N, T, O, A = 8, 24, 12, 3
-    algo = _build_algo(name, N, T, O, A, seed, extra_algo=extra, tmax=8, term_prob=0.05)
+    algo = _build_algo(name, N, T, O, A, seed, extra_algo=extra, tmax=8, term_prob=0.05, extra_lagrange=lagrange)
     theta0 = _flat_theta(algo._actor_critic)
     algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
     data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
@@ -374,6 +374,7 @@ def gen_update_trpo(name='TRPOLag', fname='update_trpolag.npz', seed=17, extra=N
     np.savez(os.path.join(OUT, fname), name=name, N=N, T=T, O=O, A=A, seed=seed, theta0=theta0,
              theta1=_flat_theta(algo._actor_critic), ep_cost=ep_cost, lam0=lam0, lam1=lam1, perms=perms, batch_size=32,
              update_iters=2, kl=_last(lg, 'Train/KL'), **{'extra_' + k: v for k, v in (extra or {}).items()},
+             **{'lagrange_' + k: v for k, v in (lagrange or {}).items()},
              **{'misc_' + k: v for k, v in misc.items()}, **{'data_' + k: v for k, v in data.items()})
 
 
@@ -443,6 +444,7 @@ if __name__ == '__main__':
     gen_cpo('PCPO', 'update_pcpo.npz', seed=11, cost_limit=1.0)
     gen_update_trpo('TRPOLag', 'update_trpolag.npz', seed=17)
     gen_update_trpo('OnCRPO', 'update_oncrpo.npz', seed=19, extra={'cost_limit': 1.0, 'distance': 0.5})
+    gen_update_trpo('RCPO', 'update_rcpo.npz', seed=27, lagrange={'cost_limit': 1.0})
     gen_update_first_order('IPO', 'update_ipo.npz', 21, {'cost_limit': 6.0, 'kappa': 0.5})
     gen_update_first_order('CPPOPID', 'update_cppopid.npz', 22, lagrange={'cost_limit': 1.0})
     gen_update_first_order('PDO', 'update_pdo.npz', 23, lagrange={'cost_limit': 1.0})

@@ -278,7 +278,7 @@ def test_trpo_family_actor_step_golden(golden_dir):
     from oracle import actor_critic as oac
     from oracle import learner as ol
 
-    for fname in ('update_trpolag.npz', 'update_oncrpo.npz'):
+    for fname in ('update_trpolag.npz', 'update_oncrpo.npz', 'update_rcpo.npz'):
         g, data = _load_update(golden_dir, fname)
         O, A = int(g['O']), int(g['A'])
         L = ol.Learner(g['theta0'], O, A, lr_actor=None, lr_critic=1e-3)
@@ -291,12 +291,16 @@ def test_trpo_family_actor_step_golden(golden_dir):
         else:
             lam = float(g['lam1'])               # the multiplier is updated before the actor (trpo_lag.py:L67-73)
             adv, cost_mode = (adv_r - lam * adv_c) / (1 + lam), False
-        accept, kl, step, x, x_hx, alpha = ol.trpo_actor_step(L, obs, act, logp, adv, cost_surrogate=cost_mode)
-        assert accept == int(g['misc_AcceptanceStep'][-1])
+        rcpo = str(g['name']) == 'RCPO'          # NaturalPG family: no line search, no KL logged
+        accept, kl, step, x, x_hx, alpha = ol.trpo_actor_step(L, obs, act, logp, adv, cost_surrogate=cost_mode,
+                                                              search=not rcpo)
+        if not rcpo:
+            assert accept == int(g['misc_AcceptanceStep'][-1])
         np.testing.assert_allclose([x_hx, alpha, float(step.norm()), float(x.norm())],
                                    [g['misc_xHx'][-1], g['misc_Alpha'][-1], g['misc_FinalStepNorm'][-1], g['misc_H_inv_g'][-1]],
                                    rtol=2e-3)
-        np.testing.assert_allclose(kl, g['kl'][-1], rtol=2e-3, atol=1e-7)
+        if not rcpo:
+            np.testing.assert_allclose(kl, g['kl'][-1], rtol=2e-3, atol=1e-7)
         na = oac.layout(O, A)['actor']['size']
         np.testing.assert_allclose(L.flat('actor'), g['theta1'][:na], rtol=2e-3, atol=2e-5)
 
