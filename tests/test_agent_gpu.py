@@ -129,10 +129,11 @@ def test_pid_lagrange_kernel_golden(cuda, golden_dir):
     assert int(pid.nan_flag) == 1
 
 
-@pytest.mark.parametrize('fname', ['update_trpolag.npz', 'update_oncrpo.npz'])
+@pytest.mark.parametrize('fname', ['update_trpolag.npz', 'update_oncrpo.npz', 'update_rcpo.npz'])
 def test_trpo_family_update_golden(cuda, tmp_path, golden_dir, fname):
-    """TRPOLag._update / OnCRPO._update (cost-surrogate branch) of the unmodified reference vs ours on
-    identical data: same natural direction, same accepted line-search step, same parameters afterwards."""
+    """TRPOLag._update / OnCRPO._update (cost-surrogate branch) / RCPO._update (plain natural step) of the
+    unmodified reference vs ours on identical data: same natural direction, same accepted line-search step,
+    same parameters afterwards."""
     import omnisafe_b200
 
     g = np.load(os.path.join(golden_dir, fname))
@@ -146,6 +147,9 @@ def test_trpo_family_update_golden(cuda, tmp_path, golden_dir, fname):
         'logger_cfgs': {'log_dir': str(tmp_path), 'window_lens': 10, 'use_tensorboard': False},
         'env_cfgs': {'obs_dim': O, 'act_dim': A, 'max_episode_steps': 8, 'term_prob': 0.05},
     }
+    lag = {k[9:]: float(g[k]) for k in g.files if k.startswith('lagrange_')}
+    if lag:
+        cfg['lagrange_cfgs'] = lag
     algo = omnisafe_b200.Agent(name, 'SyntheticBox-v0', custom_cfgs=cfg).agent
     algo._actor_critic.load_flat(g['theta0'])
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
@@ -163,10 +167,11 @@ def test_trpo_family_update_golden(cuda, tmp_path, golden_dir, fname):
     algo._update(perm=perms)
     torch.cuda.synchronize()
     m = algo._misc
-    assert int(m['Misc/AcceptanceStep']) == int(g['misc_AcceptanceStep'][-1])
     for key in ('xHx', 'Alpha', 'gradient_norm', 'H_inv_g', 'FinalStepNorm'):
         np.testing.assert_allclose(m[f'Misc/{key}'], g[f'misc_{key}'][-1], rtol=5e-3, atol=1e-5, err_msg=key)
-    np.testing.assert_allclose(float(algo._engine.kl_state[0]), g['kl'][-1], rtol=5e-3, atol=1e-6)
+    if name != 'RCPO':      # the NaturalPG family takes the natural step as is: no acceptance step, no KL logged
+        assert int(m['Misc/AcceptanceStep']) == int(g['misc_AcceptanceStep'][-1])
+        np.testing.assert_allclose(float(algo._engine.kl_state[0]), g['kl'][-1], rtol=5e-3, atol=1e-6)
     if hasattr(algo, '_lagrange'):
         np.testing.assert_allclose(float(algo._lagrange.lagrangian_multiplier), float(g['lam1']), rtol=1e-4, atol=1e-6)
     got, want = algo._actor_critic.theta.cpu().numpy(), g['theta1']
