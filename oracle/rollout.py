@@ -24,14 +24,23 @@ def action_scale(act, lo=-1.0, hi=1.0, mn=-1.0, mx=1.0):
     return (F32(lo) + t).astype(F32)
 
 
-def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_state=None):
+def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_state=None, saute=None):
     """Returns time-major slabs (dict of [T, N, ...] float32 arrays + uint8 flags).
 
     `eps` is the [T, N, A] standard-normal stream; `window` (list) receives (EpRet, EpCost, EpLen)
-    of finished episodes in (step, env) order, like the reference Logger deque."""
+    of finished episodes in (step, env) order, like the reference Logger deque.
+
+    `saute` = {'budget': per-step safety budget, 'gamma': saute_gamma, 'unsafe_reward': r} switches on the
+    SauteAdapter semantics (adapter/saute_adapter.py:L135-217): the network sees [normalised obs | safety
+    state z], z starts at 1, z <- (z - cost / budget) / gamma after every step, the stored reward becomes
+    `unsafe_reward` once z <= 0, z returns to 1 when the episode ends (so final observations carry z = 1,
+    as in the reference); episode returns keep the original reward.  `theta` is then sized for O + 1 inputs."""
     N, O, A = env.N, env.O, env.A
+    On = O + (1 if saute else 0)                     # network input width
+    z = np.ones((N, 1), F32)
+    aug = (lambda x, zz: np.concatenate([x, zz], axis=-1).astype(F32)) if saute else (lambda x, zz: x)
     sl = {
-        'obs': np.zeros((T, N, O), F32), 'act': np.zeros((T, N, A), F32),
+        'obs': np.zeros((T, N, On), F32), 'act': np.zeros((T, N, A), F32),
         'logp': np.zeros((T, N), F32), 'rew': np.zeros((T, N), F32), 'cost': np.zeros((T, N), F32),
         'val_r': np.zeros((T, N), F32), 'val_c': np.zeros((T, N), F32),
         'boot_r': np.zeros((T, N), F32), 'boot_c': np.zeros((T, N), F32),
@@ -39,15 +48,23 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
     }
     ep_ret = np.zeros(N, F32); ep_cost = np.zeros(N, F32); ep_len = np.zeros(N, F32)
     raw = env.reset()
-    obs = norm.normalize(raw) if obs_normalize else raw
+    obs = aug(norm.normalize(raw) if obs_normalize else raw, z)
     for t in range(T):
-        act, v_r, v_c, logp = ac.step(theta, obs, eps[t], O, A)
+        act, v_r, v_c, logp = ac.step(theta, obs, eps[t], On, A)
         nraw, rew, cost, term, trunc, final_raw, fin = env.step(action_scale(act))
         final_norm = np.zeros((N, O), F32)
         if fin.any():
             final_norm[fin] = norm.normalize(final_raw[fin]) if obs_normalize else final_raw[fin]
         nobs = norm.normalize(nraw) if obs_normalize else nraw
         ep_ret = (ep_ret + rew).astype(F32); ep_cost = (ep_cost + cost).astype(F32); ep_len += 1
+        if saute:
+            z = ((z - (cost[:, None] / F32(saute['budget'])).astype(F32)).astype(F32) / F32(saute['gamma'])).astype(F32)
+            safe = (z[:, 0] > 0).astype(F32)
+            rew = (safe * rew + (F32(1) - safe) * F32(saute['unsafe_reward'])).astype(F32)
+            done = (term | trunc).astype(F32)[:, None]
+            z = (z * (F32(1) - done) + done).astype(F32)
+        final_norm = aug(final_norm, z)
+        nobs = aug(nobs, z)
         sl['obs'][t] = obs; sl['act'][t] = act; sl['logp'][t] = logp
         sl['rew'][t] = rew; sl['cost'][t] = cost; sl['val_r'][t] = v_r; sl['val_c'][t] = v_c
         sl['flags'][t] = term.astype(np.uint8) * FLAG_TERMINATED + trunc.astype(np.uint8) * FLAG_TRUNCATED
@@ -56,10 +73,10 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
         need_final = trunc & ~term
         need_next = (~term) & (~trunc) & epoch_end
         if need_final.any():
-            br, bc = ac.values(theta, final_norm, O, A)
+            br, bc = ac.values(theta, final_norm, On, A)
             sl['boot_r'][t][need_final] = br[need_final]; sl['boot_c'][t][need_final] = bc[need_final]
         if np.any(need_next):
-            br, bc = ac.values(theta, obs, O, A)
+            br, bc = ac.values(theta, obs, On, A)
             sl['boot_r'][t][need_next] = br[need_next]; sl['boot_c'][t][need_next] = bc[need_next]
         for i in np.nonzero(fin)[0]:
             if window is not None:

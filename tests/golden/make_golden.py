@@ -182,14 +182,14 @@ def _flat_theta(ac):
     return torch.cat(parts).numpy().copy()
 
 
-def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled=1):
+def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled=1, extra_algo=None):
     """Epoch(s) of the unmodified OnPolicyAdapter.rollout + buffer on the synthetic env.  PDO's defaults
     switch RewardNormalize / CostNormalize on (PDO.yaml:L44-46): the slabs then hold normalised values."""
     import torch.distributions.normal as tdn
     import torch.distributions.utils as tdu
 
     N, T, O, A = 8, 24, 12, 3
-    algo = _build_algo(name, N, T, O, A, seed, epochs=2)
+    algo = _build_algo(name, N, T, O, A, seed, epochs=2, extra_algo=extra_algo)
     theta = _flat_theta(algo._actor_critic)
     drawn = []
     orig = tdn._standard_normal
@@ -229,6 +229,7 @@ def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled
                 extra.update({f'{key}_mean': z.mean.numpy(), f'{key}_std': z.std.numpy(), f'{key}_count': int(z._count)})
         w = getattr(w, '_env', None)
     got = algo._buf.get()
+    extra.update({'algo_' + k: v for k, v in (extra_algo or {}).items()})
     np.savez(os.path.join(OUT, fname), N=N, T=T, O=O, A=A, seed=seed, theta=theta, epochs_rolled=epochs_rolled, **extra,
              eps=eps, tmax=8, term_prob=0.05, gamma=0.99, lam=0.95, lam_c=0.95,
              norm_mean=nz.mean.numpy(), norm_std=nz.std.numpy(), norm_count=int(nz._count),
@@ -438,6 +439,8 @@ if __name__ == '__main__':
     algo = gen_rollout()
     gen_update_ppolag(algo)
     gen_rollout('PDO', 'rollout_pdo.npz', seed=9, epochs_rolled=2)
+    gen_rollout('PPOSaute', 'rollout_pposaute.npz', seed=31,
+                extra_algo={'safety_budget': 2.0, 'saute_gamma': 0.9, 'max_ep_len': 8, 'unsafe_reward': -0.5})
     gen_update_focops()
     gen_update_p3o()
     gen_cpo()

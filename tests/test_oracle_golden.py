@@ -328,3 +328,32 @@ def test_first_order_family_update_golden(golden_dir):
         st = L.update_ppo(data, g['perms'][::2], float(lam), batch_size=int(g['batch_size']), plain=(name == 'PDO'))
         np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6, err_msg=name)
         np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-4, atol=1e-7, err_msg=name)
+
+
+def test_rollout_saute_golden(golden_dir):
+    """Oracle rollout with the SauteAdapter semantics (safety-state augmentation, unsafe reward, z = 1 on the
+    final observations) == unmodified PPOSaute rollout on the synthetic env (adapter/saute_adapter.py:L135-217).
+    Pins the specification of the §8f rank-4 row before its CUDA implementation exists."""
+    g = np.load(os.path.join(golden_dir, 'rollout_pposaute.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    gam, L = float(g['algo_saute_gamma']), float(g['algo_max_ep_len'])
+    budget = float(g['algo_safety_budget']) * (1 - gam ** L) / (1 - gam) / L       # saute_adapter.py:L62-68
+    env = SyntheticBoxEnv(N, O, A, max_episode_steps=int(g['tmax']), seed=int(g['seed']),
+                          term_prob=float(g['term_prob']))
+    norm = Normalizer((O,))
+    window = []
+    sl = orollout.rollout_epoch(env, norm, g['theta'], T, g['eps'], window=window,
+                                saute={'budget': budget, 'gamma': gam, 'unsafe_reward': float(g['algo_unsafe_reward'])})
+    tol = dict(rtol=1e-5, atol=1e-5)
+    assert sl['obs'].shape == g['slab_obs'].shape == (T, N, O + 1)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **tol)
+    np.testing.assert_allclose(sl['act'], g['slab_act'], **tol)
+    np.testing.assert_allclose(sl['rew'], g['slab_reward'], **tol)
+    assert (sl['rew'] == np.float32(-0.5)).mean() > 0.2          # the unsafe branch is exercised
+    assert np.array_equal(sl['cost'], g['slab_cost'])
+    np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], **tol)
+    out = ogae.dual_gae_slab(sl['rew'], sl['cost'], sl['val_r'], sl['val_c'], sl['flags'], sl['boot_r'], sl['boot_c'],
+                             float(g['gamma']), float(g['lam']), float(g['lam_c']))
+    np.testing.assert_allclose(out['adv_r'], g['slab_adv_r'], rtol=1e-4, atol=2e-5)      # bootstrap on z = 1 finals
+    w = np.array(window[-10:], np.float32)
+    np.testing.assert_allclose(w[:, 0], g['win_ret'], rtol=1e-5, atol=1e-5)              # returns keep the raw reward
