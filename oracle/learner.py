@@ -338,3 +338,38 @@ def trpo_actor_step(L: 'Learner', obs, act, logp, adv, *, cost_surrogate=False, 
     step = step_frac * step_direction
     L.set_flat('actor', theta_old + step)
     return accept, final_kl, step, x, x_hx, alpha
+
+
+class SimmerPIDAgent:
+    """Safety-budget controller of the Simmer adapter (common/simmer_agent.py:L91-170): a PID on the polyak-
+    blurred error budget - cost, integral over the last 10 errors, fp32 tensors of shape [N, 1]."""
+
+    def __init__(self, kp, ki, kd, polyak, budget_bound, action_space=(-1.0, 1.0)):
+        self.kp, self.ki, self.kd, self.polyak = kp, ki, kd, polyak
+        self.bound = torch.as_tensor(budget_bound, dtype=torch.float32)
+        self.lo, self.hi = action_space
+        self.prev_action = torch.zeros(1)
+        self.prev_error = torch.zeros(1)
+        self.prev_raw_action = torch.zeros(1)
+        self.integral = []            # deque(maxlen=10)
+
+    def act(self, safety_budget: torch.Tensor, observation: torch.Tensor) -> torch.Tensor:
+        current_error = safety_budget - observation
+        blurred = self.polyak * self.prev_error + (1 - self.polyak) * current_error
+        self.integral.append(blurred)
+        if len(self.integral) > 10:
+            self.integral.pop(0)
+        sum_history = torch.as_tensor(sum(self.integral))
+        raw = self.kp * blurred + self.ki * sum_history + self.kd * (self.prev_action - self.prev_raw_action)
+        action = torch.clamp(raw, min=self.lo, max=self.hi)
+        nxt = torch.clamp(safety_budget + action, 1e-6 * torch.ones_like(safety_budget), self.bound)
+        self.prev_action, self.prev_raw_action, self.prev_error = nxt - safety_budget, raw, blurred
+        return nxt
+
+
+def simmer_control_budget(agent: SimmerPIDAgent, safety_budget, ep_cost, saute_gamma, max_ep_len):
+    """SimmerAdapter.control_budget (adapter/simmer_adapter.py:L113-131): the episode cost is put on the
+    per-step discounted scale of the budgets before the controller acts."""
+    scale = (1 - saute_gamma ** max_ep_len) / (1 - saute_gamma) / max_ep_len
+    obs = torch.as_tensor(ep_cost, dtype=torch.float32) * scale
+    return agent.act(torch.as_tensor(safety_budget, dtype=torch.float32), obs)

@@ -34,10 +34,11 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
     SauteAdapter semantics (adapter/saute_adapter.py:L135-217): the network sees [normalised obs | safety
     state z], z starts at 1, z <- (z - cost / budget) / gamma after every step, the stored reward becomes
     `unsafe_reward` once z <= 0, z returns to 1 when the episode ends (so final observations carry z = 1,
-    as in the reference); episode returns keep the original reward.  `theta` is then sized for O + 1 inputs."""
+    as in the reference); episode returns keep the original reward.  'z0' (Simmer, adapter/simmer_adapter.py:L97-111)
+    is the value z takes at the epoch's reset, the relative safety budget; episode ends still reset it to 1.  `theta` is then sized for O + 1 inputs."""
     N, O, A = env.N, env.O, env.A
     On = O + (1 if saute else 0)                     # network input width
-    z = np.ones((N, 1), F32)
+    z = np.full((N, 1), F32(saute.get('z0', 1.0)) if saute else F32(1), F32)   # Simmer starts an epoch at the relative budget
     aug = (lambda x, zz: np.concatenate([x, zz], axis=-1).astype(F32)) if saute else (lambda x, zz: x)
     sl = {
         'obs': np.zeros((T, N, On), F32), 'act': np.zeros((T, N, A), F32),

@@ -403,6 +403,32 @@ def gen_update_first_order(name, fname, seed, extra=None, lagrange=None):
              **{'lagrange_' + k: v for k, v in (lagrange or {}).items()}, **{'data_' + k: v for k, v in data.items()})
 
 
+def gen_simmer():
+    """SimmerAdapter.control_budget + SimmerPIDAgent (adapter/simmer_adapter.py:L113-131, common/simmer_agent.py:L91-170)
+    over a cost sequence, two controller settings; then one PPOSimmerPID rollout whose epoch starts at the
+    controlled relative budget."""
+    from omnisafe.common.simmer_agent import SimmerPIDAgent
+    from omnisafe.utils.config import Config
+
+    rng = np.random.default_rng(8)
+    costs = np.concatenate([np.linspace(0, 40, 20), 25 + 10 * rng.standard_normal(30), np.linspace(40, 0, 20)]).astype(np.float32)
+    out = {'costs': costs}
+    gam, L = 0.999, 1000
+    scale = (1 - gam ** L) / (1 - gam) / L
+    for i, (kp, ki, kd, polyak) in enumerate([(0.0005, 0.00001, 0.0, 0.995), (0.05, 0.002, 0.3, 0.5)]):
+        bound = torch.ones(3, 1) * 25.0 * scale
+        agent = SimmerPIDAgent(cfgs=Config.dict2config({'kp': kp, 'ki': ki, 'kd': kd, 'polyak': polyak}), budget_bound=bound)
+        budget = torch.ones(3, 1) * 15.0 * scale
+        hist = []
+        for c in costs:
+            budget = agent.act(safety_budget=budget, observation=torch.as_tensor(c) * scale)
+            hist.append(budget.numpy().copy())
+        out[f'budget_{i}'] = np.stack(hist)
+        out[f'cfg_{i}'] = np.array([kp, ki, kd, polyak])
+    out['scale'] = scale
+    np.savez(os.path.join(OUT, 'simmer_controller.npz'), **out)
+
+
 def gen_pid():
     """PIDLagrangian.pid_update (common/pid_lagrange.py:L95-125) over cost sequences that exercise the
     integral clamp, the delayed derivative (deque roll-over) and the three normalisation modes."""
@@ -451,5 +477,8 @@ if __name__ == '__main__':
     gen_update_first_order('IPO', 'update_ipo.npz', 21, {'cost_limit': 6.0, 'kappa': 0.5})
     gen_update_first_order('CPPOPID', 'update_cppopid.npz', 22, lagrange={'cost_limit': 1.0})
     gen_update_first_order('PDO', 'update_pdo.npz', 23, lagrange={'cost_limit': 1.0})
+    gen_simmer()
+    gen_rollout('PPOSimmerPID', 'rollout_pposimmer.npz', seed=33,
+                extra_algo={'safety_budget': 1.0, 'upper_budget': 2.0, 'saute_gamma': 0.9, 'max_ep_len': 8, 'unsafe_reward': -0.5})
     gen_pid()
     print('golden fixtures written to', OUT)

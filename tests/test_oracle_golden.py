@@ -357,3 +357,37 @@ def test_rollout_saute_golden(golden_dir):
     np.testing.assert_allclose(out['adv_r'], g['slab_adv_r'], rtol=1e-4, atol=2e-5)      # bootstrap on z = 1 finals
     w = np.array(window[-10:], np.float32)
     np.testing.assert_allclose(w[:, 0], g['win_ret'], rtol=1e-5, atol=1e-5)              # returns keep the raw reward
+
+
+def test_simmer_controller_and_rollout_golden(golden_dir):
+    """Oracle SimmerPIDAgent == the reference controller over a cost sequence (two gain settings, the clamp to
+    the budget bound included), and the oracle rollout started at the relative budget == an unmodified
+    PPOSimmerPID rollout (adapter/simmer_adapter.py:L97-131)."""
+    import torch
+
+    from oracle import learner as ol
+
+    c = np.load(os.path.join(golden_dir, 'simmer_controller.npz'))
+    scale = float(c['scale'])
+    for i in range(2):
+        kp, ki, kd, polyak = (float(v) for v in c[f'cfg_{i}'])
+        agent = ol.SimmerPIDAgent(kp, ki, kd, polyak, torch.ones(3, 1) * 25.0 * scale)
+        budget = torch.ones(3, 1) * 15.0 * scale
+        hist = []
+        for cost in c['costs']:
+            budget = agent.act(budget, torch.as_tensor(cost) * scale)
+            hist.append(budget.numpy().copy())
+        np.testing.assert_allclose(np.stack(hist), c[f'budget_{i}'], rtol=1e-6, atol=1e-7)
+
+    g = np.load(os.path.join(golden_dir, 'rollout_pposimmer.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    gam, L = float(g['algo_saute_gamma']), float(g['algo_max_ep_len'])
+    per_step = (1 - gam ** L) / (1 - gam) / L
+    budget, upper = float(g['algo_safety_budget']) * per_step, float(g['algo_upper_budget']) * per_step
+    env = SyntheticBoxEnv(N, O, A, max_episode_steps=int(g['tmax']), seed=int(g['seed']), term_prob=float(g['term_prob']))
+    sl = orollout.rollout_epoch(env, Normalizer((O,)), g['theta'], T, g['eps'],
+                                saute={'budget': budget, 'gamma': gam, 'unsafe_reward': float(g['algo_unsafe_reward']),
+                                       'z0': budget / upper})
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sl['rew'], g['slab_reward'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], rtol=1e-5, atol=1e-5)
