@@ -105,6 +105,40 @@ class Learner:
         surr_cadv = (ratio * adv_c).mean()
         return loss_reward + kappa * torch.relu(surr_cadv + jc_minus_limit), ratio
 
+    def loss_pi_cup(self, obs, act, logp, adv_c, old_mean, old_std, lam, coef):
+        """CUP._loss_pi_cost (first_order/cup.py:L93-147): lambda * coef * ratio * adv_c + KL(new || old), mean over
+        the [b, 1] tensor (the [b] surrogate broadcasts against the [b, 1] KL exactly as in the reference)."""
+        d = self.dist(obs)
+        ratio = torch.exp(d.log_prob(act).sum(-1) - logp)
+        kl = kl_divergence(d, Normal(old_mean, old_std)).sum(-1, keepdim=True)
+        return (lam * coef * ratio * adv_c + kl).mean()
+
+    def update_cup_stage2(self, data, perms, lam, *, batch_size, gamma=0.99, lam_gae=0.95, max_grad_norm=40.0,
+                          target_kl=0.02, kl_early_stop=True):
+        """Second stage of CUP._update (cup.py:L163-215): actor-only minibatch steps on the cost projection loss,
+        KL early stop against the policy the stage started from.  Returns the number of passes executed."""
+        t = {k: torch.as_tensor(v) for k, v in data.items()}
+        obs_all = t['obs']
+        with torch.no_grad():
+            old = self.dist(obs_all)
+            old_mean, old_std = old.loc.clone(), old.scale.clone()
+        old = Normal(old_mean, old_std)
+        coef = (1 - gamma * lam_gae) / (1 - gamma)
+        done = 0
+        for perm in perms:
+            perm = torch.as_tensor(np.asarray(perm, np.int64))
+            for s in range(0, len(perm), batch_size):
+                idx = perm[s:s + batch_size]
+                loss = self.loss_pi_cup(obs_all[idx], t['act'][idx], t['logp'][idx], t['adv_c'][idx], old_mean[idx],
+                                        old_std[idx], lam, coef)
+                self._step('actor', loss, max_grad_norm)
+            done += 1
+            with torch.no_grad():
+                kl = kl_divergence(old, self.dist(obs_all)).sum(-1, keepdim=True).mean().item()
+            if kl_early_stop and kl > target_kl:
+                break
+        return done
+
     def loss_pi_focops(self, obs, act, logp, adv, old_mean, old_std, lam_f, eta, entropy_coef=0.0):
         # NB: as in the reference, kl is [b, 1] while ratio * adv is [b]: the difference broadcasts
         # to [b, b] before the mean (first_order/focops.py:L85-89).  Kept verbatim for parity.

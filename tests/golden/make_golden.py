@@ -429,6 +429,26 @@ def gen_simmer():
     np.savez(os.path.join(OUT, 'simmer_controller.npz'), **out)
 
 
+def gen_update_cup():
+    """CUP._update of the unmodified reference: the PPO stage on adv_r, then the cost-projection stage."""
+    N, T, O, A, seed = 8, 24, 12, 3, 29
+    algo = _build_algo('CUP', N, T, O, A, seed, tmax=8, term_prob=0.05, extra_lagrange={'cost_limit': 1.0})
+    theta0 = _flat_theta(algo._actor_critic)
+    algo._env.rollout(steps_per_epoch=T, agent=algo._actor_critic, buffer=algo._buf, logger=algo._logger)
+    data = {k: v.numpy().copy() for k, v in algo._buf.get().items()}
+    algo._buf.get = lambda: {k: torch.as_tensor(v) for k, v in data.items()}      # CUP reads the buffer twice
+    Jc = algo._logger.get_stats('Metrics/EpCost')[0]
+    _, perms = _record_randperm(algo._update)
+    B = data['obs'].shape[0]
+    perms = np.stack([p.numpy() for p in perms if p.numel() == B])
+    lg = algo._logger
+    np.savez(os.path.join(OUT, 'update_cup.npz'), N=N, T=T, O=O, A=A, seed=seed, theta0=theta0,
+             theta1=_flat_theta(algo._actor_critic), Jc=Jc, lam1=float(algo._lagrange.lagrangian_multiplier.item()),
+             perms=perms, batch_size=32, update_iters=2, cost_limit=1.0, stop_iter=_last(lg, 'Train/StopIter'),
+             second_stop_iter=_last(lg, 'Train/SecondStepStopIter'), kl=_last(lg, 'Train/KL'),
+             **{'data_' + k: v for k, v in data.items()})
+
+
 def gen_pid():
     """PIDLagrangian.pid_update (common/pid_lagrange.py:L95-125) over cost sequences that exercise the
     integral clamp, the delayed derivative (deque roll-over) and the three normalisation modes."""
@@ -477,6 +497,7 @@ if __name__ == '__main__':
     gen_update_first_order('IPO', 'update_ipo.npz', 21, {'cost_limit': 6.0, 'kappa': 0.5})
     gen_update_first_order('CPPOPID', 'update_cppopid.npz', 22, lagrange={'cost_limit': 1.0})
     gen_update_first_order('PDO', 'update_pdo.npz', 23, lagrange={'cost_limit': 1.0})
+    gen_update_cup()
     gen_simmer()
     gen_rollout('PPOSimmerPID', 'rollout_pposimmer.npz', seed=33,
                 extra_algo={'safety_budget': 1.0, 'upper_budget': 2.0, 'saute_gamma': 0.9, 'max_ep_len': 8, 'unsafe_reward': -0.5})

@@ -391,3 +391,20 @@ def test_simmer_controller_and_rollout_golden(golden_dir):
     np.testing.assert_allclose(sl['obs'], g['slab_obs'], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(sl['rew'], g['slab_reward'], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], rtol=1e-5, atol=1e-5)
+
+
+def test_cup_update_golden(golden_dir):
+    """Oracle CUP (PPO stage on adv_r, then the KL-regularised cost projection stage, first_order/cup.py:L93-215)
+    == unmodified CUP._update.  Pins the specification before the CUDA loss kind exists."""
+    from oracle import learner as ol
+
+    g, data = _load_update(golden_dir, 'update_cup.npz')
+    O, A = int(g['O']), int(g['A'])
+    lam = ol.Lagrange(float(g['cost_limit']), 0.001, 0.035).update(float(g['Jc']))
+    np.testing.assert_allclose(lam, float(g['lam1']), rtol=1e-5)
+    L = ol.Learner(g['theta0'], O, A)
+    st = L.update_ppo(data, g['perms'][0:4:2], 0.0, batch_size=int(g['batch_size']))
+    assert st['iters'] == int(g['stop_iter'][-1])
+    done = L.update_cup_stage2(data, g['perms'][4:8:2], float(lam), batch_size=int(g['batch_size']))
+    assert done == int(g['second_stop_iter'][-1])
+    np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
