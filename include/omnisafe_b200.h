@@ -296,6 +296,17 @@ int osb_umma_timing(int M, int N, int reps, long long* out, void* stream);
 int osb_umma_selftest(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn,
                       float* out, void* stream);
 
+/* Split-bf16 ("bf16x3", kind::f16) building blocks of the parity-grade tensor-core mode (csrc/x3.cuh):
+ * one single-CTA GEMM D = A * B^T with A [M][K], B [N][K] (row-major fp32 in global memory), each operand
+ * staged as three bf16 tiles (SW128 or SW32) consumed K-major or MN-major; out[128][N] = raw TMEM dump
+ * (tests/test_x3_gpu.py).  The timing / epilogue probes report clock64 cycles. */
+int osb_x3_selftest(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn, int a_sw,
+                    int b_sw, int b_ones, float* out, void* stream);
+int osb_x3_selftest_dbg(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn, int a_sw,
+                        int b_sw, int b_ones, int a_lbo, int a_sbo, int b_lbo, int b_sbo, float* out, void* stream);
+int osb_x3_timing(int M, int N, int reps, int style, long long* out, void* stream);
+int osb_x3_epilogue_probe(int cols, int reps, int mode, long long* out, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
