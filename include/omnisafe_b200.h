@@ -167,6 +167,16 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
                           float entropy_coef, float focops_lam, float focops_eta,
                           const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                           float* stats_part, const int* stop_flag, void* stream);
+/* Split-bf16 ("bf16x3") parity-grade tensor-core variant (csrc/update_x3.cu): every GEMM = six kind::f16
+ * MMAs over the three bf16 pieces of its fp32 operands, fp32 accumulate; O <= 64, loss kinds 0 / 1 / 3. */
+int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, const float* act,
+                          const float* logp, const float* adv_r, const float* adv_c,
+                          const float* tv_r, const float* tv_c, const float* mu_old,
+                          const float* moments, const int* perm, long long total, unsigned perm_seed,
+                          long long mb_start, int mb_count, int loss_kind, float clip,
+                          float entropy_coef, float focops_lam, float focops_eta,
+                          const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                          float* stats_part, const int* stop_flag, void* stream);
 /* Full-batch actor pass (KL early stop policy_gradient.py:L383-397; TRPO/CPO line-search
  * evaluations trpo.py:L102-138, cpo.py:L114-171).  mu_store != NULL: write mu(theta) per row.
  * Otherwise out[8] <- {sum_s sum_a KL(old||new), sum ratio*adv, sum ratio*adv_c, sum ratio, count,

@@ -25,6 +25,14 @@ int osb_minibatch_grad_tc(const float* theta, int O, int A, const float* obs, co
                           float entropy_coef, float focops_lam, float focops_eta,
                           const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                           float* stats_part, const int* stop_flag, void* stream);
+int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, const float* act,
+                          const float* logp, const float* adv_r, const float* adv_c,
+                          const float* tv_r, const float* tv_c, const float* mu_old,
+                          const float* moments, const int* perm, long long total, unsigned perm_seed,
+                          long long mb_start, int mb_count, int loss_kind, float clip,
+                          float entropy_coef, float focops_lam, float focops_eta,
+                          const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
+                          float* stats_part, const int* stop_flag, void* stream);
 int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, const float* act,
                    const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
                    const float* logstd_old, const float* moments, const float* lagrange,
@@ -169,6 +177,9 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     OSB_CUDA(cudaMemsetAsync(train_stats, 0, 3 * 8 * sizeof(float), s));
     int rc;
     // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
+    // precision 2 = split-bf16 ("bf16x3") tcgen05 tiles: fp32-level results on the tensor cores (O <= 64,
+    // loss kinds 0/1/3; the full-batch evaluations stay on the exact fp32 tiles)
+    const bool use_x3 = precision == 2 && O <= 64 && (loss_kind == 0 || loss_kind == 1 || loss_kind == 3);
     const bool use_tc = precision == 1 && O <= 512;
     const bool train_actor = (net_mask & 1) != 0;
     if (train_actor) {
@@ -184,12 +195,12 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
         for (long long start = 0; start < total; start += batch_size) {
             const int count = (int)((total - start < batch_size) ? (total - start) : batch_size);
-            rc = (use_tc ? osb_minibatch_grad_tc : osb_minibatch_grad)(
+            rc = (use_x3 ? osb_minibatch_grad_x3 : use_tc ? osb_minibatch_grad_tc : osb_minibatch_grad)(
                 theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old, moments, perm_it, total,
                 perm_seed + 0x9E3779B9u * (unsigned)it, start, count, loss_kind, clip, entropy_coef,
                 focops_lam, focops_eta, lagrange, logstd_old, net_mask, gpart, stats_part, stop_flag, stream);
             if (rc) return rc;
-            const int nb = use_tc ? osb_tc_grid_blocks(count, net_mask) : osb_update_grid_blocks(count);
+            const int nb = (use_tc || use_x3) ? osb_tc_grid_blocks(count, net_mask) : osb_update_grid_blocks(count);
             if (world_size > 1 && peer_buf && peer_flag && p2p_error) {
                 // one cooperative kernel: reduce + clip + one-shot NVLink peer-memory all-reduce + Adam
                 static unsigned p2p_step = 0;

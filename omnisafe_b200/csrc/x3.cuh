@@ -79,6 +79,40 @@ __device__ __forceinline__ void gemm_x3(uint32_t tmem_d, uint64_t a0, uint32_t a
     }
 }
 
+
+// Warp-uniform variant for a dedicated MMA-issue warp: all 32 lanes run the descriptor arithmetic (uniform
+// datapath), only the elected lane executes the MMAs.  (Issued from divergent code, every tcgen05.mma is
+// wrapped by the compiler in a uniformisation loop that costs more than the MMA itself.)
+__device__ __forceinline__ void gemm_x3_warp(bool leader, uint32_t tmem_d, uint64_t a0, uint32_t asplit, uint32_t akstep,
+                                             uint64_t b0, uint32_t bsplit, uint32_t bkstep, uint32_t idesc, int nk,
+                                             bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+    for (int ks = 0; ks < nk; ++ks) {
+        const uint64_t a = desc_add(a0, (uint32_t)ks * akstep), b = desc_add(b0, (uint32_t)ks * bkstep);
+        const uint64_t a1 = desc_add(a, asplit), a2 = desc_add(a, 2 * asplit);
+        const uint64_t b1 = desc_add(b, bsplit), b2 = desc_add(b, 2 * bsplit);
+        if (bsplit == 0) {
+            if (leader) {
+                mma_bf16(tmem_d, a2, b, idesc, acc);
+                mma_bf16(tmem_d, a1, b, idesc, 1u);
+                mma_bf16(tmem_d, a, b, idesc, 1u);
+            }
+        } else {
+            if (leader) {
+                mma_bf16(tmem_d, a2, b, idesc, acc);
+                mma_bf16(tmem_d, a, b2, idesc, 1u);
+                mma_bf16(tmem_d, a1, b1, idesc, 1u);
+                mma_bf16(tmem_d, a1, b, idesc, 1u);
+                mma_bf16(tmem_d, a, b1, idesc, 1u);
+                mma_bf16(tmem_d, a, b, idesc, 1u);
+            }
+        }
+        __syncwarp();
+        acc = 1u;
+    }
+}
+
 // ---- fp32 <-> three bf16 ----------------------------------------------------------------------------
 // pack two floats into one bf16x2 word (lo half = a, hi half = b), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
