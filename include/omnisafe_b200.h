@@ -192,6 +192,26 @@ int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, 
                       const float* logstd_old, const float* moments, const float* lagrange,
                       long long total, int stride, float* mu_store, double* workspace, double* out,
                       void* stream);
+/* One update iteration of PolicyGradient._update (policy_gradient.py:L369-381) as ONE persistent cooperative
+ * kernel on bf16x3 tiles (csrc/update_x3.cu): every minibatch = fused forward + loss + backward, fixed-order
+ * partial reduction, per-network clip_grad_norm_, clipped-gradient exchange over NVLink peer memory when
+ * world > 1 (clip -> average -> step: policy_gradient.py:L437-443, distributed.py:L193-198) and torch-Adam,
+ * parameters re-staged in shared memory between minibatches.  perm = slab rows of this iteration or NULL. */
+int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step, int O, int A,
+                           const float* obs, const float* act, const float* logp, const float* adv_r,
+                           const float* adv_c, const float* tv_r, const float* tv_c, const float* moments,
+                           const int* perm, long long total, unsigned perm_seed, int batch_size, int loss_kind,
+                           float clip, float entropy_coef, const float* lagrange, int net_mask,
+                           float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
+                           float lr_critic_c, float* gpart, float* stats_part, float* train_stats,
+                           const int* stop_flag, void* peer_buf, void* peer_flag, int world, int rank,
+                           int* p2p_error, void* stream);
+/* Split-bf16 (parity-grade tensor-core) variant, O <= 64 (csrc/eval_x3.cu). */
+int osb_actor_eval_x3(const float* theta_actor, int O, int A, const float* obs, const float* act,
+                      const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
+                      const float* logstd_old, const float* moments, const float* lagrange,
+                      long long total, int stride, float* mu_store, double* workspace, double* out,
+                      void* stream);
 /* Fisher-vector product partials (NaturalPG._fvp, base/natural_pg.py:L74-119, analytic
  * Gauss-Newton form; damping is added by osb_reduce_partials).  gpart: blocks * P_actor floats. */
 int osb_fvp_grid_blocks(long long total, int stride);

@@ -42,13 +42,18 @@ class UpdateEngine:
         self.cg_scalars = torch.zeros(4, **f32)
         self.scalar = torch.zeros(4, **f32)
         self._perm_seed = 0x1234567
-        self.precision = 0   # 0 = exact fp32 FMA tiles (parity), 1 = TF32 tcgen05 tiles (fast)
+        self.precision = 0   # 0 = exact fp32 FMA tiles, 1 = TF32 tcgen05 tiles (5e-3), 2 = split-bf16 tcgen05 tiles (fp32-level)
 
     # ---- helpers ----------------------------------------------------------------------------
     def _tc(self) -> bool:
         return self.precision == 1 and self.O <= 512      # obs dims > 64: layer 1 K-chunked (rollout stays on fp32 tiles)
 
+    def _x3(self) -> bool:
+        return self.precision == 2 and self.O <= 64        # split-bf16 tiles: fp32-level results on the tensor cores
+
     def _eval_fn(self):
+        if self._x3():
+            return lib().osb_actor_eval_x3
         return lib().osb_actor_eval_tc if self._tc() else lib().osb_actor_eval
 
     def _batch_ptrs(self):

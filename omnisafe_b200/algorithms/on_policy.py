@@ -55,8 +55,8 @@ class PolicyGradient(BaseAlgo):
             num_envs=self._cfgs.train_cfgs.vector_env_nums, device=self._device, keep_discounted_ret=False)
         self._engine = UpdateEngine(self._actor_critic, self._buf)
         prec = str(getattr(self._cfgs.train_cfgs, 'matmul_precision', 'fp32'))
-        assert prec in ('fp32', 'tf32'), "train_cfgs.matmul_precision must be 'fp32' or 'tf32'"
-        self._engine.precision = 1 if prec == 'tf32' else 0
+        assert prec in ('fp32', 'tf32', 'bf16x3'), "train_cfgs.matmul_precision must be 'fp32', 'tf32' or 'bf16x3'"
+        self._engine.precision = {'fp32': 0, 'tf32': 1, 'bf16x3': 2}[prec]
         self._stats8 = torch.zeros(8, dtype=torch.float64, device=self._device)
 
     def _init_log(self) -> None:

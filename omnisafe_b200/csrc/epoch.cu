@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "mlp.cuh"
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 extern "C" {
@@ -39,6 +40,20 @@ int osb_actor_eval(const float* theta_actor, int O, int A, const float* obs, con
                    long long total, int stride, float* mu_store, double* workspace, double* out,
                    void* stream);
 int osb_actor_eval_tc(const float* theta_actor, int O, int A, const float* obs, const float* act,
+                      const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
+                      const float* logstd_old, const float* moments, const float* lagrange,
+                      long long total, int stride, float* mu_store, double* workspace, double* out,
+                      void* stream);
+int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam_v, int* adam_step, int O, int A,
+                           const float* obs, const float* act, const float* logp, const float* adv_r,
+                           const float* adv_c, const float* tv_r, const float* tv_c, const float* moments,
+                           const int* perm, long long total, unsigned perm_seed, int batch_size, int loss_kind,
+                           float clip, float entropy_coef, const float* lagrange, int net_mask,
+                           float critic_norm_coef, float max_grad_norm, float lr_actor, float lr_critic_r,
+                           float lr_critic_c, float* gpart, float* stats_part, float* train_stats,
+                           const int* stop_flag, void* peer_buf, void* peer_flag, int world, int rank,
+                           int* p2p_error, void* stream);
+int osb_actor_eval_x3(const float* theta_actor, int O, int A, const float* obs, const float* act,
                       const float* logp, const float* adv_r, const float* adv_c, const float* mu_old,
                       const float* logstd_old, const float* moments, const float* lagrange,
                       long long total, int stride, float* mu_store, double* workspace, double* out,
@@ -178,22 +193,35 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     int rc;
     // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
     // precision 2 = split-bf16 ("bf16x3") tcgen05 tiles: fp32-level results on the tensor cores (O <= 64,
-    // loss kinds 0/1/3; the full-batch evaluations stay on the exact fp32 tiles)
+    // loss kinds 0/1/3)
     const bool use_x3 = precision == 2 && O <= 64 && (loss_kind == 0 || loss_kind == 1 || loss_kind == 3);
+    const bool use_x3e = precision == 2 && O <= 64;
     const bool use_tc = precision == 1 && O <= 512;
     const bool train_actor = (net_mask & 1) != 0;
     if (train_actor) {
         OSB_CHECK_ARG(mu_old && logstd_old && eval_ws && eval_out, "actor update needs mu_old/logstd_old/eval buffers");
-        rc = (use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, nullptr, nullptr, nullptr, nullptr,
+        rc = (use_x3e ? osb_actor_eval_x3 : use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, nullptr, nullptr, nullptr, nullptr,
                                                           nullptr, nullptr, nullptr, nullptr, total, 1, mu_old,
                                                           nullptr, nullptr, stream);
         if (rc) return rc;
         OSB_CUDA(cudaMemcpyAsync(logstd_old, theta, A * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     const float gscale = 1.0f / (float)world_size;
+    // bf16x3 + (one rank | NVLink peer exchange): the whole iteration is one persistent kernel with the optimiser inside
+    const bool p2p_ok = world_size > 1 && peer_buf && peer_flag && p2p_error;
+    const bool fuse_x3 = use_x3 && (world_size == 1 || p2p_ok) && !getenv("OSB_X3_NO_FUSE");
     for (int it = 0; it < update_iters; ++it) {
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
-        for (long long start = 0; start < total; start += batch_size) {
+        if (fuse_x3) {
+            rc = osb_ppo_update_iter_x3(theta, grad, adam_m, adam_v, adam_step, O, A, obs, act, logp, adv_r, adv_c, tv_r,
+                                        tv_c, moments, perm_it, total, perm_seed + 0x9E3779B9u * (unsigned)it, batch_size,
+                                        loss_kind, clip, entropy_coef, lagrange, net_mask, critic_norm_coef, max_grad_norm,
+                                        lr_actor, lr_critic, lr_critic, gpart, stats_part, train_stats, stop_flag,
+                                        world_size > 1 ? peer_buf : nullptr, world_size > 1 ? peer_flag : nullptr, world_size,
+                                        rank, p2p_error, stream);
+            if (rc) return rc;
+        }
+        for (long long start = 0; start < total && !fuse_x3; start += batch_size) {
             const int count = (int)((total - start < batch_size) ? (total - start) : batch_size);
             rc = (use_x3 ? osb_minibatch_grad_x3 : use_tc ? osb_minibatch_grad_tc : osb_minibatch_grad)(
                 theta, O, A, obs, act, logp, adv_r, adv_c, tv_r, tv_c, mu_old, moments, perm_it, total,
@@ -230,7 +258,7 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
             if (rc) return rc;
         }
         if (train_actor) {
-            rc = (use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, act, logp, adv_r, adv_c, mu_old,
+            rc = (use_x3e ? osb_actor_eval_x3 : use_tc ? osb_actor_eval_tc : osb_actor_eval)(theta, O, A, obs, act, logp, adv_r, adv_c, mu_old,
                                                               logstd_old, moments, lagrange, total, 1, nullptr,
                                                               eval_ws, eval_out, stream);
             if (rc) return rc;

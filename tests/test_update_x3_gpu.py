@@ -134,3 +134,63 @@ def test_x3_epoch_matches_fp32_epoch(cuda):
     print('|x3 - fp32| / |update| =', np.linalg.norm(diff) / np.linalg.norm(delta))
     bad = ~np.isclose(out[1], out[0], rtol=2e-4, atol=2e-6)
     assert bad.mean() < 2e-3 and np.linalg.norm(diff) < 5e-3 * np.linalg.norm(delta)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('N,T,batch,iters', [(64, 32, 512, 3), (50, 26, 512, 2), (13, 100, 640, 2), (256, 80, 16384, 1)])
+def test_x3_fused_iteration_equals_stepwise(cuda, N, T, batch, iters):
+    """The persistent kernel (optimiser inside, software grid barriers, short last minibatch, CTAs without a tile)
+    and the launch-per-minibatch path (bf16x3 gradient kernel + optim_fused) produce the same parameters."""
+    rng = np.random.default_rng(N + T)
+    O, A = 60, 8
+    theta = oac.init_theta(O, A, seed=2)
+    data = _rand_data(rng, N, T, O, A, theta)
+    B = N * T
+    perms = torch.as_tensor(np.stack([_rows(rng.permutation(B), N, T) for _ in range(iters)])).to(cuda)
+    out, stats = [], []
+    for fused in (False, True):
+        if fused:
+            os.environ.pop('OSB_X3_NO_FUSE', None)
+        else:
+            os.environ['OSB_X3_NO_FUSE'] = '1'
+        try:
+            agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+            lag = torch.tensor([0.2, 0, 0, 0], dtype=torch.float32, device=cuda)
+            eng.ppo_epoch(loss_kind=0, lagrange=lag, net_mask=7, batch_size=batch, update_iters=iters, clip=0.2,
+                          critic_norm_coef=0.001, max_grad_norm=0.5, lr_actor=3e-4, lr_critic=3e-4,
+                          target_kl=10.0, kl_early_stop=False, perm=perms, precision=2)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop('OSB_X3_NO_FUSE', None)
+        out.append((agent.theta.cpu().numpy(), agent.adam_m.cpu().numpy(), agent.adam_v.cpu().numpy(), agent.adam_step.cpu().numpy()))
+        stats.append(eng.train_stats.cpu().numpy().reshape(3, 8).copy())
+    assert (out[0][3] == out[1][3]).all() and out[1][3][0] == iters * -(-B // batch)
+    for a, b, name in zip(out[0][:3], out[1][:3], ('theta', 'm', 'v')):
+        # identical arithmetic, different summation order of the partial gradients -> a few ulp on the gradient
+        bad = ~np.isclose(a, b, rtol=1e-4, atol=1e-7)
+        assert bad.mean() < 2e-3, (name, bad.sum(), np.abs(a - b).max())
+    np.testing.assert_allclose(stats[1][:, :4], stats[0][:, :4], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.timeout(300)
+def test_x3_actor_eval_matches_fp32_eval(cuda):
+    rng = np.random.default_rng(9)
+    N, T, O, A = 96, 50, 60, 8
+    theta = oac.init_theta(O, A, seed=4)
+    data = _rand_data(rng, N, T, O, A, theta)
+    agent, buf, eng = _setup(cuda, data, N, T, O, A, theta)
+    eng.precision = 0
+    eng.snapshot_old_policy()
+    mu0 = eng.mu_old.clone()
+    th2 = agent.theta.clone()
+    th2[: eng.Pa] += 0.02 * torch.randn(eng.Pa, device=cuda)
+    lag = torch.tensor([0.3], dtype=torch.float32, device=cuda)
+    ref = eng.evaluate(th2, lag)
+    eng.precision = 2
+    eng.snapshot_old_policy()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(eng.mu_old.cpu().numpy(), mu0.cpu().numpy(), rtol=0, atol=2e-6)     # tf32 tiles: 3e-3
+    eng.mu_old.copy_(mu0)
+    got = eng.evaluate(th2, lag)
+    for k in ('kl', 'loss', 'loss_c', 'loss_r', 'ratio'):
+        np.testing.assert_allclose(got[k], ref[k], rtol=2e-5, atol=2e-6, err_msg=k)              # tf32 tiles: 2e-2
