@@ -60,6 +60,7 @@ struct X3Args {
     int world, rank;
     unsigned int step_base;      // exchange step id of this launch's first minibatch (identical on all ranks)
     int* error_flag;
+    long long* dbg;              // optional clock64 stamps of CTA (0, 0): [0] = count, then (id, clock) pairs (tools/x3_stage_times.py)
 };
 
 constexpr int XT = 128;                      // samples per tile
@@ -74,7 +75,7 @@ constexpr uint32_t OFF_X = 0, OFF_H1 = OFF_X + ACT_X3, OFF_H2 = OFF_H1 + ACT_X3,
                    OFF_MISC = OFF_ONES + 512;
 // misc region (floats unless noted)
 constexpr int MF_B1 = 0, MF_B2 = 64, MF_B3 = 128, MF_LS = 144 /* logstd[16] sigma[16] dlogstd acc[16] */, MF_STAT = 192,
-              MF_RED = 200 /* [4*8 + 4*16 + 4*16] */, MF_B3ACC = 360, MF_PART = 376 /* [2][256] */, MF_SCAL = 888 /* [8] */, MF_END = 896;
+              MF_RED = 200 /* [4*8 + 4*16 + 4*16] */, MF_B3ACC = 360, MF_PART = 376 /* [2][256] */, MF_SCAL = 888 /* [16] */, MF_END = 904;
 constexpr uint32_t OFF_ROWS = OFF_MISC + MF_END * 4;                 // long long [2][128]
 constexpr uint32_t OFF_BARS = OFF_ROWS + 2 * XT * 8;                 // uint64 [NBAR]
 enum Bar { RDY_X0 = 0, RDY_X1, RDY_H1_0, RDY_H1_1, RDY_H2_0, RDY_H2_1, RDY_D, RDY_DZ2_0, RDY_DZ2_1, RDY_DZ1,
@@ -104,41 +105,59 @@ __device__ __forceinline__ unsigned long long x3_feistel(unsigned long long k, u
     return x;
 }
 
-// fp32 parameters of one network -> bf16x3 weight tiles + fp32 biases in shared memory (all NEPI epilogue threads)
+// fp32 parameters of one network -> bf16x3 weight tiles + fp32 biases in shared memory (all NEPI epilogue threads).
+// All global loads are issued before the first store (one L2 round trip instead of one per loop iteration).
+// O < 64 ("ones column"): column 63 of the X tile holds 1.0 and column 63 of the W1 tile holds b1, so the layer-1
+// bias rides in the GEMM and db1 falls out of the dW1 accumulator (column 63) -- no bias add, no db1 MMAs.
 __device__ __forceinline__ void stage_weights_x3(uint32_t sbase, float* misc, const float* __restrict__ theta,
                                                  const NetLayout& L, int net, int O, int A, int tid) {
-    for (int i = tid; i < 64 * 32; i += NEPI) {          // W1 / W2: [64 n][64 k], two columns per thread
+    const bool ones_col = O < 64;
+    float a1[4], b1[4], a2[4], b2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                          // W1 / W2: [64 n][64 k], two columns per thread
+        const int i = tid + j * NEPI;
         const int n = i >> 5, k = (i & 31) << 1;
-        const float a1 = (k < O) ? __ldcg(theta + L.off_w1 + n * O + k) : 0.f;
-        const float b1 = (k + 1 < O) ? __ldcg(theta + L.off_w1 + n * O + k + 1) : 0.f;
-        const float a2 = __ldcg(theta + L.off_w2 + n * 64 + k), b2 = __ldcg(theta + L.off_w2 + n * 64 + k + 1);
+        a1[j] = (k < O) ? __ldcg(theta + L.off_w1 + n * O + k) : 0.f;
+        b1[j] = (k + 1 < O) ? __ldcg(theta + L.off_w1 + n * O + k + 1) : ((ones_col && k == 62) ? __ldcg(theta + L.off_b1 + n) : 0.f);
+        a2[j] = __ldcg(theta + L.off_w2 + n * 64 + k); b2[j] = __ldcg(theta + L.off_w2 + n * 64 + k + 1);
+    }
+    const int o3 = tid >> 5, k3 = (tid & 31) << 1;         // W3: [16 o][64 k], rows >= out zero
+    const float a3 = (o3 < L.out) ? __ldcg(theta + L.off_w3 + o3 * 64 + k3) : 0.f;
+    const float b3 = (o3 < L.out) ? __ldcg(theta + L.off_w3 + o3 * 64 + k3 + 1) : 0.f;
+    float bb1 = 0.f, bb2 = 0.f, bb3 = 0.f, ls = 0.f;
+    if (tid < 64) { bb1 = ones_col ? 0.f : __ldcg(theta + L.off_b1 + tid); bb2 = __ldcg(theta + L.off_b2 + tid); }
+    if (tid < 16) {
+        bb3 = (tid < L.out) ? __ldcg(theta + L.off_b3 + tid) : 0.f;
+        ls = (net == 0 && tid < A) ? __ldcg(theta + L.off_logstd + tid) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * NEPI;
+        const int n = i >> 5, k = (i & 31) << 1;
         uint32_t w0, w1, w2;
         const uint32_t off = off128(n, k);
-        split2(a1, b1, w0, w1, w2);
+        split2(a1[j], b1[j], w0, w1, w2);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W1 + off), "r"(w0) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W1 + W_SUB + off), "r"(w1) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W1 + 2 * W_SUB + off), "r"(w2) : "memory");
-        split2(a2, b2, w0, w1, w2);
+        split2(a2[j], b2[j], w0, w1, w2);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W2 + off), "r"(w0) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W2 + W_SUB + off), "r"(w1) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W2 + 2 * W_SUB + off), "r"(w2) : "memory");
     }
-    {                                                      // W3: [16 o][64 k], rows >= out zero
-        const int o = tid >> 5, k = (tid & 31) << 1;
-        const float a = (o < L.out) ? __ldcg(theta + L.off_w3 + o * 64 + k) : 0.f;
-        const float b = (o < L.out) ? __ldcg(theta + L.off_w3 + o * 64 + k + 1) : 0.f;
+    {
         uint32_t w0, w1, w2;
-        split2(a, b, w0, w1, w2);
-        const uint32_t off = off128(o, k);
+        split2(a3, b3, w0, w1, w2);
+        const uint32_t off = off128(o3, k3);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W3 + off), "r"(w0) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W3 + W3_SUB + off), "r"(w1) : "memory");
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + OFF_W3 + 2 * W3_SUB + off), "r"(w2) : "memory");
     }
-    if (tid < 64) { misc[MF_B1 + tid] = __ldcg(theta + L.off_b1 + tid); misc[MF_B2 + tid] = __ldcg(theta + L.off_b2 + tid); }
+    if (tid < 64) { misc[MF_B1 + tid] = bb1; misc[MF_B2 + tid] = bb2; }
     if (tid < 16) {
-        misc[MF_B3 + tid] = (tid < L.out) ? __ldcg(theta + L.off_b3 + tid) : 0.f;
-        const float ls = (net == 0 && tid < A) ? __ldcg(theta + L.off_logstd + tid) : 0.f;
-        misc[MF_LS + tid] = ls; misc[MF_LS + 16 + tid] = expf(ls);
+        misc[MF_B3 + tid] = bb3;
+        const float sd = expf(ls);
+        misc[MF_LS + tid] = ls; misc[MF_LS + 16 + tid] = sd; misc[MF_LS + 32 + tid] = 1.f / (sd * sd);   // log sigma, sigma, 1 / sigma^2
     }
 }
 
@@ -156,6 +175,8 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+constexpr int PSTR = 9472;          // FUSED: row stride of the private partial-gradient layout [3][G][PSTR] (16 B aligned rows)
+
 // FUSED = false: one minibatch, per-CTA partial gradients out (the contract of minibatch_grad_tc_kernel).
 // FUSED = true : persistent cooperative kernel -- the CTA loops over all minibatches of one update iteration
 //   (policy_gradient.py:L369-381); after each minibatch the CTAs of a network meet at a software grid barrier,
@@ -163,7 +184,8 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int
 //   clipped slice with the peer ranks over NVLink (clip -> average -> step, policy_gradient.py:L437-443,
 //   distributed.py:L193-198), apply torch-Adam and re-stage the new weights: no relaunch, no separate
 //   optimiser kernel.
-template <bool FUSED>
+// AP = padded action width of the loss epilogue (8 or 16).
+template <bool FUSED, int AP>
 __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     if (p.stop_flag && *p.stop_flag) return;
     const int net = (gridDim.y == 1) ? (__ffs(p.net_mask) - 1) : (int)blockIdx.y;
@@ -185,17 +207,18 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     const NetLayout L = net_layout(net, O, A);
     const int noff = net_offset(net, O, A);
     const float* theta = (FUSED ? p.theta_rw : p.theta) + noff;
-    float* gout = p.gpart + (size_t)blockIdx.x * p.P + noff;
+    // partial gradients of this CTA: FUSED -> private aligned layout, else the [CTA][P] layout optim_fused reads
+    float* gout = FUSED ? p.gpart + ((size_t)((gridDim.y == 1 ? 0 : net) * G + (int)blockIdx.x)) * PSTR
+                        : p.gpart + (size_t)blockIdx.x * p.P + noff;
     const bool is_mma_warp = warp == NEPI / 32;
     const int batch = FUSED ? p.batch_size : p.b.mb_count;
     const int n_mb = (p.b.mb_count + batch - 1) / batch;
+    const bool ones_col = O < 64;          // bias of layer 1 / db1 ride in the GEMMs (see stage_weights_x3)
 
     // ---- one-time setup -------------------------------------------------------------------------------
     if (!is_mma_warp) {
         stage_weights_x3(sbase, misc, theta, L, net, O, A, tid);
         if (tid < 128) reinterpret_cast<uint32_t*>(gbase + OFF_ONES)[tid] = 0x3F803F80u;       // bf16 1.0 x 256
-        if (tid < 16) { misc[MF_LS + 32 + tid] = 0.f; misc[MF_B3ACC + tid] = 0.f; }
-        if (tid < 8) misc[MF_STAT + tid] = 0.f;
     } else {
         if (lane == 0) {
             for (int i = 0; i < NBAR; ++i) {
@@ -229,7 +252,8 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
                 const uint32_t par = (uint32_t)(it & 1);
-                const bool acc_dw = tile != (int)blockIdx.x;        // the first tile of a minibatch overwrites the accumulators
+                const bool first = tile == (int)blockIdx.x;         // the first tile of a minibatch overwrites the accumulators
+                const bool last = tile + G >= ntiles;
                 // Z1 = X W1^T  (k-steps 0-1 after the first column half of X, 2-3 after the second)
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
@@ -239,6 +263,9 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 }
                 if (leader) mma_commit_a(bar(DONE_C1));
                 __syncwarp();
+                // db2 of the PREVIOUS tile (dZ2 still sits in the H2 buffer until this tile's E2): runs under E1,
+                // completes before Z2 (in-order pipe), so DONE_C2 covers it
+                if (!first) gemm_x3_warp(leader, tmem + T_DB2, dH2, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, tile != (int)blockIdx.x + G);
                 // Z2 = H1 W2^T
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
@@ -263,10 +290,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 gemm_x3_warp(leader, tmem + T_ZA, dD, D_SUB, 32u, dW3, W3_SUB, 2048u, id_bwd, 1, false);
                 if (leader) mma_commit_a(bar(DONE_C4A));
                 __syncwarp();
-                gemm_x3_warp(leader, tmem + T_DW3, dH2, ACT_SUB, 2048u, dD, D_SUB, 512u, id_dw16, 8, acc_dw);
+                gemm_x3_warp(leader, tmem + T_DW3, dH2, ACT_SUB, 2048u, dD, D_SUB, 512u, id_dw16, 8, !first);
                 if (leader) mma_commit_a(bar(DONE_C4B));
                 __syncwarp();
-                // dZ1' = dZ2 W2 ; dW2 += dZ2^T H1 ; db2 += dZ2^T 1
+                // dZ1' = dZ2 W2 ; dW2 += dZ2^T H1
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
                     mbar_wait_a(bar(RDY_DZ2_0 + ph), par);
@@ -275,15 +302,15 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 }
                 if (leader) mma_commit_a(bar(DONE_C5A));
                 __syncwarp();
-                gemm_x3_warp(leader, tmem + T_DW2, dH2, ACT_SUB, 2048u, dH1, ACT_SUB, 2048u, id_dw, 8, acc_dw);
-                gemm_x3_warp(leader, tmem + T_DB2, dH2, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, acc_dw);
+                gemm_x3_warp(leader, tmem + T_DW2, dH2, ACT_SUB, 2048u, dH1, ACT_SUB, 2048u, id_dw, 8, !first);
                 if (leader) mma_commit_a(bar(DONE_C5B));
                 __syncwarp();
-                // dW1 += dZ1^T X ; db1 += dZ1^T 1
+                // dW1 += dZ1^T X (column 63 = db1 with the ones column) ; last tile of the minibatch: its own db2
                 mbar_wait_a(bar(RDY_DZ1), par);
                 tc_fence_after();
-                gemm_x3_warp(leader, tmem + T_DW1, dH1, ACT_SUB, 2048u, dX, ACT_SUB, 2048u, id_dw, 8, acc_dw);
-                gemm_x3_warp(leader, tmem + T_DB1, dH1, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, acc_dw);
+                gemm_x3_warp(leader, tmem + T_DW1, dH1, ACT_SUB, 2048u, dX, ACT_SUB, 2048u, id_dw, 8, !first);
+                if (!ones_col) gemm_x3_warp(leader, tmem + T_DB1, dH1, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, !first);
+                if (last) gemm_x3_warp(leader, tmem + T_DB2, dH2, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, !first);
                 if (leader) mma_commit_a(bar(DONE_C6));
                 __syncwarp();
             }
@@ -296,9 +323,9 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
         const float lam = (p.lagrange != nullptr) ? __ldg(p.lagrange) : 0.f;
         float m_r = 0.f, s_r = 1.f, m_c = 0.f;
         if (p.b.moments) { m_r = __ldg(p.b.moments + 0); s_r = __ldg(p.b.moments + 1); m_c = __ldg(p.b.moments + 2); }
+        const float inv_sr = 1.f / s_r, inv_1lam = 1.f / (1.f + lam);
         float* sB1 = misc + MF_B1; float* sB2 = misc + MF_B2; float* sB3 = misc + MF_B3; float* sLs = misc + MF_LS;
-        float* sStat = misc + MF_STAT; float* sRed = misc + MF_RED; float* sB3acc = misc + MF_B3ACC;
-        float* sPart = misc + MF_PART; float* sScal = misc + MF_SCAL;
+        float* sRed = misc + MF_RED; float* sPart = misc + MF_PART; float* sScal = misc + MF_SCAL;
 
         // X gather: thread -> row xm = tid / 4, columns 32 ph + 8 (tid % 4) .. + 7 in column half ph
         const int xm = tid >> 2, xc = (tid & 3) << 3;
@@ -322,12 +349,21 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     for (int i = 0; i < 8; ++i) xpre[8 * ph + i] = (row >= 0 && c0 + i < O) ? __ldg(p.b.obs + row * O + c0 + i) : 0.f;
                 }
             }
+            if (ones_col && xc == 24) xpre[15] = 1.0f;     // column 63: the ones column (every row: padding rows have dZ1 = 0)
         };
         auto announce = [&](int b) {        // this warp's stores of one column half are visible to the tensor core
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(b));
+        };
+        const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 256);
+        int dbg_n = 0;
+        auto stamp = [&](int id) {
+            if (dbg_on && dbg_n < 400) {
+                long long* d = p.dbg + (tid == 0 ? 0 : 1024);
+                d[1 + 2 * dbg_n] = id; d[2 + 2 * dbg_n] = clock64(); ++dbg_n; d[0] = dbg_n;
+            }
         };
         unsigned int nbar = 0;              // software grid barriers passed so far (FUSED)
         auto net_barrier = [&]() {          // all CTAs of this network: writes before it are visible after it (via L2)
@@ -342,33 +378,49 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
             ++nbar;
             epi_bar_sync();
         };
+        auto mb_geom = [&](int mb, long long& start, int& count) {
+            start = p.b.mb_start + (long long)mb * batch;
+            count = min(batch, p.b.mb_count - mb * batch);
+        };
+        auto tile_rows = [&](int mb, int tile, long long* dst) {
+            if (tid < XT) {
+                long long start; int count;
+                mb_geom(mb, start, count);
+                const int local = tile * XT + tid;
+                long long row = -1;
+                if (local < count) {
+                    const long long k = start + local;
+                    if (p.b.identity_stride > 0) row = k * p.b.identity_stride;
+                    else row = p.b.perm ? (long long)p.b.perm[k] : (long long)x3_feistel((unsigned long long)k, (unsigned long long)p.b.total, p.b.perm_seed);
+                }
+                dst[tid] = row;
+            }
+        };
         int step_t0 = 0;
         if (FUSED) step_t0 = p.adam_step[net];
+        // per-thread partial sums of the loss warps over the tiles of one minibatch (reduced once per minibatch)
+        float acc_st[4] = {0.f, 0.f, 0.f, 0.f}, acc_dls[AP], acc_db[AP];
+#pragma unroll
+        for (int a = 0; a < AP; ++a) { acc_dls[a] = 0.f; acc_db[a] = 0.f; }
 
         int rpar = 0, it = 0;
+        if ((int)blockIdx.x < (min(batch, p.b.mb_count) + XT - 1) / XT) {     // rows + X of the first tile
+            tile_rows(0, blockIdx.x, sRowBuf);
+            epi_bar_sync();
+            prefetch_x(sRowBuf);
+        }
 #pragma unroll 1
         for (int mb = 0; mb < n_mb; ++mb) {
-            const long long mb_start = p.b.mb_start + (long long)mb * batch;
-            const int count = min(batch, p.b.mb_count - mb * batch);
+            long long mb_start; int count;
+            mb_geom(mb, mb_start, count);
             const int ntiles = (count + XT - 1) / XT;
             const float inv_b = 1.0f / (float)count;
-            auto tile_rows = [&](int tile, long long* dst) {
-                if (tid < XT) {
-                    const int local = tile * XT + tid;
-                    long long row = -1;
-                    if (local < count) {
-                        const long long k = mb_start + local;
-                        if (p.b.identity_stride > 0) row = k * p.b.identity_stride;
-                        else row = p.b.perm ? (long long)p.b.perm[k] : (long long)x3_feistel((unsigned long long)k, (unsigned long long)p.b.total, p.b.perm_seed);
-                    }
-                    dst[tid] = row;
-                }
-            };
             const bool have_tiles = (int)blockIdx.x < ntiles;
-            if (have_tiles) {
-                tile_rows(blockIdx.x, sRowBuf + rpar * XT);
-                epi_bar_sync();
-                prefetch_x(sRowBuf + rpar * XT);
+            if (FUSED && tid == NEPI - 1) {        // Adam bias corrections of this minibatch's step, off the critical path
+                const int step_t = step_t0 + mb + 1;
+                const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
+                sScal[8] = (float)((double)p.lr[net] / bc1);
+                sScal[9] = (float)sqrt(bc2);
             }
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < ntiles; tile += G, ++it) {
@@ -377,8 +429,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 long long* sRowNext = sRowBuf + (rpar ^ 1) * XT;
                 const bool has_next = tile + G < ntiles;
                 // ---- E0: X tile (prefetched registers -> bf16x3) ------------------------------------------------
-                if (has_next) tile_rows(tile + G, sRowNext);
+                stamp(0);
+                if (has_next) tile_rows(mb, tile + G, sRowNext);
                 if (it > 0) mbar_wait_a(bar(DONE_C6), par ^ 1u);          // previous tile's dW1 / db1 read X and dZ1
+                stamp(1);
                 tc_fence_after();
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
@@ -389,9 +443,11 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     announce(RDY_X0 + ph);
                 }
                 epi_bar_sync();                                            // next tile's row list is complete
+                stamp(2);
                 // ---- E1: H1 = tanh(Z1 + b1) -------------------------------------------------------------------
                 mbar_wait_a(bar(DONE_C1), par);
                 tc_fence_after();
+                stamp(3);
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
                     const int c0 = 32 * ph + 8 * h;
@@ -403,8 +459,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     announce(RDY_H1_0 + ph);
                 }
                 // ---- E2: H2 = tanh(Z2 + b2) -------------------------------------------------------------------
+                stamp(4);
                 mbar_wait_a(bar(DONE_C2), par);
                 tc_fence_after();
+                stamp(5);
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
                     const int c0 = 32 * ph + 8 * h;
@@ -415,16 +473,17 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     store8_x3(sbase + OFF_H2, ACT_SUB, s_row, c0, v);
                     announce(RDY_H2_0 + ph);
                 }
+                stamp(6);
                 // ---- E3: OUT -> loss -> dOUT (warps with h == 0: one thread per sample) -------------------------
                 if (h == 0) {
-                    float pf_act[16], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
+                    float pf_act[AP], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
                     const long long prow = sRow[s_row];
 #pragma unroll
-                    for (int a = 0; a < 16; ++a) pf_act[a] = 0.f;
+                    for (int a = 0; a < AP; ++a) pf_act[a] = 0.f;
                     if (prow >= 0) {
                         if (net == 0) {
 #pragma unroll
-                            for (int a = 0; a < 16; ++a)
+                            for (int a = 0; a < AP; ++a)
                                 if (a < A) pf_act[a] = __ldg(p.b.act + prow * A + a);
                             pf_logp = __ldg(p.b.logp + prow);
                             pf_advr = __ldg(p.b.adv_r + prow);
@@ -435,32 +494,42 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     }
                     mbar_wait_a(bar(DONE_C3), par);
                     tc_fence_after();
-                    float st[4] = {0.f, 0.f, 0.f, 0.f};   // loss, ratio, kl (unused here), count
-                    float dls[16], o16[16], d16[16];
+                    stamp(7);
+                    float o[AP], d16[16];
 #pragma unroll
-                    for (int a = 0; a < 16; ++a) { dls[a] = 0.f; d16[a] = 0.f; }
-                    tmem_ld16(tmem + lane_base + T_OUT, o16);
+                    for (int a = 0; a < 16; ++a) d16[a] = 0.f;
+                    if (AP == 8) {
+                        float t8[8];
+                        tmem_ld8(tmem + lane_base + T_OUT, t8);
+#pragma unroll
+                        for (int a = 0; a < AP; ++a) o[a] = t8[a];
+                    } else {
+                        float t16[16];
+                        tmem_ld16(tmem + lane_base + T_OUT, t16);
+#pragma unroll
+                        for (int a = 0; a < AP; ++a) o[a] = t16[a];
+                    }
                     if (prow >= 0) {
                         if (net != 0) {
-                            const float d = o16[0] + sB3[0] - pf_tv;
-                            st[0] = d * d; st[3] = 1.f;
+                            const float d = o[0] + sB3[0] - pf_tv;
+                            acc_st[0] += d * d; acc_st[3] += 1.f;
                             d16[0] = 2.f * d * inv_b;
+                            acc_db[0] += d16[0];
                         } else {
-                            float logp_new = 0.f, diff[16];
+                            float logp_new = 0.f, diff[AP];
 #pragma unroll
-                            for (int a = 0; a < 16; ++a) {
+                            for (int a = 0; a < AP; ++a) {
                                 diff[a] = 0.f;
                                 if (a < A) {
-                                    const float sd = sLs[16 + a];
-                                    const float d = pf_act[a] - (o16[a] + sB3[a]);
+                                    const float d = pf_act[a] - (o[a] + sB3[a]);
                                     diff[a] = d;
-                                    logp_new += -(d * d) / (2.f * sd * sd) - sLs[a] - 0.9189385332046727f;
+                                    logp_new += -(d * d) * (0.5f * sLs[32 + a]) - sLs[a] - 0.9189385332046727f;
                                 }
                             }
                             const float ratio = expf(logp_new - pf_logp);
-                            const float adv_r = (pf_advr - m_r) / s_r;
+                            const float adv_r = (pf_advr - m_r) * inv_sr;
                             const float adv_c = pf_advc - m_c;
-                            const float adv = (adv_r - lam * adv_c) / (1.f + lam);
+                            const float adv = (adv_r - lam * adv_c) * inv_1lam;
                             float dlogp, loss;
                             if (p.kind == X3_PPO_CLIP) {
                                 const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
@@ -472,51 +541,28 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                             } else {
                                 loss = ratio * adv_c; dlogp = adv_c * ratio * inv_b;
                             }
-                            st[0] = loss; st[1] = ratio; st[3] = 1.f;
+                            acc_st[0] += loss; acc_st[1] += ratio; acc_st[3] += 1.f;
 #pragma unroll
-                            for (int a = 0; a < 16; ++a)
+                            for (int a = 0; a < AP; ++a)
                                 if (a < A) {
-                                    const float sd = sLs[16 + a];
-                                    const float iv = 1.f / (sd * sd);
-                                    d16[a] = dlogp * diff[a] * iv;
-                                    dls[a] = dlogp * (diff[a] * diff[a] * iv - 1.f);
+                                    const float iv = sLs[32 + a];
+                                    const float dm = dlogp * diff[a] * iv;
+                                    d16[a] = dm;
+                                    acc_db[a] += dm;
+                                    acc_dls[a] += dlogp * (diff[a] * diff[a] * iv - 1.f);
                                 }
                         }
                     }
                     store16_x3_sw32(sbase + OFF_D, D_SUB, s_row, d16);
                     announce(RDY_D);
-                    // deterministic reductions over the 128 sample threads
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) st[i] = warp_sum(st[i]);
-                    if (net == 0) {
-#pragma unroll
-                        for (int a = 0; a < 16; ++a) dls[a] = warp_sum(dls[a]);
-                    }
-                    float db[16];   // db3[o] = sum_s dOUT[s][o]
-#pragma unroll
-                    for (int a = 0; a < 16; ++a) db[a] = (a < L.out) ? warp_sum(d16[a]) : 0.f;
-                    if (lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sRed[q * 8 + i] = st[i];
-#pragma unroll
-                        for (int a = 0; a < 16; ++a) { sRed[32 + q * 16 + a] = dls[a]; sRed[96 + q * 16 + a] = db[a]; }
-                    }
-                    loss_bar_sync();
-                    if (tid < 4) sStat[tid] += sRed[tid] + sRed[8 + tid] + sRed[16 + tid] + sRed[24 + tid];
-                    if (net == 0 && tid >= 32 && tid < 48) {
-                        const int a = tid - 32;
-                        sLs[32 + a] += sRed[32 + a] + sRed[48 + a] + sRed[64 + a] + sRed[80 + a];
-                    }
-                    if (tid >= 64 && tid < 64 + L.out) {
-                        const int a = tid - 64;
-                        sB3acc[a] += sRed[96 + a] + sRed[112 + a] + sRed[128 + a] + sRed[144 + a];
-                    }
-                    loss_bar_sync();                          // sRed is rewritten by the next tile
+                    stamp(8);
                 }
+                stamp(9);
                 // ---- E4: dZ2 = (dOUT W3) (1 - H2^2), stored over H2 once dW3 has read it --------------------------
                 if (has_next) prefetch_x(sRowNext);                        // next tile's rows fly during the backward half
                 mbar_wait_a(bar(DONE_C4A), par);
                 tc_fence_after();
+                stamp(10);
                 float dz[16];
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
@@ -527,7 +573,9 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dz[8 * ph + i] = v[i] * (1.f - hh[i] * hh[i]);
                 }
+                stamp(11);
                 mbar_wait_a(bar(DONE_C4B), par);
+                stamp(12);
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
                     float v[8];
@@ -537,8 +585,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     announce(RDY_DZ2_0 + ph);
                 }
                 // ---- E5: dZ1 = (dZ2 W2) (1 - H1^2), stored over H1 once dW2 has read it --------------------------
+                stamp(13);
                 mbar_wait_a(bar(DONE_C5A), par);
                 tc_fence_after();
+                stamp(14);
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
                     const int c0 = 32 * ph + 8 * h;
@@ -548,7 +598,9 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dz[8 * ph + i] = v[i] * (1.f - hh[i] * hh[i]);
                 }
+                stamp(15);
                 mbar_wait_a(bar(DONE_C5B), par);
+                stamp(16);
 #pragma unroll
                 for (int ph = 0; ph < 2; ++ph) {
                     float v[8];
@@ -557,25 +609,69 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     store8_x3(sbase + OFF_H1, ACT_SUB, s_row, 32 * ph + 8 * h, v);
                 }
                 announce(RDY_DZ1);
+                stamp(17);
                 rpar ^= 1;
+            }
+            stamp(20);
+            // ---- rows + X of the first tile of the NEXT minibatch: the gather flies under the optimiser phases ------
+            if (FUSED && mb + 1 < n_mb) {
+                long long s2; int c2;
+                mb_geom(mb + 1, s2, c2);
+                if ((int)blockIdx.x < (c2 + XT - 1) / XT) {
+                    tile_rows(mb + 1, blockIdx.x, sRowBuf + rpar * XT);
+                    epi_bar_sync();
+                    prefetch_x(sRowBuf + rpar * XT);
+                }
             }
             // ---- this CTA's partial gradient of the minibatch: TMEM accumulators -> global ------------------------
             if (have_tiles) {
+                // loss-warp sums: lanes -> warp (butterfly) -> the four loss warps (fixed order)
+                if (h == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc_st[i] = warp_sum(acc_st[i]);
+#pragma unroll
+                    for (int a = 0; a < AP; ++a) { acc_dls[a] = warp_sum(acc_dls[a]); acc_db[a] = warp_sum(acc_db[a]); }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sRed[q * 8 + i] = acc_st[i];
+#pragma unroll
+                        for (int a = 0; a < AP; ++a) { sRed[32 + q * 16 + a] = acc_dls[a]; sRed[96 + q * 16 + a] = acc_db[a]; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc_st[i] = 0.f;
+#pragma unroll
+                    for (int a = 0; a < AP; ++a) { acc_dls[a] = 0.f; acc_db[a] = 0.f; }
+                }
                 mbar_wait_a(bar(DONE_C6), (uint32_t)((it - 1) & 1));
                 tc_fence_after();
+                stamp(21);
                 const int t_row = 16 * q + lane;       // row (lane < 16) of the M = 64 accumulators
                 const int c16 = 16 * h;
                 float v[16];
                 tmem_ld16(tmem + lane_base + T_DW2 + (uint32_t)c16, v);
                 if (lane < 16) {
+                    float* dst = gout + L.off_w2 + t_row * 64 + c16;
+                    if (FUSED && (L.off_w2 & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) __stcg(gout + L.off_w2 + t_row * 64 + c16 + i, v[i]);       // rows of P floats: 4 B aligned only
+                        for (int i = 0; i < 16; i += 4) __stcg(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) __stcg(dst + i, v[i]);
+                    }
                 }
                 tmem_ld16(tmem + lane_base + T_DW1 + (uint32_t)c16, v);
                 if (lane < 16) {
+                    float* dst = gout + L.off_w1 + t_row * O + c16;
+                    if (FUSED && ((L.off_w1 | O) & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c16 + i < O) __stcg(gout + L.off_w1 + t_row * O + c16 + i, v[i]);
+                        for (int i = 0; i < 16; i += 4)
+                            if (c16 + i < O) __stcg(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c16 + i < O) __stcg(dst + i, v[i]);
+                    }
+                    if (ones_col && h == 3) __stcg(gout + L.off_b1 + t_row, v[15]);        // column 63 of dW1 = db1
                 }
                 if (h == 0) {      // dW3^T [k][o]
                     tmem_ld16(tmem + lane_base + T_DW3, v);
@@ -584,45 +680,58 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                         for (int o = 0; o < 16; ++o)
                             if (o < L.out) __stcg(gout + L.off_w3 + o * 64 + t_row, v[o]);
                 } else if (h == 1) {
-                    tmem_ld16(tmem + lane_base + T_DB1, v);
-                    if (lane < 16) __stcg(gout + L.off_b1 + t_row, v[0]);
+                    if (!ones_col) {
+                        tmem_ld16(tmem + lane_base + T_DB1, v);
+                        if (lane < 16) __stcg(gout + L.off_b1 + t_row, v[0]);
+                    }
                 } else if (h == 2) {
                     tmem_ld16(tmem + lane_base + T_DB2, v);
                     if (lane < 16) __stcg(gout + L.off_b2 + t_row, v[0]);
                 }
                 tc_fence_before();
-                if (tid < L.out) __stcg(gout + L.off_b3 + tid, sB3acc[tid]);
-                if (net == 0 && tid < A) {
-                    float g = sLs[32 + tid];
+                epi_bar_sync();                        // sRed of the four loss warps
+                if (tid < L.out) __stcg(gout + L.off_b3 + tid, (sRed[96 + tid] + sRed[112 + tid]) + (sRed[128 + tid] + sRed[144 + tid]));
+                if (net == 0 && tid >= 32 && tid < 32 + A) {
+                    const int a = tid - 32;
+                    float g = (sRed[32 + a] + sRed[48 + a]) + (sRed[64 + a] + sRed[80 + a]);
                     if (blockIdx.x == 0 && p.kind == X3_PPO_CLIP) g -= p.entropy_coef / (float)A;
-                    __stcg(gout + L.off_logstd + tid, g);
+                    __stcg(gout + L.off_logstd + a, g);
                 }
-                if (tid < 8) __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + tid, (tid < 4) ? sStat[tid] : 0.f);
+                if (tid >= 64 && tid < 72) {
+                    const int i = tid - 64;
+                    __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + i, (i < 4) ? (sRed[i] + sRed[8 + i]) + (sRed[16 + i] + sRed[24 + i]) : 0.f);
+                }
             } else {
                 for (int i = tid; i < L.size; i += NEPI) __stcg(gout + i, 0.f);      // no tile of this (short) minibatch
                 if (tid < 8) __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + tid, 0.f);
             }
+            stamp(22);
             if (!FUSED) break;
 
             // ================= in-kernel optimiser step =========================================================
             net_barrier();                                             // every partial gradient of this network is in L2
+            stamp(23);
             const int S = (L.size + G - 1) / G;                        // parameters owned by this CTA: [p0, p0 + S)
             const int p0 = (int)blockIdx.x * S;
             const int Gh = (G + 1) >> 1;
+            const float* gnet = p.gpart + (size_t)((gridDim.y == 1 ? 0 : net) * G) * PSTR;
             float ssq = 0.f, st2 = 0.f;
             for (int base = 0; base < S; base += 256) {
                 const int pi = base + (tid & 255), part = tid >> 8;
                 const bool valid = pi < S && p0 + pi < L.size;
                 float sacc = 0.f;
                 if (valid) {
-                    const float* src = p.gpart + noff + p0 + pi;
+                    const float* src = gnet + p0 + pi;
                     const int b1 = min(G, (part + 1) * Gh);
-                    for (int b = part * Gh; b < b1; b += 16) {
-                        float t[16];
+                    for (int b = part * Gh; b < b1; b += 32) {       // 32 partial rows in flight per thread
+                        float t[32];
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) t[u] = (b + u < b1) ? __ldcg(src + (size_t)(b + u) * p.P) : 0.f;
-                        sacc += (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) +
-                                (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
+                        for (int u = 0; u < 32; ++u) t[u] = (b + u < b1) ? __ldcg(src + (size_t)(b + u) * PSTR) : 0.f;
+#pragma unroll
+                        for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+                            for (int u = 0; u < w; ++u) t[u] += t[u + w];
+                        sacc += t[0];
                     }
                 }
                 sPart[tid] = sacc;
@@ -630,8 +739,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 if (part == 0 && valid) {
                     const int qg = noff + p0 + pi;
                     float g = sPart[tid] + sPart[256 + tid];
-                    const float th = __ldcg(p.theta_rw + qg);
-                    if (net != 0 && p.critic_norm_coef > 0.f) { g += 2.f * p.critic_norm_coef * th; st2 += th * th; }
+                    if (net != 0 && p.critic_norm_coef > 0.f) {
+                        const float th = __ldcg(p.theta_rw + qg);
+                        g += 2.f * p.critic_norm_coef * th; st2 += th * th;
+                    }
                     __stcg(p.grad + qg, g);
                     ssq += g * g;
                 }
@@ -646,17 +757,15 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 __stcg(p.sumsq_part + (net * 2 + 0) * G + blockIdx.x, a);
                 __stcg(p.sumsq_part + (net * 2 + 1) * G + blockIdx.x, b);
             }
+            stamp(24);
             net_barrier();                                             // every slice norm of this network is in L2
-            const int step_t = step_t0 + mb + 1;
+            stamp(25);
             if (warp == 0) {
                 float tot = 0.f, t2 = 0.f;
                 for (int b = lane; b < G; b += 32) { tot += __ldcg(p.sumsq_part + (net * 2 + 0) * G + b); t2 += __ldcg(p.sumsq_part + (net * 2 + 1) * G + b); }
                 tot = warp_sum(tot); t2 = warp_sum(t2);
                 if (lane == 0) {
                     sScal[0] = (p.max_grad_norm > 0.f) ? fminf(p.max_grad_norm / (sqrtf(tot) + 1e-6f), 1.0f) : 1.0f;
-                    const double bc1 = 1.0 - pow(0.9, (double)step_t), bc2 = 1.0 - pow(0.999, (double)step_t);
-                    sScal[1] = (float)((double)p.lr[net] / bc1);
-                    sScal[2] = (float)sqrt(bc2);
                     sScal[3] = t2;
                 }
             } else if (warp == 1 && blockIdx.x == 0) {               // loss statistics of this minibatch (logger means)
@@ -677,7 +786,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 ts[2] += sScal[6] * inv;
                 ts[3] += 1.f;
             }
-            const float clipc = sScal[0], step_size = sScal[1], bc2_sqrt = sScal[2];
+            const float clipc = sScal[0], step_size = sScal[8], bc2_sqrt = sScal[9];
             const unsigned int xstep = p.step_base + (unsigned int)mb;
             const int xpar = (int)(xstep & 1u);
             const int cta_g = (gridDim.y == 1 ? 0 : net) * G + (int)blockIdx.x;
@@ -736,11 +845,12 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     }
                 }
             }
+            stamp(26);
             net_barrier();                                             // the new parameters of this network are in L2
+            stamp(27);
             stage_weights_x3(sbase, misc, theta, L, net, O, A, tid);   // visible to the tensor core with the next X announce
-            if (tid < 16) { misc[MF_LS + 32 + tid] = 0.f; misc[MF_B3ACC + tid] = 0.f; }
-            if (tid < 8) misc[MF_STAT + tid] = 0.f;
             epi_bar_sync();
+            stamp(28);
         }
         if (FUSED && blockIdx.x == 0 && tid == 0) p.adam_step[net] = step_t0 + n_mb;     // every CTA read it before the first barrier
     }
@@ -757,12 +867,18 @@ extern "C" {
 
 int osb_tc_grid_blocks(long long rows, int net_mask);
 
+static long long* g_x3_dbg = nullptr;
+// development aid: clock64 stamps of CTA (0, 0) of the next launches go to buf (2048 long long), NULL turns it off
+int osb_x3_debug_buffer(long long* buf) { g_x3_dbg = buf; return OSB_OK; }
+
 static int x3_set_attr() {
     static bool attr = false;
     if (!attr) {
         const size_t smem = 1024 + X3_SMEM;
-        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OSB_CUDA(cudaFuncSetAttribute(minibatch_grad_x3_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     return OSB_OK;
@@ -789,12 +905,13 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
     p.kind = loss_kind; p.clip = clip; p.entropy_coef = entropy_coef; p.lagrange = lagrange;
     p.theta = theta; p.gpart = gpart; p.stats_part = stats_part; p.stop_flag = stop_flag;
     p.O = O; p.A = A; p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size; p.net_mask = net_mask;
-    p.batch_size = mb_count; p.world = 1;
+    p.batch_size = mb_count; p.world = 1; p.dbg = g_x3_dbg;
     const int nb = osb_tc_grid_blocks(mb_count, net_mask);
     int rc = x3_set_attr();
     if (rc) return rc;
     const bool single = (net_mask & (net_mask - 1)) == 0;
-    minibatch_grad_x3_kernel<false><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
+    if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
+    else minibatch_grad_x3_kernel<false, 16><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
@@ -836,7 +953,7 @@ int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam
     p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
     p.sumsq_part = d_ws + 64; p.train_stats = train_stats; p.bar_ctr = reinterpret_cast<unsigned int*>(d_ws);
     p.peer_buf = (float* const*)peer_buf; p.peer_flag = (unsigned int* const*)peer_flag;
-    p.world = world; p.rank = rank; p.error_flag = p2p_error;
+    p.world = world; p.rank = rank; p.error_flag = p2p_error; p.dbg = g_x3_dbg;
     const int n_mb = (int)((total + batch_size - 1) / batch_size);
     p.step_base = step_base + 1u;
     step_base += (unsigned int)n_mb;
@@ -846,8 +963,8 @@ int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam
     if (rc) return rc;
     const bool single = (net_mask & (net_mask - 1)) == 0;
     void* args[] = {&p};
-    OSB_CUDA(cudaLaunchCooperativeKernel((void*)minibatch_grad_x3_kernel<true>, dim3(nb, single ? 1 : 3), dim3(NTX3), args,
-                                         1024 + X3_SMEM, s));
+    OSB_CUDA(cudaLaunchCooperativeKernel(A <= 8 ? (void*)minibatch_grad_x3_kernel<true, 8> : (void*)minibatch_grad_x3_kernel<true, 16>,
+                                         dim3(nb, single ? 1 : 3), dim3(NTX3), args, 1024 + X3_SMEM, s));
     return OSB_OK;
 }
 
