@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "mlp.cuh"
 #include "umma.cuh"
+#include "x3.cuh"
 
 namespace osb {
 
@@ -230,7 +231,7 @@ struct StepArgs {
     uint32_t global_step; // epoch * T + t, Philox counter
     int t, T, N;
     int is_tail;          // t == T: critics only (epoch-end bootstrap)
-    int precision;        // 0 = fp32 FMA tiles of 32 envs, 1 = tcgen05 TF32 tiles of 128 envs (O <= 64)
+    int precision;        // 0 = fp32 FMA tiles of 32 envs, 1 = tcgen05 TF32 tiles of 128 envs, 2 = split-bf16 tcgen05 tiles (O <= 64)
 };
 
 // normalise (or copy) a tile of raw observations into sX (chunk kc), zero padded.
@@ -498,14 +499,21 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
 constexpr int RTC = 128;
 constexpr int SNW = KC + 1;   // row stride of the next-state staging tiles
 
+// X3 = false: kind::tf32 tiles (5e-3);  X3 = true: split-bf16 tiles (csrc/x3.cuh), fp32-level values / log-probs:
+// one bf16x3 activation buffer (X, H1, H2 overwrite each other in place), accurate tanh, warp-uniform MMA issue.
+constexpr uint32_t RX_SUB = RTC * 128, RX_WSUB = 64 * 128, RX_W3SUB = 16 * 128;
+constexpr uint32_t RTC_FOFF_TF32 = 2 * RTC * 256 + 2 * 16384 + 4096, RTC_FOFF_X3 = 3 * RX_SUB + 6 * RX_WSUB + 3 * RX_W3SUB;
+
+template <bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p) {
     using namespace umma;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
-    const uint32_t B0 = smem_u32(smem_raw) + pad;       // X -> H2
-    const uint32_t B2 = B0 + RTC * 256;                 // H1
-    const uint32_t sW1 = B2 + RTC * 256, sW2 = sW1 + 16384, sW3 = sW2 + 16384;
-    float* fbase = reinterpret_cast<float*>(smem_raw + pad + 2 * RTC * 256 + 2 * 16384 + 4096);
+    const uint32_t B0 = smem_u32(smem_raw) + pad;       // X -> H2   (X3: X -> H1 -> H2, bf16x3)
+    const uint32_t B2 = B0 + RTC * 256;                 // H1        (X3: unused)
+    const uint32_t sW1 = X3 ? B0 + 3 * RX_SUB : B2 + RTC * 256;
+    const uint32_t sW2 = sW1 + (X3 ? 3 * RX_WSUB : 16384u), sW3 = sW2 + (X3 ? 3 * RX_WSUB : 16384u);
+    float* fbase = reinterpret_cast<float*>(smem_raw + pad + (X3 ? RTC_FOFF_X3 : RTC_FOFF_TF32));
     float* sB1 = fbase;            // [64]
     float* sB2 = sB1 + 64;         // [64]
     float* sB3 = sB2 + 64;         // [16]
@@ -538,6 +546,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     int ep_step = 0; uint32_t epi = 0, gstep = 0;
     if (my_ok) { ep_step = p.st.ep_step[my_env]; epi = p.st.episode[my_env]; gstep = p.st.gstep[my_env]; }
 
+    if constexpr (X3) {   // weights -> bf16x3 tiles (all loads first)
+        float a1[8], b1[8], a2[8], b2[8], a3[2], b3[2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + j * NTHREADS, n = i >> 5, k = (i & 31) << 1;
+            a1[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
+            b1[j] = (k + 1 < O) ? __ldg(theta + L.off_w1 + n * O + k + 1) : 0.f;
+            a2[j] = __ldg(theta + L.off_w2 + n * 64 + k); b2[j] = __ldg(theta + L.off_w2 + n * 64 + k + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + j * NTHREADS, o = i >> 5, k = (i & 31) << 1;
+            a3[j] = (o < L.out) ? __ldg(theta + L.off_w3 + o * 64 + k) : 0.f;
+            b3[j] = (o < L.out) ? __ldg(theta + L.off_w3 + o * 64 + k + 1) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = tid + j * NTHREADS, n = i >> 5, k = (i & 31) << 1;
+            uint32_t w0, w1, w2;
+            const uint32_t off = x3::off128(n, k);
+            x3::split2(a1[j], b1[j], w0, w1, w2);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW1 + off), "r"(w0) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW1 + RX_WSUB + off), "r"(w1) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW1 + 2 * RX_WSUB + off), "r"(w2) : "memory");
+            x3::split2(a2[j], b2[j], w0, w1, w2);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW2 + off), "r"(w0) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW2 + RX_WSUB + off), "r"(w1) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW2 + 2 * RX_WSUB + off), "r"(w2) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + j * NTHREADS, o = i >> 5, k = (i & 31) << 1;
+            uint32_t w0, w1, w2;
+            const uint32_t off = x3::off128(o, k);
+            x3::split2(a3[j], b3[j], w0, w1, w2);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW3 + off), "r"(w0) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW3 + RX_W3SUB + off), "r"(w1) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sW3 + 2 * RX_W3SUB + off), "r"(w2) : "memory");
+        }
+    } else
     {   // weights (batched loads)
         float w1v[16], w2v[16], w3v[4];
         const int k = tid & 63;
@@ -616,9 +664,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     }
                     if (obs_out) *reinterpret_cast<float4*>(obs_out + (size_t)env * O + k4) = v;
                 }
+                if constexpr (X3) {
+                    uint32_t w0[2], w1[2], w2[2];
+                    x3::split2(v.x, v.y, w0[0], w1[0], w2[0]);
+                    x3::split2(v.z, v.w, w0[1], w1[1], w2[1]);
+                    const uint32_t o = B0 + x3::off128(e, k4);
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o), "r"(w0[0]), "r"(w0[1]) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o + RX_SUB), "r"(w1[0]), "r"(w1[1]) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o + 2 * RX_SUB), "r"(w2[0]), "r"(w2[1]) : "memory");
+                } else {
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile_addr(B0, e, k4, RTC)),
                              "f"(tf32r(v.x)), "f"(tf32r(v.y)), "f"(tf32r(v.z)), "f"(tf32r(v.w))
                              : "memory");
+                }
             }
         } else {
             const int k = tid & 63;
@@ -633,11 +691,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     if (norm_on) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v, -mk), sk), -5.f), 5.f);
                     if (obs_out) obs_out[(size_t)env * O + k] = v;
                 }
-                sts(tile_addr(B0, e, k, RTC), tf32r(v));
+                if constexpr (X3) x3::store1_x3(B0, RX_SUB, x3::off128(e, k), v);
+                else sts(tile_addr(B0, e, k, RTC), tf32r(v));
             }
         }
         fence_async_smem();
         __syncthreads();
+        if constexpr (X3) {
+            // three layers on bf16x3 tiles, one activation buffer: every epilogue starts after its layer's MMAs completed
+            const bool leader = (warp == 0) && x3::elect_one_sync();
+            const uint64_t dAct = x3::desc128(B0), dW1 = x3::desc128(sW1), dW2 = x3::desc128(sW2), dW3 = x3::desc128(sW3);
+            if (warp == 0) {
+                tc_fence_after();
+                x3::gemm_x3_warp(leader, tmem + C_Z, dAct, RX_SUB, 32u, dW1, RX_WSUB, 32u, x3::idesc_bf16(128, 64, 0, 0), 4, false);
+                if (leader) mma_commit(&bar);
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int c0 = 32 * h + 8 * c8;
+                float v[8];
+                x3::tmem_ld8(tmem + lane_base + C_Z + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = x3::tanh_acc(v[i] + sB1[c0 + i]);
+                x3::store8_x3(B0, RX_SUB, 32 * q + lane, c0, v);
+            }
+            fence_async_smem(); tc_fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                tc_fence_after();
+                x3::gemm_x3_warp(leader, tmem + C_Z, dAct, RX_SUB, 32u, dW2, RX_WSUB, 32u, x3::idesc_bf16(128, 64, 0, 0), 4, false);
+                if (leader) mma_commit(&bar);
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int c0 = 32 * h + 8 * c8;
+                float v[8];
+                x3::tmem_ld8(tmem + lane_base + C_Z + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = x3::tanh_acc(v[i] + sB2[c0 + i]);
+                x3::store8_x3(B0, RX_SUB, 32 * q + lane, c0, v);
+            }
+            fence_async_smem(); tc_fence_before();
+            __syncthreads();
+            if (warp == 0) {
+                tc_fence_after();
+                x3::gemm_x3_warp(leader, tmem + C_OUT, dAct, RX_SUB, 32u, dW3, RX_W3SUB, 32u, x3::idesc_bf16(128, 16, 0, 0), 4, false);
+                if (leader) mma_commit(&bar);
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+        } else {
         if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B0, RTC, sW1, 64, 128, 64, 64, false); mma_commit(&bar); }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
@@ -665,6 +775,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_OUT, B0, RTC, sW3, 16, 128, 16, 64, false); mma_commit(&bar); }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
+        }
         if (h == 0) {
             float o16[16];
             tmem_ld16(tmem + lane_base + C_OUT, o16);
@@ -846,8 +957,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-static size_t rollout_tc_smem_bytes() {
-    return 1024 + 2 * RTC * 256 + 2 * 16384 + 4096 +
+static size_t rollout_tc_smem_bytes(bool x3) {
+    return 1024 + (x3 ? RTC_FOFF_X3 : RTC_FOFF_TF32) +
            (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * RTC * SNW) * sizeof(float) + 4 * 4 * 64 * sizeof(long long) +
            RTC * sizeof(int) + 64;
 }
@@ -981,15 +1092,18 @@ int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned t
 }
 
 static int launch_step(StepArgs& p, cudaStream_t stream) {
-    if (p.precision == 1 && p.es.O <= 64) {
-        const size_t smem_tc = rollout_tc_smem_bytes();
+    if ((p.precision == 1 || p.precision == 2) && p.es.O <= 64) {
+        const bool x3 = p.precision == 2;
+        const size_t smem_tc = rollout_tc_smem_bytes(x3);
         static bool attr_tc = false;
         if (!attr_tc) {
-            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(false)));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(true)));
             attr_tc = true;
         }
         dim3 grid_tc((p.N + RTC - 1) / RTC, p.is_tail ? 2 : 3);
-        rollout_step_tc_kernel<<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
+        if (x3) rollout_step_tc_kernel<true><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
+        else rollout_step_tc_kernel<false><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
         OSB_LAUNCH_CHECK();
         return OSB_OK;
     }

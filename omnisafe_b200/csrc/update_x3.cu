@@ -367,13 +367,11 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
         };
         unsigned int nbar = 0;              // software grid barriers passed so far (FUSED)
         auto net_barrier = [&]() {          // all CTAs of this network: writes before it are visible after it (via L2)
-            epi_bar_sync();
+            epi_bar_sync();                  // the CTA's writes happen-before thread 0's release (cumulative at gpu scope)
             if (tid == 0) {
-                __threadfence();
-                atomicAdd(p.bar_ctr + net, 1u);
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.bar_ctr + net), "r"(1u) : "memory");
                 const unsigned int target = (unsigned int)G * (nbar + 1u);
                 while (ld_acquire_gpu_u32(p.bar_ctr + net) < target) {}
-                __threadfence();
             }
             ++nbar;
             epi_bar_sync();
@@ -757,6 +755,10 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 __stcg(p.sumsq_part + (net * 2 + 0) * G + blockIdx.x, a);
                 __stcg(p.sumsq_part + (net * 2 + 1) * G + blockIdx.x, b);
             }
+            // Adam state of this thread's parameter: loaded before the barrier, consumed after it
+            const bool own = tid < S && p0 + tid < L.size;
+            float pre_th = 0.f, pre_m = 0.f, pre_v = 0.f;
+            if (own) { pre_th = __ldcg(p.theta_rw + noff + p0 + tid); pre_m = __ldcg(p.adam_m + noff + p0 + tid); pre_v = __ldcg(p.adam_v + noff + p0 + tid); }
             stamp(24);
             net_barrier();                                             // every slice norm of this network is in L2
             stamp(25);
@@ -835,8 +837,9 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                             g = __ldcg(p.grad + qg) * clipc;
                         }
                         __stcg(p.grad + qg, g);
-                        const float th = __ldcg(p.theta_rw + qg);
-                        float m = __ldcg(p.adam_m + qg), v = __ldcg(p.adam_v + qg);
+                        const bool pre = base == 0;                     // first chunk: state prefetched before the barrier
+                        const float th = pre ? pre_th : __ldcg(p.theta_rw + qg);
+                        float m = pre ? pre_m : __ldcg(p.adam_m + qg), v = pre ? pre_v : __ldcg(p.adam_v + qg);
                         m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));                       // exp_avg.lerp_(grad, 1 - beta1)
                         v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
                         const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);

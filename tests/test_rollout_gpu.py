@@ -27,13 +27,14 @@ def _model_cfgs():
 
 
 def _gpu_rollout(dev, N, T, O, A, seed, theta, eps, tmax, term_prob, obs_normalize=True, window=100, epochs=1,
-                 rc_normalize=False):
+                 rc_normalize=False, precision=0):
     from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
     from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
     from omnisafe_b200.models import ConstraintActorCritic
 
     cfgs = _cfgs(obs_normalize, window, rc_normalize, obs_dim=O, act_dim=A, max_episode_steps=tmax, term_prob=term_prob)
     ad = OnPolicyAdapter('SyntheticBox-v0', N, seed, cfgs, device=dev)
+    ad.precision = precision
     agent = ConstraintActorCritic(O, A, _model_cfgs(), epochs=1, device=dev)
     agent.load_flat(theta)
     buf = VectorOnPolicyBuffer(O, A, T, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=N, device=dev)
@@ -62,12 +63,13 @@ def _compare(sl_gpu, sl_ref, tol=2e-5):
     np.testing.assert_allclose(sl_gpu['boot_c'][need], sl_ref['boot_c'][need], **t)
 
 
-def test_rollout_golden_reference(cuda, golden_dir):
+@pytest.mark.parametrize('precision', [0, 2])      # exact fp32 FMA tiles / split-bf16 tensor-core tiles: same bar
+def test_rollout_golden_reference(cuda, golden_dir, precision):
     """Same seed / params / noise as the unmodified reference run -> same slabs."""
     g = np.load(os.path.join(golden_dir, 'rollout_ppolag.npz'))
     N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
     ad, buf, outs = _gpu_rollout(cuda, N, T, O, A, int(g['seed']), g['theta'], g['eps'][None],
-                                 int(g['tmax']), float(g['term_prob']), window=10)
+                                 int(g['tmax']), float(g['term_prob']), window=10, precision=precision)
     sl = outs[0]
     t = dict(rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(sl['obs'], g['slab_obs'], **t)
@@ -237,3 +239,20 @@ def test_rollout_tensor_core_mode(cuda, N, T, tmax, term_prob):
     assert (sl['cost'] != ref['cost']).mean() < 5e-3
     need = ((ref['flags'] != 0) | (np.arange(T)[:, None] == T - 1)) & ((ref['flags'] & 1) == 0)
     np.testing.assert_allclose(sl['boot_r'][need], ref['boot_r'][need], **tol)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('N,T,tmax,term_prob,precision', [(256, 24, 8, 0.0, 2), (200, 20, 6, 0.05, 2), (100, 33, 7, 0.02, 2),
+                                                          (4096, 128, 64, 0.0, 0), (4096, 128, 64, 0.0, 2)])
+def test_rollout_vs_oracle_bf16x3_and_headline(cuda, N, T, tmax, term_prob, precision):
+    """matmul_precision = bf16x3 (tcgen05 kind::f16, three bf16 pieces per fp32 operand) is held to the bar of the exact
+    fp32 tiles -- 2e-5 on every slab vs the oracle (the tf32 tiles get 5e-3) -- and both modes are checked at the headline
+    size of the bench workload (4096 envs x 128 steps, obs 60 / act 8)."""
+    O, A = 60, 8
+    rng = np.random.default_rng(N + T)
+    theta = oac.init_theta(O, A, seed=3)
+    eps = rng.standard_normal((1, T, N, A)).astype(np.float32)
+    ad, buf, outs = _gpu_rollout(cuda, N, T, O, A, 9, theta, eps, tmax, term_prob, window=16, precision=precision)
+    ref = orollout.rollout_epoch(OEnv(N, O, A, max_episode_steps=tmax, seed=9, term_prob=term_prob),
+                                 ONormalizer((O,)), theta, T, eps[0])
+    _compare(outs[0], ref, tol=2e-5)
