@@ -1,20 +1,24 @@
-"""bench.py -- env-steps/sec over full PPO-Lag epochs (rollout + dual GAE + update).
+"""bench.py -- env-steps/sec over full on-policy SafeRL epochs (rollout + dual GAE + update).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--algo PPOLag|CPO|TRPOLag|FOCOPS] [--obs-dim D] [--precision bf16x3|tf32|fp32]
 
-A "step" is one epoch of the BASELINE.json workload `configs[1]`: PPOLag on the synthetic Box env
-(obs 60 / act 8), 4096 HBM-resident envs per GPU, T = 128 steps per env (524 288 samples per GPU),
-update_iters 8, batch_size 16384 -- i.e. the reference's `Time/FPS = steps_per_epoch / epoch_time`
-(omnisafe/algorithms/on_policy/base/policy_gradient.py:L280).  Prints ONE JSON line.
+A "step" is one epoch of a BASELINE.json workload: by default `configs[1]` = PPOLag on the synthetic Box env
+(obs 60 / act 8), 4096 HBM-resident envs per GPU, T = 128 steps per env (524 288 samples per GPU), update_iters 8,
+batch_size 16384 -- i.e. the reference's `Time/FPS = steps_per_epoch / epoch_time`
+(omnisafe/algorithms/on_policy/base/policy_gradient.py:L280).  `--algo CPO` is `configs[2]`, `--algo TRPOLag|FOCOPS
+--obs-dim 17|60|111|376` is the sweep of `configs[4]`.  Prints ONE JSON line.
 
-  value   : device-timed (CUDA events, barrier + synchronize on both sides, max over ranks),
-            everything resident in HBM, in-kernel Philox noise.
-  e2e     : the same metric through the public `omnisafe_b200.Agent(...)` training loop with HOST
-            buffers: every epoch the standard-normal action-noise stream is copied from pinned host
-            memory (parity-mode input of the rollout) and the epoch's logged metrics are read back.
-  --impl reference : the CPU restatement of the reference path (oracle/, torch-CPU + numpy) timed
-            on the host cores on a bounded sample of the same workload (fewer envs, same T / update
-            schedule per sample); /root/reference does not exist on the GPU box.
+  value   : device-timed (CUDA events, barrier + synchronize on both sides, max over ranks), everything resident in
+            HBM, in-kernel Philox noise.  Arithmetic = `--precision`, default bf16x3: every layer GEMM runs on the
+            tensor cores as six kind::f16 MMAs over the three bf16 pieces of its fp32 operands with fp32
+            accumulation -- held by the tests to the bar of the exact-fp32 path (reference: fp32 Linear layers).
+            The tf32 mode (5e-3) is reported as a labelled extra, never as the headline.
+  e2e     : the same metric through the public `omnisafe_b200.Agent(...)` training loop with HOST buffers: every
+            epoch the standard-normal action-noise stream is copied from pinned host memory (parity-mode input of
+            the rollout) and the epoch's logged metrics are read back.
+  --impl reference : the CPU restatement of the reference path (oracle/, torch-CPU + numpy) timed on the host cores
+            on the SAME workload size (4096 envs x T = 128 per step); /root/reference does not exist on the GPU box.
 """
 from __future__ import annotations
 
@@ -35,6 +39,11 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(algo='PPOLag', env='SyntheticBox-v0', obs_dim=60, act_dim=8, envs_per_gpu=4096,
                 steps_per_env=128, batch_size=16384, update_iters=8, max_episode_steps=64)
+ALGOS = ('PPOLag', 'CPO', 'TRPOLag', 'FOCOPS')
+DTYPES = {'bf16x3': 'bf16x3 (fp32 operands as 3 bf16 pieces, 6 tcgen05 kind::f16 MMAs per product, fp32 accumulate: fp32-level '
+                    'results; GAE fp64 carry)',
+          'tf32': 'tf32 (fp32 storage/accumulate; GAE fp64 carry)',
+          'fp32': 'f32 (FMA tiles; GAE fp64 carry)'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,27 +102,37 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def _custom_cfgs(world: int, log_dir: str, epochs: int) -> dict:
+def _custom_cfgs(world: int, log_dir: str, epochs: int, obs_dim: int | None = None, precision: str | None = None) -> dict:
     w = WORKLOAD
     spe = world * w['envs_per_gpu'] * w['steps_per_env']
-    return {
+    cfg = {
         'seed': 0,
         'train_cfgs': {'device': 'cuda', 'vector_env_nums': w['envs_per_gpu'], 'parallel': world,
                        'total_steps': spe * epochs},
         'algo_cfgs': {'steps_per_epoch': spe, 'batch_size': w['batch_size'], 'update_iters': w['update_iters']},
         'logger_cfgs': {'log_dir': log_dir, 'use_tensorboard': False, 'save_model_freq': 10 ** 9},
-        'env_cfgs': {'obs_dim': w['obs_dim'], 'act_dim': w['act_dim'], 'max_episode_steps': w['max_episode_steps']},
+        'env_cfgs': {'obs_dim': obs_dim or w['obs_dim'], 'act_dim': w['act_dim'], 'max_episode_steps': w['max_episode_steps']},
     }
+    if precision:
+        cfg['train_cfgs']['matmul_precision'] = precision
+    return cfg
 
 
-def _launches_per_epoch() -> int:
-    w = WORKLOAD
-    T = w['steps_per_env']
-    n_mb = -(-(w['envs_per_gpu'] * T) // w['batch_size'])
-    rollout = 1 + (T + 1) + 2            # reset, T steps + bootstrap launch, episode window + sums
-    gae = 2 + 1                          # scan + stats reduce, moments
-    update = 1 + 1 + w['update_iters'] * (n_mb * 2 + 3)   # lagrange, old-policy snapshot, (fused fwd+bwd, fused reduce+clip+adam)*mb + (eval, reduce, kl)
-    return rollout + gae + update
+def _workload_name(algo: str, obs_dim: int) -> str:
+    which = ('configs[1]' if (algo, obs_dim) == ('PPOLag', 60) else 'configs[2]' if (algo, obs_dim) == ('CPO', 60)
+             else 'configs[4] obs-dim sweep' if algo in ('TRPOLag', 'FOCOPS') else 'variant')
+    return (f'{algo} SyntheticBox-v0 obs{obs_dim}/act8, 4096 envs/GPU x T=128, batch 16384, update_iters 8 '
+            f'(BASELINE.json {which})')
+
+
+def _flops_per_sample(O: int, A: int) -> int:
+    """fwd + bwd multiply-adds x2 of the three trunks (actor O-64-64-A, two critics O-64-64-1);
+    backward = 2x forward except that no dX is formed for layer 1 (SURVEY §8a row 3)."""
+    def net(out):
+        fwd = 2 * (O * 64 + 64 * 64 + 64 * out)
+        bwd = 2 * (O * 64 + 2 * 64 * 64 + 2 * 64 * out)
+        return fwd + bwd
+    return net(A) + 2 * net(1)
 
 
 def run_b200(args) -> dict:
@@ -131,10 +150,8 @@ def run_b200(args) -> dict:
     if world > 1:
         distributed.init_process_group('cuda')
     w = WORKLOAD
-    T, N = w['steps_per_env'], w['envs_per_gpu']
-    tmp = tempfile.mkdtemp(prefix='osb_bench_')
-    agent = omnisafe_b200.Agent(w['algo'], w['env'], custom_cfgs=_custom_cfgs(world, tmp, args.steps + args.warmup + 8))
-    algo = agent.agent
+    T, N, O, A = w['steps_per_env'], w['envs_per_gpu'], args.obs_dim, w['act_dim']
+    samples_global = world * N * T
 
     def barrier():
         torch.cuda.synchronize()
@@ -156,18 +173,27 @@ def run_b200(args) -> dict:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def make(precision):
+        tmp = tempfile.mkdtemp(prefix='osb_bench_')
+        agent = omnisafe_b200.Agent(args.algo, w['env'], custom_cfgs=_custom_cfgs(world, tmp, args.steps + args.warmup + 16, O, precision))
+        return agent.agent
+
+    algo = make(args.precision)
+    warm = max(args.warmup, 3)
+
     # ---- device-resident number ("value") -------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         algo.train_epoch()
+    barrier()
+    l0 = lib().osb_launch_count()
     with ClockSampler(local_rank) as clk:
         ms = timed(algo.train_epoch, args.steps)
+    launches = int(lib().osb_launch_count() - l0)
     clocks = clk.summary()
     ms_per_step = ms / args.steps
-    samples_global = world * N * T
     value = samples_global / (ms_per_step * 1e-3)
 
     # ---- end to end through the public loop with host buffers ----------------------------------
-    A = w['act_dim']
     host_eps = torch.randn(T, N, A, dtype=torch.float32).pin_memory()
     dev_eps = torch.empty(T, N, A, dtype=torch.float32, device='cuda')
     d2h = {'bytes': 0}
@@ -184,74 +210,105 @@ def run_b200(args) -> dict:
            'h2d_bytes_per_step': host_eps.numel() * 4, 'd2h_bytes_per_step': d2h['bytes'],
            'ms_per_step': ms_e2e}
 
-    # ---- roofline of the dominant kernel (fused minibatch fwd+bwd), timed live -----------------
+    # ---- stage split + roofline of the dominant kernel, timed live with CUDA events -------------
     peaks = _peaks()
     eng, buf, ac = algo._engine, algo._buf, algo._actor_critic
+    lag_state = getattr(getattr(algo, '_lagrange', None), 'state', None)
+    if lag_state is None:
+        lag_state = torch.zeros(4, dtype=torch.float32, device='cuda')
     d = buf.data
     total = T * N
-
-    def grad_launch():
-        lib().osb_minibatch_grad_tc(ptr(ac.theta), w['obs_dim'], A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']),
-                                    ptr(d['adv_r']), ptr(d['adv_c']), ptr(d['target_value_r']), ptr(d['target_value_c']),
-                                    ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 12345, 0, w['batch_size'], 0, 0.2, 0.0,
-                                    1.0, 0.0, ptr(algo._lagrange.state), ptr(eng.logstd_old), 7, ptr(eng.gpart), ptr(eng.stats_part), 0,
-                                    current_stream())
-
-    ms_grad = timed(grad_launch, 50) / 50
-    flop_per_sample = _flops_per_sample(w['obs_dim'], A)
-    ach_tf = flop_per_sample * w['batch_size'] / (ms_grad * 1e-3) / 1e12
+    ms_roll = timed(lambda: algo._env.rollout(algo._steps_per_epoch, ac, buf, algo._logger), 5) / 5
     ms_gae = timed(buf.finish_paths, 50) / 50
+    ms_upd = timed(algo._update, 5) / 5
+    flop_per_sample = _flops_per_sample(O, A)
+    n_mb = -(-total // w['batch_size'])
+    x3_path = args.precision == 'bf16x3' and O <= 64
+    if x3_path:
+        # one launch of the persistent kernel = one update iteration = n_mb minibatch steps (forward + loss + backward + optimiser)
+        def iter_launch():
+            lib().osb_ppo_update_iter_x3(ptr(ac.theta), ptr(ac.grad), ptr(ac.adam_m), ptr(ac.adam_v), ptr(ac.adam_step), O, A,
+                                         ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']),
+                                         ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(buf.adv_moments), 0, total, 12345,
+                                         w['batch_size'], 0, 0.2, 0.0, ptr(lag_state), 7, 0.001, 40.0, 0.0, 0.0, 0.0,
+                                         ptr(eng.gpart), ptr(eng.stats_part), ptr(eng.train_stats), 0, 0, 0, 1, 0, 0, current_stream())
+        ms_k = timed(iter_launch, 10) / 10          # learning rates 0: the parameters stay put
+        kname, rows_per_launch = 'minibatch_grad_x3_kernel<fused> (persistent: 1 launch = 1 update iteration)', total
+        traffic = None
+    else:
+        fn = lib().osb_minibatch_grad_tc if args.precision == 'tf32' else lib().osb_minibatch_grad
+
+        def iter_launch():
+            fn(ptr(ac.theta), O, A, ptr(d['obs']), ptr(d['act']), ptr(d['logp']), ptr(d['adv_r']), ptr(d['adv_c']),
+               ptr(d['target_value_r']), ptr(d['target_value_c']), ptr(eng.mu_old), ptr(buf.adv_moments), 0, total, 12345, 0,
+               w['batch_size'], 0, 0.2, 0.0, 1.0, 0.0, ptr(lag_state), ptr(eng.logstd_old), 7, ptr(eng.gpart),
+               ptr(eng.stats_part), 0, current_stream())
+        ms_k = timed(iter_launch, 50) / 50
+        kname = 'minibatch_grad_tc_kernel' if args.precision == 'tf32' else 'minibatch_grad_kernel'
+        rows_per_launch = w['batch_size']
+        traffic = 14.57e6 if (args.precision == 'tf32' and O == 60) else None     # ncu --set full, profiles/r01_ncu_minibatch_grad_tc.md
+    ach_tf = flop_per_sample * rows_per_launch / (ms_k * 1e-3) / 1e12
+    row_bytes = 4.0 * (O + A + 5)
     gae_gbs = 33.0 * total / (ms_gae * 1e-3) / 1e9
-    roofline = {'kernel': 'minibatch_grad_tc_kernel', 'bound': 'tensor', 'achieved': ach_tf,
-                'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': ach_tf / peaks['bf16_tflops_sustained'],
-                'traffic': 14.57e6,   # dram bytes read + written per launch, ncu --set full (profiles/r01_ncu_minibatch_grad_tc.md)
-                'algorithmic_bytes': 292.0 * w['batch_size'] + 147 * 24850 * 4.0,   # sample rows read + per-CTA partial gradients written
-                'peak_source': peaks['source'] + ' (cuBLAS bf16 sustained; kernel runs tcgen05 kind::tf32, nominal tf32 peak = half of bf16)',
-                'us_per_launch': ms_grad * 1e3,
-                'gae': {'kernel': 'gae_dual_kernel', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
-                        'unit': 'GB/s', 'frac': gae_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae * 1e3,
-                        'bytes_per_sample': 33}}
+    roofline = {
+        'kernel': kname, 'bound': 'tensor', 'achieved': ach_tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+        'frac': ach_tf / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+        'algorithmic_flops_per_launch': float(flop_per_sample) * rows_per_launch,
+        'algorithmic_bytes': row_bytes * rows_per_launch + 4.0 * eng.P * (rows_per_launch // w['batch_size']),   # sample rows read once + one gradient per minibatch step
+        'peak_source': peaks['source'] + ' (cuBLAS bf16, sustained); fp32-equivalent FLOPs are counted once although the '
+                       'bf16x3 mode executes 6 bf16 MMAs per product' if x3_path else peaks['source'] + ' (cuBLAS bf16, sustained)',
+        'us_per_launch': ms_k * 1e3, 'us_per_minibatch_step': ms_k * 1e3 / (rows_per_launch // w['batch_size']),
+        'mma_executed_tflops': ach_tf * 6.0 if x3_path else None,
+        'gae': {'kernel': 'gae_dual_kernel', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
+                'unit': 'GB/s', 'frac': gae_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae * 1e3, 'bytes_per_sample': 33,
+                'note': 'T = 128: 17 MB, latency bound (one wave); the long-horizon figure is in profiles/'},
+        'rollout_step': {'kernel': 'rollout_step_tc_kernel<bf16x3>' if x3_path else ('rollout_step_tc_kernel<tf32>' if args.precision == 'tf32' and O <= 64 else 'rollout_step_kernel'),
+                         'bound': 'latency', 'us_per_step': ms_roll * 1e3 / (T + 1),
+                         'achieved_tflops': (2 * (O * 64 + 64 * 64 + 64 * A) + 4 * (O * 64 + 64 * 64 + 64)) * N / (ms_roll * 1e-3 / (T + 1)) / 1e12,
+                         'appended_bytes_per_step': row_bytes * N},
+        'stage_ms': {'rollout': ms_roll, 'gae': ms_gae, 'update': ms_upd},
+    }
 
     out = {
-        'metric': 'env-steps/sec (rollout+GAE+update) PPO-Lag', 'value': value, 'unit': 'env-steps/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 storage/accumulate; GAE fp64 carry)', 'data': 'synthetic',
-        'config': {'workload': 'PPOLag SyntheticBox-v0 obs60/act8, 4096 envs/GPU x T=128, batch 16384, update_iters 8 '
-                               '(BASELINE.json configs[1])', 'envs_per_gpu': N, 'steps_per_env': T,
-                   'global_samples_per_step': samples_global, 'parallelism': f'dp{world}',
-                   'l2_policy': 'inputs larger than L2 (per-epoch slabs ~157 MB > 126 MB)', 'noise': 'in-kernel Philox'},
-        'e2e': e2e, 'gpu_launches': _launches_per_epoch() * args.steps, 'clocks': clocks, 'roofline': roofline,
+        'metric': f'env-steps/sec (rollout+GAE+update) {args.algo.replace("PPOLag", "PPO-Lag")}', 'value': value, 'unit': 'env-steps/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPES[args.precision] if (x3_path or args.precision != 'bf16x3') else DTYPES['fp32'] + ' [obs_dim > 64 is not on the bf16x3 path]',
+        'data': 'synthetic',
+        'config': {'workload': _workload_name(args.algo, O), 'algo': args.algo, 'obs_dim': O, 'envs_per_gpu': N, 'steps_per_env': T,
+                   'global_samples_per_step': samples_global, 'parallelism': f'dp{world}', 'matmul_precision': args.precision,
+                   'l2_policy': f'inputs larger than L2 (per-epoch slabs ~{(row_bytes + 48) * total / 1e6:.0f} MB > 126 MB)' if (row_bytes + 48) * total > 126e6
+                   else 'per-epoch slabs fit L2; every epoch rewrites them (rollout) before the update reads them',
+                   'noise': 'in-kernel Philox'},
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
     }
+    if rank == 0 and world == 1 and not args.no_extras and args.precision == 'bf16x3':
+        del algo
+        alt = make('tf32')
+        for _ in range(3):
+            alt.train_epoch()
+        ms_alt = timed(alt.train_epoch, max(3, args.steps // 2)) / max(3, args.steps // 2)
+        out['extra'] = {'tf32': {'value': samples_global / (ms_alt * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': ms_alt,
+                                 'note': 'kind::tf32 tiles: 10-bit mantissa, certified only to 5e-3 -- NOT the headline'}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(budget_s=20.0)
+        out['cpu_baseline'] = cpu_baseline(args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out if rank == 0 else {}
 
 
-def _flops_per_sample(O: int, A: int) -> int:
-    """fwd + bwd multiply-adds x2 of the three trunks (actor O-64-64-A, two critics O-64-64-1);
-    backward = 2x forward except that no dX is formed for layer 1 (SURVEY §8a row 3)."""
-    def net(out):
-        fwd = 2 * (O * 64 + 64 * 64 + 64 * out)
-        bwd = 2 * (O * 64 + 2 * 64 * 64 + 2 * 64 * out)
-        return fwd + bwd
-    return net(A) + 2 * net(1)
-
-
 # ------------------------------------------------------------------------------------------------
-def _oracle_epoch(state, n_envs: int):
-    """One epoch of the CPU restatement on n_envs envs (same T / update schedule per sample)."""
+def _oracle_epoch(state, n_envs: int, algo: str):
+    """One epoch of the CPU restatement on n_envs envs (same T / update schedule)."""
     from oracle import gae as ogae
     from oracle import learner as ol
     from oracle import rollout as orollout
 
     w = WORKLOAD
-    T, O, A = w['steps_per_env'], w['obs_dim'], w['act_dim']
+    T, A = w['steps_per_env'], w['act_dim']
     eps = state['rng'].standard_normal((T, n_envs, A)).astype(np.float32)
-    theta = state['learner'].flat()
+    L = state['learner']
+    theta = L.flat()
     window = state['window']
     sl = orollout.rollout_epoch(state['env'], state['norm'], theta, T, eps, window=window)
     out = ogae.dual_gae_slab(sl['rew'], sl['cost'], sl['val_r'], sl['val_c'], sl['flags'], sl['boot_r'], sl['boot_c'],
@@ -262,22 +319,38 @@ def _oracle_epoch(state, n_envs: int):
     data = {'obs': em(sl['obs']), 'act': em(sl['act']), 'logp': em(sl['logp']), 'adv_r': em(sr), 'adv_c': em(sc),
             'target_value_r': em(out['tv_r']), 'target_value_c': em(out['tv_c'])}
     jc = float(np.mean([c for _, c, _ in window[-100:]]))
-    lam = state['lagrange'].update(jc)
     bs = max(64, w['batch_size'] * n_envs // w['envs_per_gpu'])
     perms = [state['rng'].permutation(B) for _ in range(w['update_iters'])]
-    state['learner'].update_ppo(data, perms, lam, batch_size=bs)
+    if algo in ('PPOLag', 'FOCOPS'):
+        lam = state['lagrange'].update(jc)
+        L.update_ppo(data, perms, lam, batch_size=bs, focops={'lam': 1.5, 'eta': 0.02} if algo == 'FOCOPS' else None)
+        return B
+    # natural-gradient family: critics over the minibatches, then one full-batch actor step
+    t = {k: torch.as_tensor(v) for k, v in data.items()}
+    for perm in perms:
+        perm = torch.as_tensor(np.asarray(perm, np.int64))
+        for s in range(0, B, bs):
+            idx = perm[s:s + bs]
+            L.critic_step('reward_critic', t['obs'][idx], t['target_value_r'][idx], 0.001, 40.0)
+            L.critic_step('cost_critic', t['obs'][idx], t['target_value_c'][idx], 0.001, 40.0)
+    if algo == 'TRPOLag':
+        lam = state['lagrange'].update(jc)
+        adv = (t['adv_r'] - lam * t['adv_c']) / (1 + lam)
+        ol.trpo_actor_step(L, t['obs'], t['act'], t['logp'], adv)
+    else:  # CPO
+        ol.cpo_actor_step(L, t['obs'], t['act'], t['logp'], t['adv_r'], t['adv_c'], jc - 25.0)
     return B
 
 
-def _oracle_state(n_envs: int):
+def _oracle_state(n_envs: int, obs_dim: int):
     from oracle import actor_critic as oac
     from oracle import learner as ol
     from oracle.normalizer import Normalizer
     from oracle.synthetic_env import SyntheticBoxEnv
 
     w = WORKLOAD
-    return {'env': SyntheticBoxEnv(n_envs, w['obs_dim'], w['act_dim'], max_episode_steps=w['max_episode_steps'], seed=0),
-            'norm': Normalizer((w['obs_dim'],)), 'learner': ol.Learner(oac.init_theta(w['obs_dim'], w['act_dim'], 0), w['obs_dim'], w['act_dim']),
+    return {'env': SyntheticBoxEnv(n_envs, obs_dim, w['act_dim'], max_episode_steps=w['max_episode_steps'], seed=0),
+            'norm': Normalizer((obs_dim,)), 'learner': ol.Learner(oac.init_theta(obs_dim, w['act_dim'], 0), obs_dim, w['act_dim']),
             'lagrange': ol.Lagrange(25.0, 0.001, 0.035), 'rng': np.random.default_rng(0), 'window': []}
 
 
@@ -290,49 +363,53 @@ def _host_threads() -> int:
     return n
 
 
-def _sized_sample(budget_s: float) -> int:
-    """Largest env count (multiple of 64, <= 4096) whose epoch fits `budget_s`, from a 256-env probe."""
-    t0 = time.time(); st = _oracle_state(256); _oracle_epoch(st, 256); probe = time.time() - t0
-    per_env = probe / 256.0                      # pessimistic: per-env cost falls with n
-    return int(min(WORKLOAD['envs_per_gpu'], max(64, (budget_s / max(per_env, 1e-9)) // 64 * 64)))
+REF_ENVS = WORKLOAD['envs_per_gpu']      # the reference arm runs the FULL per-GPU workload: same config as the GPU arm
+REF_ENVS_SECOND_ORDER = 1024             # TRPOLag / CPO: 33 full-batch double-backward passes per epoch on the CPU -> a FIXED quarter
 
 
-def cpu_baseline(budget_s: float = 20.0) -> dict:
-    """The oracle port timed on the host cores on a bounded sample: one full epoch on n envs."""
+def _ref_envs(algo: str) -> int:
+    return REF_ENVS if algo in ('PPOLag', 'FOCOPS') else min(REF_ENVS, REF_ENVS_SECOND_ORDER)
+
+
+def cpu_baseline(args) -> dict:
+    """The oracle port timed on the host cores: one full-size epoch (after a small warm-up epoch that pays for thread
+    pool / allocator start-up)."""
     threads = _host_threads()
-    n = _sized_sample(budget_s)
-    st = _oracle_state(n)
-    t0 = time.time(); B = _oracle_epoch(st, n); dt = time.time() - t0
+    _oracle_epoch(_oracle_state(128, args.obs_dim), 128, args.algo)
+    n = _ref_envs(args.algo)
+    st = _oracle_state(n, args.obs_dim)
+    t0 = time.time(); B = _oracle_epoch(st, n, args.algo); dt = time.time() - t0
     return {'value': B / dt, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-            'sample': f'1 PPOLag epoch (rollout+GAE+update, update_iters 8) on {n} envs x T=128 = {B} env-steps, '
+            'sample': f'1 {args.algo} epoch (rollout+GAE+update, update_iters 8, batch 16384) on {n} envs x T=128 = {B} env-steps (fixed size; the GPU arm runs 4096), '
                       f'oracle/ torch-CPU+numpy restatement, {threads} torch threads of {os.cpu_count()} cores, {dt:.1f} s'}
 
 
 def run_reference(args) -> dict:
-    """--impl reference: the CPU restatement of the reference path on the host cores, bounded sample
-    per step.  Under torchrun only rank 0 works."""
+    """--impl reference: the CPU restatement of the reference path on the host cores, every step one epoch of the
+    same workload as the GPU arm (4096 envs x T = 128).  Under torchrun only rank 0 works."""
     if int(os.environ.get('RANK', '0')) != 0:
         return {}
     threads = _host_threads()
     steps, warm = args.steps, max(args.warmup, 1)
-    n = _sized_sample(120.0 / (steps + warm))            # whole run within a few minutes
-    st = _oracle_state(n)
-    for _ in range(warm):
-        _oracle_epoch(st, n)
+    n = _ref_envs(args.algo)
+    _oracle_epoch(_oracle_state(128, args.obs_dim), 128, args.algo)        # thread pool / allocator start-up
+    st = _oracle_state(n, args.obs_dim)
+    for _ in range(min(warm, 2)):                     # epochs are seconds long: two warm-up epochs settle the caches
+        _oracle_epoch(st, n, args.algo)
     t0 = time.time()
     done = 0
     for _ in range(steps):
-        done += _oracle_epoch(st, n)
+        done += _oracle_epoch(st, n, args.algo)
     dt = time.time() - t0
     v = done / dt
-    sample = (f'each step = 1 PPOLag epoch (rollout+GAE+update, update_iters 8, batch scaled) on {n} envs x T=128; '
-              f'oracle/ torch-CPU+numpy restatement of the reference path, {threads} torch threads of {os.cpu_count()} cores')
-    return {'impl': 'reference', 'metric': 'env-steps/sec (rollout+GAE+update) PPO-Lag', 'value': v,
-            'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+    sample = (f'each step = 1 {args.algo} epoch (rollout+GAE+update, update_iters 8, batch 16384) on {n} envs x T=128 (fixed size; the GPU arm\'s per-GPU '
+              f'workload is 4096 envs); oracle/ torch-CPU+numpy restatement of the reference path, {threads} torch threads of {os.cpu_count()} cores')
+    return {'impl': 'reference', 'metric': f'env-steps/sec (rollout+GAE+update) {args.algo.replace("PPOLag", "PPO-Lag")}', 'value': v,
+            'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': min(warm, 2),
             'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'PPOLag SyntheticBox-v0 obs60/act8, T=128, update_iters 8 (bounded sample of '
-                                   'BASELINE.json configs[1])', 'sample_envs': n},
+            'config': {'workload': _workload_name(args.algo, args.obs_dim), 'algo': args.algo, 'obs_dim': args.obs_dim,
+                       'envs_per_gpu': n, 'steps_per_env': WORKLOAD['steps_per_env'], 'sample_envs': n},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -344,7 +421,11 @@ def main() -> None:
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--algo', default=WORKLOAD['algo'], choices=ALGOS)
+    ap.add_argument('--obs-dim', type=int, default=WORKLOAD['obs_dim'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     out = run_reference(args) if args.impl == 'reference' else run_b200(args)
     if out:

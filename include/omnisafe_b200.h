@@ -28,6 +28,8 @@ extern "C" {
 /* ---- plumbing ---------------------------------------------------------------------------- */
 const char* osb_last_error(void);
 int osb_abi_version(void);
+/* kernels launched by this library in this process so far (bench.py counts its timed region with it) */
+long long osb_launch_count(void);
 int osb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- dual GAE (segmented reverse scan) ----------------------------------------------------

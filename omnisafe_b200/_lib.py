@@ -72,7 +72,7 @@ class _Lib:
     def __getattr__(self, name: str):
         fn = getattr(self._dll, name)
         # size / version queries return their value; everything else returns an error code
-        if name.endswith(('_blocks', '_doubles', '_version')) or name not in self._checked:
+        if name.endswith(('_blocks', '_doubles', '_version', '_count')) or name not in self._checked:
             return fn
 
         def checked(*args):

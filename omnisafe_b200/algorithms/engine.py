@@ -98,9 +98,9 @@ class UpdateEngine:
         """loss.backward() of the full-batch surrogate + avg_grads (natural_pg.py:L150-157):
         out_grad <- sign * d loss / d theta_actor; returns the device scalar `loss` (rank-averaged)."""
         a = self.agent
-        if self._tc() and loss_kind in (LOSS_RATIO, LOSS_COST):
+        if (self._tc() or self._x3()) and loss_kind in (LOSS_RATIO, LOSS_COST):
             nb = lib().osb_tc_grid_blocks(self.total, NET_ACTOR)
-            lib().osb_minibatch_grad_tc(
+            (lib().osb_minibatch_grad_x3 if self._x3() else lib().osb_minibatch_grad_tc)(
                 ptr(a.theta), self.O, self.A, *self._batch_ptrs(), ptr(self.mu_old), ptr(self.buf.adv_moments),
                 0, self.total, self.next_perm_seed(), 0, self.total, int(loss_kind), 0.0, 0.0, 1.0, 0.0,
                 ptr(lagrange), ptr(self.logstd_old), NET_ACTOR, ptr(self.gpart), ptr(self.stats_part), 0,

@@ -418,25 +418,39 @@ class CPO(TRPO):
         return 0, A, B
 
     def _step_direction(self, optim_case, xHx, x, A, B, q, p, r, s, ep_costs):
+        """second_order/cpo.py:L271-337.  The reference evaluates these scalars as fp32 tensors, i.e. with IEEE
+        semantics: sqrt of a negative number (A = q - r^2/s can come out slightly negative after an inexact CG solve)
+        and x / 0 give NaN / inf instead of raising, a NaN comparison is False, so the search falls back to
+        lambda_b_star or a zero step.  `_sqrt` / `_div` reproduce that instead of Python's exceptions."""
         kl = self._cfgs.algo_cfgs.target_kl
+        nan, inf = float('nan'), math.inf
+        _sqrt = lambda v: math.sqrt(v) if v >= 0 else nan   # noqa: E731  (NaN input: comparison False -> NaN)
+
+        def _div(a, b):
+            if b != 0:
+                return a / b
+            return nan if (a == 0 or a != a) else math.copysign(inf, a) * math.copysign(1.0, b)
+
+        def clampf(v, lo, hi):      # torch.clamp: NaN stays NaN
+            return v if v != v else min(max(v, lo), hi)
+
         if optim_case in (3, 4):
-            alpha = math.sqrt(2 * kl / (xHx + 1e-8))
-            return alpha * x, 1 / (alpha + 1e-8), 0.0
+            alpha = _sqrt(_div(2 * kl, xHx + 1e-8))
+            return alpha * x, _div(1.0, alpha + 1e-8), 0.0
         if optim_case in (1, 2):
-            lambda_a = math.sqrt(A / B)
-            lambda_b = math.sqrt(q / (2 * kl))
-            bound = r / (ep_costs + 1e-8)
-            clampf = lambda v, lo, hi: min(max(v, lo), hi)   # noqa: E731
+            lambda_a = _sqrt(_div(A, B))
+            lambda_b = _sqrt(_div(q, 2 * kl))
+            bound = _div(r, ep_costs + 1e-8)
             if ep_costs < 0:
-                lambda_a_star, lambda_b_star = clampf(lambda_a, 0.0, bound), clampf(lambda_b, bound, math.inf)
+                lambda_a_star, lambda_b_star = clampf(lambda_a, 0.0, bound), clampf(lambda_b, bound, inf)
             else:
-                lambda_a_star, lambda_b_star = clampf(lambda_a, bound, math.inf), clampf(lambda_b, 0.0, bound)
-            f_a = lambda lam: -0.5 * (A / (lam + 1e-8) + B * lam) - r * ep_costs / (s + 1e-8)   # noqa: E731
-            f_b = lambda lam: -0.5 * (q / (lam + 1e-8) + 2 * kl * lam)   # noqa: E731
+                lambda_a_star, lambda_b_star = clampf(lambda_a, bound, inf), clampf(lambda_b, 0.0, bound)
+            f_a = lambda lam: -0.5 * (_div(A, lam + 1e-8) + B * lam) - _div(r * ep_costs, s + 1e-8)   # noqa: E731
+            f_b = lambda lam: -0.5 * (_div(q, lam + 1e-8) + 2 * kl * lam)   # noqa: E731
             lambda_star = lambda_a_star if f_a(lambda_a_star) >= f_b(lambda_b_star) else lambda_b_star
-            nu_star = max(lambda_star * ep_costs - r, 0.0) / (s + 1e-8)
-            return 1.0 / (lambda_star + 1e-8) * (x - nu_star * p), lambda_star, nu_star
-        nu_star = math.sqrt(2 * kl / (s + 1e-8))
+            nu_star = _div(max(lambda_star * ep_costs - r, 0.0), s + 1e-8)
+            return _div(1.0, lambda_star + 1e-8) * (x - nu_star * p), lambda_star, nu_star
+        nu_star = _sqrt(_div(2 * kl, s + 1e-8))
         return -nu_star * p, 0.0, nu_star
 
     def _cpo_search_step(self, step_direction, theta_old, loss_reward_before, loss_cost_before,

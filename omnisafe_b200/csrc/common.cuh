@@ -10,6 +10,7 @@
 #define OSB_ERR_UNSUPPORTED 3
 
 extern "C" void osb_set_error(const char* msg);
+extern "C" void osb_count_launch(void);   // kernel-launch counter behind osb_launch_count() (bench.py: gpu_launches)
 
 #define OSB_CHECK_ARG(cond, msg)                                   \
     do {                                                           \
@@ -31,7 +32,11 @@ extern "C" void osb_set_error(const char* msg);
         }                                                                            \
     } while (0)
 
-#define OSB_LAUNCH_CHECK() OSB_CUDA(cudaGetLastError())
+#define OSB_LAUNCH_CHECK()              \
+    do {                                \
+        osb_count_launch();             \
+        OSB_CUDA(cudaGetLastError());   \
+    } while (0)
 
 // Segment flag bits of the `flags[T][N]` slab (one byte per sample).
 #define OSB_FLAG_TERMINATED 1u

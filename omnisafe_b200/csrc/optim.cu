@@ -538,6 +538,7 @@ int osb_optim_fused(const float* gpart, const float* stats_part, int nblocks, in
     p.m = adam_m; p.v = adam_v; p.max_grad_norm = max_grad_norm;
     p.lr[0] = lr_actor; p.lr[1] = lr_critic_r; p.lr[2] = lr_critic_c;
     void* args[] = {&p};
+    osb_count_launch();
     OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
                                          (cudaStream_t)stream));
     return OSB_OK;
@@ -588,6 +589,7 @@ int osb_optim_fused_p2p(const float* gpart, const float* stats_part, int nblocks
     a.peer_buf = (float* const*)peer_buf; a.peer_flag = (unsigned int* const*)peer_flag;
     a.world = world; a.rank = rank; a.step_id = step_id; a.error_flag = error_flag;
     void* args[] = {&a};
+    osb_count_launch();
     OSB_CUDA(cudaLaunchCooperativeKernel((void*)optim_fused_p2p_kernel, dim3(osb_optim_blocks(O, A), 3), dim3(OT), args, 0,
                                          (cudaStream_t)stream));
     return OSB_OK;

@@ -966,6 +966,7 @@ int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam
     if (rc) return rc;
     const bool single = (net_mask & (net_mask - 1)) == 0;
     void* args[] = {&p};
+    osb_count_launch();
     OSB_CUDA(cudaLaunchCooperativeKernel(A <= 8 ? (void*)minibatch_grad_x3_kernel<true, 8> : (void*)minibatch_grad_x3_kernel<true, 16>,
                                          dim3(nb, single ? 1 : 3), dim3(NTX3), args, 1024 + X3_SMEM, s));
     return OSB_OK;

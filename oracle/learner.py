@@ -407,3 +407,50 @@ def simmer_control_budget(agent: SimmerPIDAgent, safety_budget, ep_cost, saute_g
     scale = (1 - saute_gamma ** max_ep_len) / (1 - saute_gamma) / max_ep_len
     obs = torch.as_tensor(ep_cost, dtype=torch.float32) * scale
     return agent.act(torch.as_tensor(safety_budget, dtype=torch.float32), obs)
+
+
+def cpo_actor_step(L: 'Learner', obs, act, logp, adv_r, adv_c, ep_costs, *, damping=0.1, cg_iters=15, target_kl=0.01,
+                   total_steps=20, decay=0.8):
+    """CPO._update_actor (second_order/cpo.py:L340-462) on the oracle Learner: reward / cost surrogate gradients,
+    two CG solves, case analysis, closed-form step and the cost-aware backtracking line search (cpo.py:L57-180).
+    `ep_costs` = mean episode cost - cost_limit.  Returns (optim_case, acceptance_step)."""
+    theta_old = torch.as_tensor(L.flat('actor')).clone()
+    with torch.no_grad():
+        pd = L.dist(obs)
+        p_dist = Normal(pd.loc.clone(), pd.scale.clone())
+    L.zero_grad('actor')
+    loss_reward_before = L.loss_pi_plain(obs, act, logp, adv_r)
+    loss_reward_before.backward()
+    grads = -L.flat_grad('actor')
+    fvp = lambda v: L.fvp(v, obs, damping)   # noqa: E731
+    x = conjugate_gradients(fvp, grads.numpy(), cg_iters)
+    xHx = float(x.dot(fvp(x)))
+    L.zero_grad('actor')
+    loss_cost_before = L.loss_pi_cost(obs, act, logp, adv_c)
+    loss_cost_before.backward()
+    b_grads = L.flat_grad('actor').clone()
+    p = conjugate_gradients(fvp, b_grads.numpy(), cg_iters)
+    q, r, s = xHx, float(grads.dot(p)), float(b_grads.dot(p))
+    case, A, B = cpo_determine_case(float(b_grads.dot(b_grads)), ep_costs, q, r, s, target_kl)
+    step_direction, _, _ = cpo_step_direction(case, xHx, x, A, B, q, p, r, s, ep_costs, target_kl)
+    step_direction = torch.as_tensor(step_direction, dtype=torch.float32)
+    step_frac, accept = 1.0, 0
+    for step in range(total_steps):
+        L.set_flat('actor', theta_old + step_frac * step_direction)
+        with torch.no_grad():
+            loss_r = L.loss_pi_plain(obs, act, logp, adv_r)
+            loss_c = L.loss_pi_cost(obs, act, logp, adv_c)
+            kl = float(kl_divergence(p_dist, L.dist(obs)).mean())
+        improve = float(loss_reward_before.detach() - loss_r)
+        cost_diff = float(loss_c - loss_cost_before.detach())
+        if not np.isfinite(kl):
+            continue
+        if (case > 1 and improve < 0) or cost_diff > max(-ep_costs, 0) or kl > target_kl:
+            step_frac *= decay
+            continue
+        accept = step + 1
+        break
+    else:
+        step_direction = torch.zeros_like(step_direction)
+    L.set_flat('actor', theta_old + step_frac * step_direction)
+    return case, accept

@@ -96,3 +96,32 @@ def test_two_rank_gloo_host_logic():
         assert T == 8 and abs(avg - 1.5) < 1e-6 and bad
         assert sums == [3.0, 20.0, 2.0, 10.0]          # SUM over ranks of the epoch statistics vector
         assert env_off == rank * 16                    # rank r owns global envs [r*N, (r+1)*N)
+
+
+def test_cpo_step_direction_ieee_fallbacks():
+    """after an inexact CG solve A = q - r^2/s can be slightly negative and s <= 0; the reference
+    (second_order/cpo.py:L271-337, fp32 tensors) then gets NaN, the NaN comparison is False and lambda_b_star is
+    chosen / the step is NaN (rejected by the line search) -- it never raises."""
+    import math
+    from types import SimpleNamespace as NS
+
+    import torch
+
+    from omnisafe_b200.algorithms.on_policy import CPO
+
+    me = NS(_cfgs=NS(algo_cfgs=NS(target_kl=0.01)))
+    x, p = torch.ones(4), torch.full((4,), 0.5)
+    # case 1/2 with A < 0: lambda_a is NaN -> f_a >= f_b is False -> lambda_b_star
+    q, kl = 0.3, 0.01
+    step, lam, nu = CPO._step_direction(me, 2, q, x, -1e-3, 0.5, q, p, 0.1, 1.0, -0.2)
+    lam_b = max(math.sqrt(q / (2 * kl)), 0.1 / (-0.2 + 1e-8))
+    assert abs(lam - lam_b) < 1e-9 and torch.isfinite(step).all()
+    # B == 0: A / B is inf, not ZeroDivisionError
+    step, lam, nu = CPO._step_direction(me, 1, q, x, 0.2, 0.0, q, p, 0.1, 1.0, 0.2)
+    assert math.isfinite(lam) and torch.isfinite(step).all()
+    # case 0 with s < 0: NaN step (the line search then rejects it) instead of `math domain error`
+    step, lam, nu = CPO._step_direction(me, 0, q, x, 0.2, -0.1, q, p, 0.1, -0.5, 0.2)
+    assert nu != nu and torch.isnan(step).all()
+    # well-conditioned values still give the closed form
+    step, lam, nu = CPO._step_direction(me, 3, 0.5, x, 0.1, -0.1, 0.5, p, 0.1, 1.0, -0.2)
+    assert abs(float(step[0]) - math.sqrt(2 * kl / (0.5 + 1e-8))) < 1e-7
