@@ -454,3 +454,65 @@ def cpo_actor_step(L: 'Learner', obs, act, logp, adv_r, adv_c, ep_costs, *, damp
         step_direction = torch.zeros_like(step_direction)
     L.set_flat('actor', theta_old + step_frac * step_direction)
     return case, accept
+
+
+def update_ppo_multirank(L: 'Learner', datas, perms_per_rank, lam, *, batch_size, clip=0.2, entropy_coef=0.0,
+                         critic_norm_coef=0.001, max_grad_norm=40.0, target_kl=0.02, kl_early_stop=True):
+    """PolicyGradient._update under `parallel = P` (policy_gradient.py:L345-405, L437-443; distributed.py:L193-198),
+    simulated in ONE process: every rank has its own env-major data and DataLoader orders, the parameters are
+    replicated.  Per minibatch step and network: each rank's gradient is clipped locally (clip_grad_norm_), the clipped
+    gradients are averaged over the ranks, then ONE Adam step.  The early-stop KL is the rank average."""
+    P = len(datas)
+    ts = [{k: torch.as_tensor(v) for k, v in d.items()} for d in datas]
+    olds = []
+    with torch.no_grad():
+        for t in ts:
+            o = L.dist(t['obs'])
+            olds.append(Normal(o.loc.clone(), o.scale.clone()))
+    n_iters = len(perms_per_rank[0])
+    stats = {'kl': [], 'iters': 0}
+
+    def avg_step(net, loss_fn):
+        params = list(L.params[net].values())
+        acc = [torch.zeros_like(p_) for p_ in params]
+        for r in range(P):
+            L.opt[net].zero_grad()
+            loss_fn(r).backward()
+            if max_grad_norm is not None:
+                clip_grad_norm_(params, max_grad_norm)
+            for a, p_ in zip(acc, params):
+                a += p_.grad
+        for a, p_ in zip(acc, params):
+            p_.grad = a / P
+        L.opt[net].step()
+
+    for it in range(n_iters):
+        perms = [torch.as_tensor(np.asarray(perms_per_rank[r][it], np.int64)) for r in range(P)]
+        for s in range(0, len(perms[0]), batch_size):
+            idx = [pm[s:s + batch_size] for pm in perms]
+
+            def critic_loss(net, tgt):
+                def f(r):
+                    v = ac.critic_value(L.params[net], ts[r]['obs'][idx[r]])
+                    loss = torch.nn.functional.mse_loss(v, ts[r][tgt][idx[r]])
+                    for p_ in L.params[net].values():
+                        loss = loss + p_.pow(2).sum() * critic_norm_coef
+                    return loss
+                return f
+
+            avg_step('reward_critic', critic_loss('reward_critic', 'target_value_r'))
+            avg_step('cost_critic', critic_loss('cost_critic', 'target_value_c'))
+
+            def actor_loss(r):
+                t = ts[r]
+                adv = (t['adv_r'][idx[r]] - lam * t['adv_c'][idx[r]]) / (1 + lam)
+                return L.loss_pi_ppo(t['obs'][idx[r]], t['act'][idx[r]], t['logp'][idx[r]], adv, clip, entropy_coef)[0]
+
+            avg_step('actor', actor_loss)
+        with torch.no_grad():
+            kl = float(np.mean([kl_divergence(olds[r], L.dist(ts[r]['obs'])).sum(-1, keepdim=True).mean().item() for r in range(P)]))
+        stats['kl'].append(kl)
+        stats['iters'] += 1
+        if kl_early_stop and kl > target_kl:
+            break
+    return stats

@@ -408,3 +408,22 @@ def test_cup_update_golden(golden_dir):
     done = L.update_cup_stage2(data, g['perms'][4:8:2], float(lam), batch_size=int(g['batch_size']))
     assert done == int(g['second_stop_iter'][-1])
     np.testing.assert_allclose(L.flat(), g['theta1'], rtol=1e-5, atol=1e-6)
+
+
+def test_multirank_update_golden(golden_dir):
+    """The reference under parallel = 2 (two gloo ranks of the unmodified reference, tests/golden/
+    make_golden_parallel2.py): clip locally -> average -> Adam per minibatch, rank-averaged KL, all-reduced Jc."""
+    from oracle import learner as ol
+
+    g = np.load(os.path.join(golden_dir, 'update_ppolag_parallel2.npz'))
+    O, A = int(g['O']), int(g['A'])
+    datas = [{k[len(f'r{r}_data_'):]: g[k] for k in g.files if k.startswith(f'r{r}_data_')} for r in (0, 1)]
+    lag = ol.Lagrange(float(g['cost_limit']), float(g['lam0']), float(g['lambda_lr']))
+    lam = lag.update(float(g['Jc']))
+    assert abs(lam - float(g['lam1'])) < 1e-6
+    L = ol.Learner(g['theta0'], O, A)
+    st = ol.update_ppo_multirank(L, datas, [g['perms_r0'][::2], g['perms_r1'][::2]], lam, batch_size=int(g['batch_size']))   # every DataLoader pass draws two permutations, the second one is used
+    got, want = L.flat(), g['theta1']
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6)
+    assert st['iters'] == int(g['stop_iter'][-1])
+    np.testing.assert_allclose(st['kl'][-1], g['kl'][-1], rtol=1e-3, atol=1e-7)
