@@ -37,7 +37,7 @@ class OnPolicyAdapter:
         self.ep_meta = torch.zeros(2, dtype=torch.int32, device=self._device)
         self.window_sums = torch.zeros(4, dtype=torch.float64, device=self._device)
         self._epoch_index = 0
-        prec = str(getattr(cfgs.train_cfgs, 'matmul_precision', 'fp32') if hasattr(cfgs, 'train_cfgs') else 'fp32')
+        prec = str(getattr(cfgs.train_cfgs, 'matmul_precision', 'bf16x3') if hasattr(cfgs, 'train_cfgs') else 'fp32')
         self.precision = {'fp32': 0, 'tf32': 1, 'bf16x3': 2}[prec]
         self.noise_seed = (int(seed) * 2654435761 + 12345) & 0xFFFFFFFF
 

@@ -54,7 +54,7 @@ class PolicyGradient(BaseAlgo):
             a.adv_estimation_method, a.penalty_coef, a.standardized_rew_adv, a.standardized_cost_adv,
             num_envs=self._cfgs.train_cfgs.vector_env_nums, device=self._device, keep_discounted_ret=False)
         self._engine = UpdateEngine(self._actor_critic, self._buf)
-        prec = str(getattr(self._cfgs.train_cfgs, 'matmul_precision', 'fp32'))
+        prec = str(getattr(self._cfgs.train_cfgs, 'matmul_precision', 'bf16x3'))   # upstream YAMLs have no such key: parity-grade tensor-core tiles
         assert prec in ('fp32', 'tf32', 'bf16x3'), "train_cfgs.matmul_precision must be 'fp32', 'tf32' or 'bf16x3'"
         self._engine.precision = {'fp32': 0, 'tf32': 1, 'bf16x3': 2}[prec]
         self._stats8 = torch.zeros(8, dtype=torch.float64, device=self._device)

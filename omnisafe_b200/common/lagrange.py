@@ -24,14 +24,25 @@ class Lagrange:
         # state = {lambda, adam m, adam v, adam t}
         self.state = torch.tensor([init_value, 0.0, 0.0, 0.0], dtype=torch.float32, device=device)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._jc_sums = None
 
     @property
     def lagrangian_multiplier(self) -> torch.Tensor:
         return self.state[0]
 
-    def update_lagrange_multiplier(self, window_sums: torch.Tensor) -> None:
-        """`window_sums` = device fp64 {sum EpRet, sum EpCost, sum EpLen, count} of the episode
-        window (already all-reduced): Jc = sum EpCost / count (common/lagrange.py:L114-136)."""
+    def update_lagrange_multiplier(self, Jc) -> None:   # noqa: N803  (the reference's argument name)
+        """Reference signature `update_lagrange_multiplier(Jc: float)` (common/lagrange.py:L114-136): Adam step on
+        lambda with gradient -(Jc - cost_limit), then projection onto [0, upper_bound].
+
+        Overload (the training loop's fast path, no host synchronisation): a device fp64 tensor
+        {sum EpRet, sum EpCost, sum EpLen, count} of the (already all-reduced) episode window, Jc = sum EpCost / count."""
+        if not isinstance(Jc, torch.Tensor):
+            if self._jc_sums is None:
+                self._jc_sums = torch.zeros(4, dtype=torch.float64, device=self.state.device)
+            self._jc_sums[1] = float(Jc)       # a NaN Jc raises the same assertion as the reference (ppo_lag.py:L74) via nan_flag
+            self._jc_sums[3] = 1.0
+            Jc = self._jc_sums
+        assert Jc.dtype == torch.float64 and Jc.numel() >= 4, 'device fast path: fp64 {sum EpRet, sum EpCost, sum EpLen, count}'
         ub = -1.0 if self.lagrangian_upper_bound is None else float(self.lagrangian_upper_bound)
-        lib().osb_lagrange_update(ptr(window_sums), self.cost_limit, self.lambda_lr, ub,
+        lib().osb_lagrange_update(ptr(Jc), self.cost_limit, self.lambda_lr, ub,
                                   ptr(self.state), ptr(self.nan_flag), current_stream())
