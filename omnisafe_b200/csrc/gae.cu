@@ -17,7 +17,9 @@
 // (separately rounded fp64 mul/add) from the exact carry-in.  Tiles of 128 steps are walked from
 // the end of the horizon to its start with a per-env carry.
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace osb {
 
@@ -282,6 +284,240 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
     }
 }
 
+
+// =====================================================================================================
+// Streaming variant of the training instantiation ('gae', no discounted_ret): the hot path of
+// VectorOnPolicyBuffer.finish_path (onpolicy_buffer.py:L148-203, L299-303; utils/math.py:L59-82).
+//
+// One CTA owns 32 envs (one full 128 B line per slab row) and walks the horizon backwards in tiles of 128
+// steps.  A producer warp streams the five input planes of a tile (reward, cost, value_r, value_c, flags)
+// into shared memory with TMA (cp.async.bulk.tensor.2d, one box per plane, completion on an mbarrier),
+// two stages deep, so the next tile is in flight while the current one is scanned.  16 consumer warps own
+// 8 consecutive steps each (lanes = envs: every shared-memory and global access is a full line, no
+// transposes): pass 1 forms the fp32 deltas with the reference's three roundings and folds the chunk into
+// an affine map, one named barrier publishes the 16 maps, every warp composes the maps of the later chunks
+// into its carry-in (<= 15 fp64 FMAs), pass 2 replays the reference's separately rounded fp64 recurrence
+// from that carry and stores the four output rows straight from registers (coalesced 128 B stores).
+// Bootstrap values of cut paths (sparse) are fetched one tile ahead.  Per tile: one barrier among the
+// consumers; stage hand-over through full / empty mbarriers.
+constexpr int SW = 16;                                  // consumer warps = time chunks per tile
+constexpr int SL = 8;                                   // steps per chunk
+constexpr int ST = SW * SL;                             // 128 steps per tile
+constexpr int SE = 32;                                  // envs per CTA
+constexpr int STHREADS = (SW + 1) * 32;                 // + producer warp
+constexpr uint32_t S_PLANE = ST * SE * 4;               // reward / cost plane of a tile
+constexpr uint32_t S_PLANE_V = (ST + 1) * SE * 4;       // value planes carry one more row: V_{t+1} of the tile's last step
+constexpr uint32_t S_FLAGS = ST * SE;
+constexpr uint32_t S_OFF_REW = 0, S_OFF_COST = S_PLANE, S_OFF_VR = 2 * S_PLANE, S_OFF_VC = 2 * S_PLANE + S_PLANE_V,
+                   S_OFF_FL = 2 * S_PLANE + 2 * S_PLANE_V, S_STAGE = S_OFF_FL + S_FLAGS;            // 69 888 B
+constexpr uint32_t S_OFF_MAPS = 2 * S_STAGE;                                 // double [2][SW][2][32]
+constexpr uint32_t S_OFF_ENDS = S_OFF_MAPS + 2 * SW * 2 * 32 * 8;            // uint32 [2][SW][32]
+constexpr uint32_t S_OFF_CARRY = S_OFF_ENDS + 2 * SW * 32 * 4;               // double [2][2][32]
+constexpr uint32_t S_OFF_RED = S_OFF_CARRY + 2 * 2 * 32 * 8;                 // double [3][SW]
+constexpr uint32_t S_OFF_BARS = S_OFF_RED + 3 * SW * 8;                      // full[2], empty[2]
+constexpr uint32_t S_SMEM = S_OFF_BARS + 4 * 8 + 16;
+
+struct GaeMaps { CUtensorMap rew, cost, val_r, val_c, flags; };
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void s_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void s_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool s_mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one box of a [T][N] plane -> shared memory; coordinates (env, step) may lie outside the tensor (zero fill)
+__device__ __forceinline__ void s_tma_load(uint32_t dst, const CUtensorMap* tm, int env0, int t0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(env0), "r"(t0), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_constant__ GaeMaps tm, GaeArgs p, double gl8_r, double gl8_c) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    const uint32_t pad = (128u - (s_u32(s_raw) & 127u)) & 127u;
+    uint8_t* sm = s_raw + pad;
+    const uint32_t sb = s_u32(sm);
+    double* sMaps = reinterpret_cast<double*>(sm + S_OFF_MAPS);
+    uint32_t* sEnds = reinterpret_cast<uint32_t*>(sm + S_OFF_ENDS);
+    double* sCarry = reinterpret_cast<double*>(sm + S_OFF_CARRY);
+    double* sRed = reinterpret_cast<double*>(sm + S_OFF_RED);
+    __shared__ int s_last;
+    const uint32_t bars = sb + S_OFF_BARS;
+    auto full = [&](int s) { return bars + (uint32_t)s * 8u; };
+    auto empty = [&](int s) { return bars + 16u + (uint32_t)s * 8u; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N, T = p.T;
+    const int env0 = blockIdx.x * SE, env = env0 + lane;
+    const bool env_ok = env < N;
+    const int ntiles = (T + ST - 1) / ST;
+
+    if (tid == 0) {
+        s_mbar_init(full(0), 1u); s_mbar_init(full(1), 1u);
+        s_mbar_init(empty(0), (uint32_t)SW); s_mbar_init(empty(1), (uint32_t)SW);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < 2 * 2 * 32) sCarry[tid] = 0.0;
+    __syncthreads();
+
+    double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
+    if (warp == SW) {
+        // ============================ producer: one lane feeds the two stages ================================
+        if (lane == 0) {
+            for (int k = 0; k < ntiles; ++k) {
+                const int s = k & 1;
+                if (k >= 2) s_mbar_wait(empty(s), (uint32_t)(((k >> 1) & 1) ^ 1));
+                const int t0 = T - (k + 1) * ST;
+                const uint32_t dst = sb + (uint32_t)s * S_STAGE;
+                s_mbar_expect_tx(full(s), S_STAGE);
+                s_tma_load(dst + S_OFF_REW, &tm.rew, env0, t0, full(s));
+                s_tma_load(dst + S_OFF_COST, &tm.cost, env0, t0, full(s));
+                s_tma_load(dst + S_OFF_VR, &tm.val_r, env0, t0, full(s));
+                s_tma_load(dst + S_OFF_VC, &tm.val_c, env0, t0, full(s));
+                s_tma_load(dst + S_OFF_FL, &tm.flags, env0, t0, full(s));
+            }
+        }
+    } else {
+        // ============================ consumers: warp = 8 consecutive steps, lane = env ======================
+        const int row0 = warp * SL;
+        float bootr[SL], bootc[SL];
+        // bootstrap values of the paths cut inside my chunk of tile k (sparse: only truncated / epoch-end steps)
+        auto fetch_boot = [&](int k) {
+            const uint8_t* fl = sm + (uint32_t)(k & 1) * S_STAGE + S_OFF_FL;
+            const int t0 = T - (k + 1) * ST;
+#pragma unroll
+            for (int i = 0; i < SL; ++i) {
+                const int t = t0 + row0 + i;
+                const unsigned f = fl[(row0 + i) * SE + lane];
+                const bool need = env_ok && t >= 0 && (f != 0u || t == T - 1) && !(f & OSB_FLAG_TERMINATED);
+                const size_t idx = (size_t)(need ? t : 0) * N + (need ? env : 0);
+                bootr[i] = need ? __ldg(p.boot_r + idx) : 0.f;
+                bootc[i] = need ? __ldg(p.boot_c + idx) : 0.f;
+            }
+        };
+        s_mbar_wait(full(0), 0u);
+        fetch_boot(0);
+#pragma unroll 1
+        for (int k = 0; k < ntiles; ++k) {
+            const int s = k & 1;
+            const int t0 = T - (k + 1) * ST;
+            const uint8_t* stg = sm + (uint32_t)s * S_STAGE;
+            const float* sRew = reinterpret_cast<const float*>(stg + S_OFF_REW);
+            const float* sCost = reinterpret_cast<const float*>(stg + S_OFF_COST);
+            const float* sVr = reinterpret_cast<const float*>(stg + S_OFF_VR);
+            const float* sVc = reinterpret_cast<const float*>(stg + S_OFF_VC);
+            const uint8_t* sFl = stg + S_OFF_FL;
+            // ---- pass 1: fp32 deltas (three separately rounded ops, onpolicy_buffer.py:L301) + chunk map ----
+            float dr[SL], dc[SL];
+            unsigned endmask = 0u;
+            double br = 0.0, bc = 0.0;
+            float nvr = sVr[(row0 + SL) * SE + lane], nvc = sVc[(row0 + SL) * SE + lane];
+#pragma unroll
+            for (int i = SL - 1; i >= 0; --i) {
+                const int row = row0 + i, t = t0 + row;
+                const float r = sRew[row * SE + lane], c = sCost[row * SE + lane];
+                const float vr = sVr[row * SE + lane], vc = sVc[row * SE + lane];
+                const unsigned f = sFl[row * SE + lane];
+                const bool valid = env_ok && t >= 0;
+                const bool end = valid && (f != 0u || t == T - 1);
+                float nr = nvr, nc = nvc;
+                if (end) { nr = bootr[i]; nc = bootc[i]; }           // 0 for terminated paths (fetch_boot)
+                const float rp = __fadd_rn(r, -__fmul_rn(p.pen, c));
+                dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -vr);
+                dc[i] = __fadd_rn(__fadd_rn(c, __fmul_rn(p.gamma_f, nc)), -vc);
+                if (end) { endmask |= 1u << i; br = (double)dr[i]; bc = (double)dc[i]; }
+                else if (valid) { br = (double)dr[i] + p.gl_r * br; bc = (double)dc[i] + p.gl_c * bc; }
+                nvr = vr; nvc = vc;
+            }
+            {
+                double* m = sMaps + ((size_t)(s * SW + warp) * 2) * 32;
+                m[lane] = br; m[32 + lane] = bc;
+                sEnds[(s * SW + warp) * 32 + lane] = endmask;
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(SW * 32) : "memory");
+            // ---- bootstrap values of the next tile, if it has landed already (else after pass 2) -------------
+            const bool more = k + 1 < ntiles;
+            bool fetched = false;
+            if (more && s_mbar_test(full(s ^ 1), (uint32_t)(((k + 1) >> 1) & 1))) { fetch_boot(k + 1); fetched = true; }
+            // ---- carry-in: compose the maps of the later chunks of this tile onto the tile carry -------------
+            double Ar = sCarry[((s ^ 1) * 2 + 0) * 32 + lane], Ac = sCarry[((s ^ 1) * 2 + 1) * 32 + lane];
+#pragma unroll 1
+            for (int w2 = SW - 1; w2 > warp; --w2) {
+                const double* m = sMaps + ((size_t)(s * SW + w2) * 2) * 32;
+                const bool e = sEnds[(s * SW + w2) * 32 + lane] != 0u;
+                Ar = e ? m[lane] : m[lane] + gl8_r * Ar;
+                Ac = e ? m[32 + lane] : m[32 + lane] + gl8_c * Ac;
+            }
+            // ---- pass 2: the reference's sequential fp64 recurrence (utils/math.py:L77) from the carry-in -----
+#pragma unroll
+            for (int i = SL - 1; i >= 0; --i) {
+                const int row = row0 + i, t = t0 + row;
+                if (env_ok && t >= 0) {
+                    if ((endmask >> i) & 1u) { Ar = (double)dr[i]; Ac = (double)dc[i]; }
+                    else {
+                        Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
+                        Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
+                    }
+                    const float vr = sVr[row * SE + lane], vc = sVc[row * SE + lane];
+                    const size_t idx = (size_t)t * N + env;
+                    const float o_ar = (float)Ar, o_ac = (float)Ac;
+                    p.adv_r[idx] = o_ar;
+                    p.adv_c[idx] = o_ac;
+                    p.tv_r[idx] = (float)(Ar + (double)vr);
+                    p.tv_c[idx] = (float)(Ac + (double)vc);
+                    st_r += (double)o_ar; st_r2 += (double)o_ar * (double)o_ar; st_c += (double)o_ac;
+                }
+            }
+            if (warp == 0) { sCarry[(s * 2 + 0) * 32 + lane] = Ar; sCarry[(s * 2 + 1) * 32 + lane] = Ac; }
+            __syncwarp();
+            if (lane == 0) s_mbar_arrive(empty(s));                   // this warp is done with the stage
+            if (more && !fetched) { s_mbar_wait(full(s ^ 1), (uint32_t)(((k + 1) >> 1) & 1)); fetch_boot(k + 1); }
+        }
+        st_r = warp_sum(st_r); st_r2 = warp_sum(st_r2); st_c = warp_sum(st_c);
+        if (lane == 0) { sRed[warp] = st_r; sRed[SW + warp] = st_r2; sRed[2 * SW + warp] = st_c; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < SW; ++w) { a += sRed[w]; b += sRed[SW + w]; c += sRed[2 * SW + w]; }
+        double* o = p.partials + (size_t)blockIdx.x * 4;
+        o[0] = a; o[1] = b; o[2] = c;
+        o[3] = (double)min(SE, N - env0) * (double)T;
+        __threadfence();
+        s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        double acc[4] = {0, 0, 0, 0};
+        for (int bb = tid; bb < (int)gridDim.x; bb += 32)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += __ldcg(p.partials + (size_t)bb * 4 + q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+        if (tid == 0) {
+            for (int q = 0; q < 4; ++q) p.sums[q] = acc[q];
+            *p.ticket = 0u;
+        }
+    }
+}
+
 // sums[4] = {sum adv_r, sum adv_r^2, sum adv_c, count}; one warp, fixed order.
 __global__ void gae_stats_reduce_kernel(const double* __restrict__ partials, int nblocks,
                                         double* __restrict__ sums) {
@@ -360,6 +596,62 @@ __global__ void discount_cumsum_kernel(const TIn* __restrict__ x, int rows, int 
 
 using namespace osb;
 
+// ---- tensor maps of the streaming kernel (driver entry point through the runtime: no -lcuda) ------------
+typedef CUresult (*osb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static osb_encode_tiled_fn osb_encode_tiled() {
+    static osb_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<osb_encode_tiled_fn>(f);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+// [T][N] plane -> 2-D map (dim 0 = env, dim 1 = step), box = 32 envs x `rows` steps
+static bool osb_plane_map(CUtensorMap* m, const void* base, int T, int N, int elem, int rows) {
+    osb_encode_tiled_fn enc = osb_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * (cuuint64_t)elem};
+    const cuuint32_t box[2] = {(cuuint32_t)SE, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2u, const_cast<void*>(base), dims,
+               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// returns 0 when launched, 1 when the shape / alignment / driver does not allow the TMA path (caller falls back)
+static int osb_gae_stream_launch(const GaeArgs& a, cudaStream_t s) {
+    static const bool legacy = getenv("OSB_GAE_LEGACY") != nullptr;
+    if (legacy || (a.N & 15) != 0) return 1;                      // row strides of the u8 plane must be 16 B multiples
+    const uintptr_t al = (uintptr_t)a.rew | (uintptr_t)a.cost | (uintptr_t)a.val_r | (uintptr_t)a.val_c | (uintptr_t)a.flags;
+    if (al & 15u) return 1;
+    struct Key { const void* p[5]; int T, N; };
+    static Key key = {};
+    static GaeMaps maps;
+    static bool have = false, attr = false;
+    const Key now = {{a.rew, a.cost, a.val_r, a.val_c, a.flags}, a.T, a.N};
+    if (!have || memcmp(&key, &now, sizeof(Key)) != 0) {
+        if (!osb_plane_map(&maps.rew, a.rew, a.T, a.N, 4, ST) || !osb_plane_map(&maps.cost, a.cost, a.T, a.N, 4, ST) ||
+            !osb_plane_map(&maps.val_r, a.val_r, a.T, a.N, 4, ST + 1) || !osb_plane_map(&maps.val_c, a.val_c, a.T, a.N, 4, ST + 1) ||
+            !osb_plane_map(&maps.flags, a.flags, a.T, a.N, 1, ST)) { have = false; return 1; }
+        key = now; have = true;
+    }
+    if (!attr) {
+        if (cudaFuncSetAttribute(gae_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+        attr = true;
+    }
+    double g8r = 1.0, g8c = 1.0;
+    for (int i = 0; i < SL; ++i) { g8r *= a.gl_r; g8c *= a.gl_c; }
+    gae_stream_kernel<<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    return 0;
+}
+
 extern "C" {
 
 // partials [blocks][4] + one 8-byte ticket slot (zero-initialised by the caller, self-resetting)
@@ -406,10 +698,9 @@ int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, co
         gae_dual_kernel<true, 0, true><<<nblocks, blk, 0, s>>>(a);
     } else if (ret) {
         gae_dual_kernel<false, 0, true><<<nblocks, blk, 0, s>>>(a);
-    } else {
-        // training path (no discounted_ret slab): two scans instead of three.  A segment-sequential variant
-        // (32-env warps, 16-step segments composed through shared memory) was measured slower at every
-        // horizon (12.7 vs 11.5 us at T=128, 1.4 vs 2.8 TB/s at T=2048): too few warps, too long chains.
+    } else if (osb_gae_stream_launch(a, s) != 0) {
+        // training path (no discounted_ret slab) when the TMA streaming kernel cannot take the shape (N % 16 != 0,
+        // unaligned slabs) or OSB_GAE_LEGACY is set: the two-scan instantiation of the generic kernel
         gae_dual_kernel<false, 0, false><<<nblocks, blk, 0, s>>>(a);
     }
     OSB_LAUNCH_CHECK();
