@@ -52,6 +52,7 @@ struct GaeArgs {
     double g;         // gamma            (discounted return)
     double gl_r;      // gamma * lam      (python double product)
     double gl_c;      // gamma * lam_c
+    long long* dbg;   // optional clock64 stamps of CTA 0 (tools/gae_stage_times.py), normally null
 };
 
 struct GaeTile {      // one thread's 4 steps (+ the value after them) of one env
@@ -290,32 +291,35 @@ __global__ void __launch_bounds__(GTHREADS, (MULTI || EST == 1 || EST == 3) ? 1 
 // VectorOnPolicyBuffer.finish_path (onpolicy_buffer.py:L148-203, L299-303; utils/math.py:L59-82).
 //
 // One CTA owns 32 envs (one full 128 B line per slab row) and walks the horizon backwards in tiles of 128
-// steps.  A producer warp streams the five input planes of a tile (reward, cost, value_r, value_c, flags)
-// into shared memory with TMA (cp.async.bulk.tensor.2d, one box per plane, completion on an mbarrier),
-// two stages deep, so the next tile is in flight while the current one is scanned.  16 consumer warps own
-// 8 consecutive steps each (lanes = envs: every shared-memory and global access is a full line, no
+// steps.  The five input planes of a tile (reward, cost, value_r, value_c, flags) are streamed into shared
+// memory with TMA (cp.async.bulk.tensor.2d, one box per plane, completion on mbarriers), two stages deep and
+// in two halves: A = reward / cost / flags (free again after pass 1), B = the value planes (read until the end
+// of pass 2); one elected thread refills the free halves right after the tile's only block barrier, which
+// proves that every warp is done with them -- no empty barriers, no producer warp.  16 warps own 8
+// consecutive steps each (lanes = envs: every shared-memory and global access is a full line, no
 // transposes): pass 1 forms the fp32 deltas with the reference's three roundings and folds the chunk into
-// an affine map, one named barrier publishes the 16 maps, every warp composes the maps of the later chunks
-// into its carry-in (<= 15 fp64 FMAs), pass 2 replays the reference's separately rounded fp64 recurrence
-// from that carry and stores the four output rows straight from registers (coalesced 128 B stores).
-// Bootstrap values of cut paths (sparse) are fetched one tile ahead.  Per tile: one barrier among the
-// consumers; stage hand-over through full / empty mbarriers.
-constexpr int SW = 16;                                  // consumer warps = time chunks per tile
+// an affine map (a, b), the barrier publishes the 16 maps, every warp composes the maps of the later chunks
+// onto the tile carry (<= 15 fp64 FMAs), pass 2 replays the reference's separately rounded fp64 recurrence
+// from that carry-in and stores the four output rows straight from registers (coalesced 128 B stores).
+// Path ends and the bootstrap values of cut paths (sparse) are fetched one tile ahead.
+// Measured on B200 (tools/gae_times.py): 4.1-4.2 TB/s of algorithmic traffic at T = 2048 x 4096 envs
+// (277 MB, larger than L2), 4.4-4.6 TB/s at T = 4096; the generic kernel above: 2.8 TB/s.
+constexpr int SW = 16;                                  // warps = time chunks per tile
 constexpr int SL = 8;                                   // steps per chunk
 constexpr int ST = SW * SL;                             // 128 steps per tile
 constexpr int SE = 32;                                  // envs per CTA
-constexpr int STHREADS = (SW + 1) * 32;                 // + producer warp
+constexpr int STHREADS = SW * 32;
 constexpr uint32_t S_PLANE = ST * SE * 4;               // reward / cost plane of a tile
 constexpr uint32_t S_PLANE_V = (ST + 1) * SE * 4;       // value planes carry one more row: V_{t+1} of the tile's last step
 constexpr uint32_t S_FLAGS = ST * SE;
 constexpr uint32_t S_OFF_REW = 0, S_OFF_COST = S_PLANE, S_OFF_VR = 2 * S_PLANE, S_OFF_VC = 2 * S_PLANE + S_PLANE_V,
                    S_OFF_FL = 2 * S_PLANE + 2 * S_PLANE_V, S_STAGE = S_OFF_FL + S_FLAGS;            // 69 888 B
-constexpr uint32_t S_OFF_MAPS = 2 * S_STAGE;                                 // double [2][SW][2][32]
-constexpr uint32_t S_OFF_ENDS = S_OFF_MAPS + 2 * SW * 2 * 32 * 8;            // uint32 [2][SW][32]
-constexpr uint32_t S_OFF_CARRY = S_OFF_ENDS + 2 * SW * 32 * 4;               // double [2][2][32]
+constexpr int NSTG = 2;                                  // stages of the input pipeline (three stages measured no faster)
+constexpr uint32_t S_OFF_MAPS = NSTG * S_STAGE;                                 // double [2][SW][4][32]: (a_r, b_r, a_c, b_c) per chunk
+constexpr uint32_t S_OFF_CARRY = S_OFF_MAPS + 2 * SW * 4 * 32 * 8;           // double [2][2][32]
 constexpr uint32_t S_OFF_RED = S_OFF_CARRY + 2 * 2 * 32 * 8;                 // double [3][SW]
-constexpr uint32_t S_OFF_BARS = S_OFF_RED + 3 * SW * 8;                      // full[2], empty[2]
-constexpr uint32_t S_SMEM = S_OFF_BARS + 4 * 8 + 16;
+constexpr uint32_t S_OFF_BARS = S_OFF_RED + 3 * SW * 8;                      // fullA[2] (reward, cost, flags), fullB[2] (values)
+constexpr uint32_t S_SMEM = S_OFF_BARS + 2 * NSTG * 8 + 16;
 
 struct GaeMaps { CUtensorMap rew, cost, val_r, val_c, flags; };
 
@@ -348,146 +352,237 @@ __device__ __forceinline__ void s_tma_load(uint32_t dst, const CUtensorMap* tm, 
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(env0), "r"(t0), "r"(bar) : "memory");
 }
 
+// 16 bytes global -> shared, asynchronously (LDGSTS); src_bytes == 0 zero-fills (rows / envs outside the slab)
+__device__ __forceinline__ void s_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's earlier cp.async copies arrive on the mbarrier when they have landed (counted in the barrier's expected arrivals)
+__device__ __forceinline__ void s_cp_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+// TMA = false (OSB_GAE_LDGSTS=1): every thread copies 16-byte pieces of the tile with cp.async (LDGSTS) -- ~9 copies per thread
+//   and tile, each thread's batch arriving on the stage's mbarrier.
+// TMA = true (default): one elected thread issues cp.async.bulk.tensor.2d boxes {32 envs x 128 (129) steps}.
+//   Measured on B200: boxes with 128-byte rows 4N bytes apart stream at only ~21 GB/s per SM (one row request per
+//   ~10 cycles, from DRAM and from L2 alike), capping the kernel at 2.7 TB/s with the arithmetic removed.
+template <bool TMA>
 __global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_constant__ GaeMaps tm, GaeArgs p, double gl8_r, double gl8_c) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     const uint32_t pad = (128u - (s_u32(s_raw) & 127u)) & 127u;
     uint8_t* sm = s_raw + pad;
     const uint32_t sb = s_u32(sm);
     double* sMaps = reinterpret_cast<double*>(sm + S_OFF_MAPS);
-    uint32_t* sEnds = reinterpret_cast<uint32_t*>(sm + S_OFF_ENDS);
     double* sCarry = reinterpret_cast<double*>(sm + S_OFF_CARRY);
     double* sRed = reinterpret_cast<double*>(sm + S_OFF_RED);
     __shared__ int s_last;
     const uint32_t bars = sb + S_OFF_BARS;
-    auto full = [&](int s) { return bars + (uint32_t)s * 8u; };
-    auto empty = [&](int s) { return bars + 16u + (uint32_t)s * 8u; };
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, T = p.T;
     const int env0 = blockIdx.x * SE, env = env0 + lane;
     const bool env_ok = env < N;
     const int ntiles = (T + ST - 1) / ST;
 
+    auto fullA = [&](int s) { return bars + (uint32_t)s * 8u; };
+    auto fullB = [&](int s) { return bars + (uint32_t)(NSTG + s) * 8u; };
+    // the two halves of a tile's load (one elected thread).  A = reward, cost, flags: dead after pass 1 of the tile that
+    // used the stage; B = the two value planes: read until the end of pass 2.
+    // one 16-byte piece c of a [rows][32 envs] float plane of tile k (8 pieces per row)
+    auto cp_f32 = [&](const float* plane, uint32_t dst, int t0, int c) {
+        const int row = c >> 3, part = c & 7, t = t0 + row, e = env0 + 4 * part;
+        const bool ok = t >= 0 && t < T && e < N;
+        s_cp16(dst + (uint32_t)c * 16u, plane + (ok ? (size_t)t * N + e : 0), ok ? 16u : 0u);
+    };
+    auto load_A = [&](int k) {
+        const int s = k % NSTG, t0 = T - (k + 1) * ST;
+        const uint32_t dst = sb + (uint32_t)s * S_STAGE;
+        if constexpr (TMA) {
+            if (tid == 0) {
+                s_mbar_expect_tx(fullA(s), 2 * S_PLANE + S_FLAGS);
+                s_tma_load(dst + S_OFF_REW, &tm.rew, env0, t0, fullA(s));
+                s_tma_load(dst + S_OFF_COST, &tm.cost, env0, t0, fullA(s));
+                s_tma_load(dst + S_OFF_FL, &tm.flags, env0, t0, fullA(s));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < ST * 8 / STHREADS; ++j) {
+                cp_f32(p.rew, dst + S_OFF_REW, t0, tid + j * STHREADS);
+                cp_f32(p.cost, dst + S_OFF_COST, t0, tid + j * STHREADS);
+            }
+            if (tid < ST * 2) {                                          // flags: 2 pieces of 16 envs per row
+                const int row = tid >> 1, part = tid & 1, t = t0 + row, e = env0 + 16 * part;
+                const bool ok = t >= 0 && e < N;
+                s_cp16(dst + S_OFF_FL + (uint32_t)tid * 16u, p.flags + (ok ? (size_t)t * N + e : 0), ok ? 16u : 0u);
+            }
+            s_cp_arrive(fullA(s));
+        }
+    };
+    auto load_B = [&](int k) {
+        const int s = k % NSTG, t0 = T - (k + 1) * ST;
+        const uint32_t dst = sb + (uint32_t)s * S_STAGE;
+        if constexpr (TMA) {
+            if (tid == 0) {
+                s_mbar_expect_tx(fullB(s), 2 * S_PLANE_V);
+                s_tma_load(dst + S_OFF_VR, &tm.val_r, env0, t0, fullB(s));
+                s_tma_load(dst + S_OFF_VC, &tm.val_c, env0, t0, fullB(s));
+            }
+        } else {
+            for (int c = tid; c < (ST + 1) * 8; c += STHREADS) {
+                cp_f32(p.val_r, dst + S_OFF_VR, t0, c);
+                cp_f32(p.val_c, dst + S_OFF_VC, t0, c);
+            }
+            s_cp_arrive(fullB(s));
+        }
+    };
     if (tid == 0) {
-        s_mbar_init(full(0), 1u); s_mbar_init(full(1), 1u);
-        s_mbar_init(empty(0), (uint32_t)SW); s_mbar_init(empty(1), (uint32_t)SW);
+        const uint32_t cnt = TMA ? 1u : (uint32_t)STHREADS;
+        for (int i = 0; i < NSTG; ++i) { s_mbar_init(fullA(i), cnt); s_mbar_init(fullB(i), cnt); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 2 * 2 * 32) sCarry[tid] = 0.0;
     __syncthreads();
+    for (int j = 0; j < NSTG && j < ntiles; ++j) { load_A(j); load_B(j); }
 
     double st_r = 0.0, st_r2 = 0.0, st_c = 0.0;
-    if (warp == SW) {
-        // ============================ producer: one lane feeds the two stages ================================
-        if (lane == 0) {
-            for (int k = 0; k < ntiles; ++k) {
-                const int s = k & 1;
-                if (k >= 2) s_mbar_wait(empty(s), (uint32_t)(((k >> 1) & 1) ^ 1));
-                const int t0 = T - (k + 1) * ST;
-                const uint32_t dst = sb + (uint32_t)s * S_STAGE;
-                s_mbar_expect_tx(full(s), S_STAGE);
-                s_tma_load(dst + S_OFF_REW, &tm.rew, env0, t0, full(s));
-                s_tma_load(dst + S_OFF_COST, &tm.cost, env0, t0, full(s));
-                s_tma_load(dst + S_OFF_VR, &tm.val_r, env0, t0, full(s));
-                s_tma_load(dst + S_OFF_VC, &tm.val_c, env0, t0, full(s));
-                s_tma_load(dst + S_OFF_FL, &tm.flags, env0, t0, full(s));
-            }
-        }
-    } else {
+    {
         // ============================ consumers: warp = 8 consecutive steps, lane = env ======================
         const int row0 = warp * SL;
+        const float gam = p.gamma_f, pen = p.pen;
+        const double glr = p.gl_r, glc = p.gl_c;
         float bootr[SL], bootc[SL];
-        // bootstrap values of the paths cut inside my chunk of tile k (sparse: only truncated / epoch-end steps)
+        unsigned endmask = 0u;       // bit i: step row0 + i ends a path (flag set or last step of the epoch)
+        // path ends of my chunk of tile k + the bootstrap values of the cut paths (sparse: only truncated / epoch-end
+        // steps need one; terminated paths bootstrap with 0)
         auto fetch_boot = [&](int k) {
-            const uint8_t* fl = sm + (uint32_t)(k & 1) * S_STAGE + S_OFF_FL;
-            const int t0 = T - (k + 1) * ST;
+            const uint8_t* fl = sm + (uint32_t)(k % NSTG) * S_STAGE + S_OFF_FL + row0 * SE + lane;
+            const int t0 = T - (k + 1) * ST + row0;
+            unsigned em = 0u, need = 0u;
 #pragma unroll
             for (int i = 0; i < SL; ++i) {
-                const int t = t0 + row0 + i;
-                const unsigned f = fl[(row0 + i) * SE + lane];
-                const bool need = env_ok && t >= 0 && (f != 0u || t == T - 1) && !(f & OSB_FLAG_TERMINATED);
-                const size_t idx = (size_t)(need ? t : 0) * N + (need ? env : 0);
-                bootr[i] = need ? __ldg(p.boot_r + idx) : 0.f;
-                bootc[i] = need ? __ldg(p.boot_c + idx) : 0.f;
+                const unsigned f = fl[i * SE];
+                const bool end = (f != 0u) || (t0 + i == T - 1);
+                em |= (end ? 1u : 0u) << i;
+                need |= ((end && !(f & OSB_FLAG_TERMINATED) && env_ok && t0 + i >= 0) ? 1u : 0u) << i;
+                bootr[i] = 0.f; bootc[i] = 0.f;
+            }
+            endmask = em;
+            if (__any_sync(0xffffffffu, need != 0u)) {
+#pragma unroll
+                for (int i = 0; i < SL; ++i) {
+                    if ((need >> i) & 1u) {
+                        const size_t idx = (size_t)(t0 + i) * N + env;
+                        bootr[i] = __ldg(p.boot_r + idx);
+                        bootc[i] = __ldg(p.boot_c + idx);
+                    }
+                }
             }
         };
-        s_mbar_wait(full(0), 0u);
+        const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == SW - 1);
+        int dbg_n = 0;
+        auto stamp = [&](int id) {
+            if (dbg_on && dbg_n < 250) {
+                long long* d = p.dbg + (warp == 0 ? 0 : 512);
+                d[1 + 2 * dbg_n] = id; d[2 + 2 * dbg_n] = clock64(); ++dbg_n; d[0] = dbg_n;
+            }
+        };
+        stamp(0);
+        s_mbar_wait(fullA(0), 0u);
+        stamp(1);
         fetch_boot(0);
 #pragma unroll 1
         for (int k = 0; k < ntiles; ++k) {
-            const int s = k & 1;
-            const int t0 = T - (k + 1) * ST;
-            const uint8_t* stg = sm + (uint32_t)s * S_STAGE;
-            const float* sRew = reinterpret_cast<const float*>(stg + S_OFF_REW);
-            const float* sCost = reinterpret_cast<const float*>(stg + S_OFF_COST);
-            const float* sVr = reinterpret_cast<const float*>(stg + S_OFF_VR);
-            const float* sVc = reinterpret_cast<const float*>(stg + S_OFF_VC);
-            const uint8_t* sFl = stg + S_OFF_FL;
+            stamp(2);
+            const int s = k & 1;                              // parity of the map / carry buffers
+            const int sg = k % NSTG, sgn = (k + 1) % NSTG;    // input stage of this tile / of the next one
+            const uint32_t phn = (uint32_t)(((k + 1) / NSTG) & 1);
+            const int t0 = T - (k + 1) * ST + row0;          // first step of my chunk (negative only in the last tile)
+            const uint8_t* stg = sm + (uint32_t)sg * S_STAGE;
+            const float* sRew = reinterpret_cast<const float*>(stg + S_OFF_REW) + row0 * SE + lane;
+            const float* sCost = reinterpret_cast<const float*>(stg + S_OFF_COST) + row0 * SE + lane;
+            const float* sVr = reinterpret_cast<const float*>(stg + S_OFF_VR) + row0 * SE + lane;
+            const float* sVc = reinterpret_cast<const float*>(stg + S_OFF_VC) + row0 * SE + lane;
+            const unsigned em = endmask;
+            s_mbar_wait(fullB(sg), (uint32_t)((k / NSTG) & 1));
+            stamp(8);
             // ---- pass 1: fp32 deltas (three separately rounded ops, onpolicy_buffer.py:L301) + chunk map ----
-            float dr[SL], dc[SL];
-            unsigned endmask = 0u;
+            // (rows with t < 0 of the last tile and lanes past N see TMA zero fill: they are computed and discarded)
+            double dr[SL], dc[SL];
+            {
+                // (a) the eight rows are independent: loads, fp32 arithmetic and conversions pipeline freely
+                float fr[SL], fc[SL];
+                float nvr = sVr[SL * SE], nvc = sVc[SL * SE];
+#pragma unroll
+                for (int i = SL - 1; i >= 0; --i) {
+                    const float r = sRew[i * SE], c = sCost[i * SE], vr = sVr[i * SE], vc = sVc[i * SE];
+                    const bool end = (em >> i) & 1u;
+                    const float nr = end ? bootr[i] : nvr, nc = end ? bootc[i] : nvc;
+                    const float rp = __fadd_rn(r, -__fmul_rn(pen, c));
+                    fr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(gam, nr)), -vr);
+                    fc[i] = __fadd_rn(__fadd_rn(c, __fmul_rn(gam, nc)), -vc);
+                    nvr = vr; nvc = vc;
+                }
+#pragma unroll
+                for (int i = 0; i < SL; ++i) { dr[i] = (double)fr[i]; dc[i] = (double)fc[i]; }
+            }
+            // (b) the chunk's affine map: the only sequential part of pass 1
             double br = 0.0, bc = 0.0;
-            float nvr = sVr[(row0 + SL) * SE + lane], nvc = sVc[(row0 + SL) * SE + lane];
 #pragma unroll
             for (int i = SL - 1; i >= 0; --i) {
-                const int row = row0 + i, t = t0 + row;
-                const float r = sRew[row * SE + lane], c = sCost[row * SE + lane];
-                const float vr = sVr[row * SE + lane], vc = sVc[row * SE + lane];
-                const unsigned f = sFl[row * SE + lane];
-                const bool valid = env_ok && t >= 0;
-                const bool end = valid && (f != 0u || t == T - 1);
-                float nr = nvr, nc = nvc;
-                if (end) { nr = bootr[i]; nc = bootc[i]; }           // 0 for terminated paths (fetch_boot)
-                const float rp = __fadd_rn(r, -__fmul_rn(p.pen, c));
-                dr[i] = __fadd_rn(__fadd_rn(rp, __fmul_rn(p.gamma_f, nr)), -vr);
-                dc[i] = __fadd_rn(__fadd_rn(c, __fmul_rn(p.gamma_f, nc)), -vc);
-                if (end) { endmask |= 1u << i; br = (double)dr[i]; bc = (double)dc[i]; }
-                else if (valid) { br = (double)dr[i] + p.gl_r * br; bc = (double)dc[i] + p.gl_c * bc; }
-                nvr = vr; nvc = vc;
+                const bool end = (em >> i) & 1u;
+                br = fma(glr, end ? 0.0 : br, dr[i]);
+                bc = fma(glc, end ? 0.0 : bc, dc[i]);
             }
             {
-                double* m = sMaps + ((size_t)(s * SW + warp) * 2) * 32;
-                m[lane] = br; m[32 + lane] = bc;
-                sEnds[(s * SW + warp) * 32 + lane] = endmask;
+                double* m = sMaps + ((size_t)(s * SW + warp) * 4) * 32 + lane;
+                m[0] = em ? 0.0 : gl8_r; m[32] = br; m[64] = em ? 0.0 : gl8_c; m[96] = bc;
             }
+            stamp(3);
             asm volatile("bar.sync 1, %0;\n" ::"n"(SW * 32) : "memory");
-            // ---- bootstrap values of the next tile, if it has landed already (else after pass 2) -------------
+            stamp(4);
+            // every warp is past pass 1 of this tile and past pass 2 of the previous one: the A half of this stage and
+            // the B half of the other stage are free -> refill them (tile k + 2 resp. k + 1; B of tile 1 went out at start)
+            if (k + NSTG < ntiles) load_A(k + NSTG);
+            if (k >= 1 && k + NSTG - 1 < ntiles) load_B(k + NSTG - 1);
+            // ---- path ends / bootstrap values of the next tile (its A half was requested a whole tile ago) ----------
             const bool more = k + 1 < ntiles;
             bool fetched = false;
-            if (more && s_mbar_test(full(s ^ 1), (uint32_t)(((k + 1) >> 1) & 1))) { fetch_boot(k + 1); fetched = true; }
+            if (more && s_mbar_test(fullA(sgn), phn)) { fetch_boot(k + 1); fetched = true; }
             // ---- carry-in: compose the maps of the later chunks of this tile onto the tile carry -------------
             double Ar = sCarry[((s ^ 1) * 2 + 0) * 32 + lane], Ac = sCarry[((s ^ 1) * 2 + 1) * 32 + lane];
-#pragma unroll 1
-            for (int w2 = SW - 1; w2 > warp; --w2) {
-                const double* m = sMaps + ((size_t)(s * SW + w2) * 2) * 32;
-                const bool e = sEnds[(s * SW + w2) * 32 + lane] != 0u;
-                Ar = e ? m[lane] : m[lane] + gl8_r * Ar;
-                Ac = e ? m[32 + lane] : m[32 + lane] + gl8_c * Ac;
+#pragma unroll
+            for (int w2 = SW - 1; w2 > 0; --w2) {
+                if (w2 > warp) {                                         // warp-uniform
+                    const double* m = sMaps + ((size_t)(s * SW + w2) * 4) * 32 + lane;
+                    Ar = fma(m[0], Ar, m[32]);
+                    Ac = fma(m[64], Ac, m[96]);
+                }
             }
+            stamp(5);
             // ---- pass 2: the reference's sequential fp64 recurrence (utils/math.py:L77) from the carry-in -----
+            const bool partial = t0 < 0;                                 // warp-uniform; only in the last tile
+            float* o_base = p.adv_r + (ptrdiff_t)t0 * N + env;           // never dereferenced where t < 0 / env >= N
+            const ptrdiff_t d_ac = p.adv_c - p.adv_r, d_tr = p.tv_r - p.adv_r, d_tc = p.tv_c - p.adv_r;
+            // A path end restarts the recurrence (x + d * 0 == x exactly).  Each row's roundings / stores sit in their own
+            // guarded block on purpose: bursts of 64-bit conversions (XU pipe) issued back to back throttle the shared
+            // memory / special-function queue (measured 6 % slower as straight-line code).  The statistics sum the fp64
+            // advantages before their rounding to fp32 (|difference| <= 2^-25 relative per element, random sign).
 #pragma unroll
             for (int i = SL - 1; i >= 0; --i) {
-                const int row = row0 + i, t = t0 + row;
-                if (env_ok && t >= 0) {
-                    if ((endmask >> i) & 1u) { Ar = (double)dr[i]; Ac = (double)dc[i]; }
-                    else {
-                        Ar = __dadd_rn((double)dr[i], __dmul_rn(p.gl_r, Ar));
-                        Ac = __dadd_rn((double)dc[i], __dmul_rn(p.gl_c, Ac));
+                const bool end = (em >> i) & 1u;
+                Ar = __dadd_rn(dr[i], __dmul_rn(glr, end ? 0.0 : Ar));
+                Ac = __dadd_rn(dc[i], __dmul_rn(glc, end ? 0.0 : Ac));
+                if (!partial || t0 + i >= 0) {
+                    if (env_ok) {
+                        float* o = o_base + (ptrdiff_t)i * N;
+                        o[0] = (float)Ar; o[d_ac] = (float)Ac;
+                        o[d_tr] = (float)(Ar + (double)sVr[i * SE]); o[d_tc] = (float)(Ac + (double)sVc[i * SE]);
                     }
-                    const float vr = sVr[row * SE + lane], vc = sVc[row * SE + lane];
-                    const size_t idx = (size_t)t * N + env;
-                    const float o_ar = (float)Ar, o_ac = (float)Ac;
-                    p.adv_r[idx] = o_ar;
-                    p.adv_c[idx] = o_ac;
-                    p.tv_r[idx] = (float)(Ar + (double)vr);
-                    p.tv_c[idx] = (float)(Ac + (double)vc);
-                    st_r += (double)o_ar; st_r2 += (double)o_ar * (double)o_ar; st_c += (double)o_ac;
+                    st_r += Ar; st_r2 = fma(Ar, Ar, st_r2); st_c += Ac;
                 }
             }
             if (warp == 0) { sCarry[(s * 2 + 0) * 32 + lane] = Ar; sCarry[(s * 2 + 1) * 32 + lane] = Ac; }
-            __syncwarp();
-            if (lane == 0) s_mbar_arrive(empty(s));                   // this warp is done with the stage
-            if (more && !fetched) { s_mbar_wait(full(s ^ 1), (uint32_t)(((k + 1) >> 1) & 1)); fetch_boot(k + 1); }
+            stamp(fetched ? 6 : 7);
+            if (more && !fetched) { s_mbar_wait(fullA(sgn), phn); fetch_boot(k + 1); }
         }
         st_r = warp_sum(st_r); st_r2 = warp_sum(st_r2); st_c = warp_sum(st_c);
         if (lane == 0) { sRed[warp] = st_r; sRed[SW + warp] = st_r2; sRed[2 * SW + warp] = st_c; }
@@ -631,30 +726,40 @@ static int osb_gae_stream_launch(const GaeArgs& a, cudaStream_t s) {
     if (legacy || (a.N & 15) != 0) return 1;                      // row strides of the u8 plane must be 16 B multiples
     const uintptr_t al = (uintptr_t)a.rew | (uintptr_t)a.cost | (uintptr_t)a.val_r | (uintptr_t)a.val_c | (uintptr_t)a.flags;
     if (al & 15u) return 1;
-    struct Key { const void* p[5]; int T, N; };
-    static Key key = {};
-    static GaeMaps maps;
-    static bool have = false, attr = false;
-    const Key now = {{a.rew, a.cost, a.val_r, a.val_c, a.flags}, a.T, a.N};
-    if (!have || memcmp(&key, &now, sizeof(Key)) != 0) {
-        if (!osb_plane_map(&maps.rew, a.rew, a.T, a.N, 4, ST) || !osb_plane_map(&maps.cost, a.cost, a.T, a.N, 4, ST) ||
-            !osb_plane_map(&maps.val_r, a.val_r, a.T, a.N, 4, ST + 1) || !osb_plane_map(&maps.val_c, a.val_c, a.T, a.N, 4, ST + 1) ||
-            !osb_plane_map(&maps.flags, a.flags, a.T, a.N, 1, ST)) { have = false; return 1; }
-        key = now; have = true;
+    static const bool use_tma = getenv("OSB_GAE_LDGSTS") == nullptr;
+    static GaeMaps maps = {};
+    if (use_tma) {
+        struct Key { const void* p[5]; int T, N; };
+        static Key key = {};
+        static bool have = false;
+        const Key now = {{a.rew, a.cost, a.val_r, a.val_c, a.flags}, a.T, a.N};
+        if (!have || memcmp(&key, &now, sizeof(Key)) != 0) {
+            if (!osb_plane_map(&maps.rew, a.rew, a.T, a.N, 4, ST) || !osb_plane_map(&maps.cost, a.cost, a.T, a.N, 4, ST) ||
+                !osb_plane_map(&maps.val_r, a.val_r, a.T, a.N, 4, ST + 1) || !osb_plane_map(&maps.val_c, a.val_c, a.T, a.N, 4, ST + 1) ||
+                !osb_plane_map(&maps.flags, a.flags, a.T, a.N, 1, ST)) { have = false; return 1; }
+            key = now; have = true;
+        }
     }
+    static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(gae_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+        if (cudaFuncSetAttribute(gae_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess ||
+            cudaFuncSetAttribute(gae_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
         attr = true;
     }
     double g8r = 1.0, g8c = 1.0;
     for (int i = 0; i < SL; ++i) { g8r *= a.gl_r; g8c *= a.gl_c; }
-    gae_stream_kernel<<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    if (use_tma) gae_stream_kernel<true><<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    else gae_stream_kernel<false><<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
     return 0;
 }
 
 extern "C" {
 
 // partials [blocks][4] + one 8-byte ticket slot (zero-initialised by the caller, self-resetting)
+static long long* g_gae_dbg = nullptr;
+// development aid: clock64 stamps of CTA 0 of the next streaming-GAE launches go to buf (1024 long long), NULL turns it off
+int osb_gae_debug_buffer(long long* buf) { g_gae_dbg = buf; return OSB_OK; }
+
 int osb_gae_workspace_doubles(int n_envs) { return ((n_envs + GE - 1) / GE) * 4 + 8; }
 
 int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, const float* val_c,
@@ -676,6 +781,7 @@ int osb_adv_estimate(const float* rew, const float* cost, const float* val_r, co
     a.T = T; a.N = N;
     a.gamma_f = (float)gamma; a.pen = (float)penalty_coef;
     a.g = gamma; a.gl_r = gamma * lam; a.gl_c = gamma * lam_c;
+    a.dbg = g_gae_dbg;
     const int nblocks = (N + GE - 1) / GE;
     a.sums = sums;
     a.ticket = reinterpret_cast<unsigned int*>(workspace + (size_t)nblocks * 4 + 1);
