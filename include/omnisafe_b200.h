@@ -337,6 +337,8 @@ int osb_x3_selftest(const float* A, const float* B, int M, int N, int K, int a_m
 int osb_x3_debug_buffer(long long* buf);
 /* development aid: clock64 stamps of CTA 0 of the streaming GAE kernel (tools/gae_stage_times.py); NULL turns it off */
 int osb_gae_debug_buffer(long long* buf);
+/* same for the persistent rollout kernel (tools/rollout_stage_times.py) */
+int osb_rollout_debug_buffer(long long* buf);
 int osb_x3_selftest_dbg(const float* A, const float* B, int M, int N, int K, int a_mn, int b_mn, int a_sw,
                         int b_sw, int b_ones, int a_lbo, int a_sbo, int b_lbo, int b_sbo, float* out, void* stream);
 int osb_x3_timing(int M, int N, int reps, int style, long long* out, void* stream);

@@ -14,6 +14,7 @@
 // ObsNormalize reduction is done with order-independent fixed-point atomics and finalised by the
 // last actor CTA of the launch; the next launch (= kernel boundary = grid sync) consumes it.
 #include "common.cuh"
+#include <stdlib.h>
 #include "mlp.cuh"
 #include "umma.cuh"
 #include "x3.cuh"
@@ -110,9 +111,9 @@ __device__ __forceinline__ float norm_std(float sumsq, long long count) {
 __device__ void norm_finalize(const NormState& ns, int O, long long n_all) {
     __threadfence();
     const int nfin = *((volatile int*)ns.fin_count);
-    long long count = ns.count[0];
+    long long count = __ldcg(ns.count);          // (.cg: in the persistent kernel another SM may have written these last step)
     for (int j = threadIdx.x; j < O; j += blockDim.x) {
-        float mean = ns.mean[j], sumsq = ns.sumsq[j];
+        float mean = __ldcg(ns.mean + j), sumsq = __ldcg(ns.sumsq + j);
         long long c = count;
         if (nfin > 0) {
             norm_push(mean, sumsq, c, nfin, __ldcg(ns.acc_fin + j), __ldcg(ns.acc_fin + O + j));
@@ -138,7 +139,9 @@ __device__ void norm_finalize(const NormState& ns, int O, long long n_all) {
     }
 }
 
-__device__ __forceinline__ long long to_fix(float x) { return __double2ll_rn((double)x * FIX_SCALE); }
+// x * 2^36 rounded to the nearest integer.  The scaling by a power of two is exact in fp32 as well (|x| <= 10 by the env
+// spec), so one fp32 -> int64 conversion gives the same integer as the fp64 product did.
+__device__ __forceinline__ long long to_fix(float x) { return __float2ll_rn(x * 68719476736.0f); }
 
 // ---------------------------------------------------------------------------------------------
 // reset of all envs (OnPolicyAdapter.rollout resets every epoch: onpolicy_adapter.py:L80) and the
@@ -220,6 +223,24 @@ __device__ float philox_normal(uint32_t seed, uint32_t gid, uint32_t step, int a
     return (a & 1) ? r * sn : r * cs;
 }
 
+// both normals of action pair pr (actions 2 pr, 2 pr + 1): same values as philox_normal(seed, gid, step, 2 pr [+ 1])
+__device__ void philox_normal2(uint32_t seed, uint32_t gid, uint32_t step, int pr, float& n0, float& n1) {
+    uint32_t c[4] = {gid, step, (uint32_t)(pr >> 1), 0x0B200u};
+    uint32_t k0 = seed, k1 = 0xCAFEF00Du;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const int pair = pr & 1;
+    const float u0 = ((float)(c[2 * pair] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u1 = ((float)(c[2 * pair + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u0));
+    float sn, cs;
+    sincosf(6.283185307179586f * u1, &sn, &cs);
+    n0 = r * cs; n1 = r * sn;
+}
+
 struct StepArgs {
     EnvSpec es;
     EnvState st;
@@ -232,6 +253,9 @@ struct StepArgs {
     int t, T, N;
     int is_tail;          // t == T: critics only (epoch-end bootstrap)
     int precision;        // 0 = fp32 FMA tiles of 32 envs, 1 = tcgen05 TF32 tiles of 128 envs, 2 = split-bf16 tcgen05 tiles (O <= 64)
+    unsigned int* bar_ctr;    // persistent epoch kernel: grid-barrier arrival counter and release flag (zero at launch)
+    unsigned int* bar_flag;
+    long long* dbg;           // optional clock64 stamps (persistent kernel), normally null
 };
 
 // normalise (or copy) a tile of raw observations into sX (chunk kc), zero padded.
@@ -504,7 +528,12 @@ constexpr int SNW = KC + 1;   // row stride of the next-state staging tiles
 constexpr uint32_t RX_SUB = RTC * 128, RX_WSUB = 64 * 128, RX_W3SUB = 16 * 128;
 constexpr uint32_t RTC_FOFF_TF32 = 2 * RTC * 256 + 2 * 16384 + 4096, RTC_FOFF_X3 = 3 * RX_SUB + 6 * RX_WSUB + 3 * RX_W3SUB;
 
-template <bool X3>
+// PERSIST = true: ONE cooperative launch runs the whole epoch (steps 0 .. T, the last one being the critics' epoch-end
+// bootstrap): the weight tiles, biases and the TMEM allocation stay resident, every step ends in a grid barrier whose
+// last arriver folds the step's normaliser sums into the running statistics before it releases the others
+// (adapter/onpolicy_adapter.py:L58-136 is the loop this replaces).  Data written by other CTAs in earlier steps
+// (raw states, flags, normaliser statistics) is read with ld.global.cg.
+template <bool X3, bool PERSIST>
 __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p) {
     using namespace umma;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -520,31 +549,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     float* sMean = sB3 + 16;       // [64]
     float* sRstd = sMean + 64;     // [64]  1 / std
     float* sAct = sRstd + 64;      // [128][16]
-    float* sNew = sAct + RTC * OUTP;           // [128][65] next observation (post reset)
-    float* sFin = sNew + RTC * SNW;            // [128][65] final observation of finished envs
-    long long* sAcc = reinterpret_cast<long long*>(sFin + RTC * SNW);   // [4][4][64] partial fixed-point sums
-    int* sFlag = reinterpret_cast<int*>(sAcc + 4 * 4 * 64);             // [128]
+    float* sRaw = sAct + RTC * OUTP;           // [128][65] raw current state of the tile (actor CTAs; kept by the obs staging)
+    float* sSn = sRaw + RTC * SNW;             // [128][65] state after the transition, before any reset
+    long long* sAcc = reinterpret_cast<long long*>(sSn + RTC * SNW);    // [4][4][64] partial fixed-point sums
+    int* sFlag = reinterpret_cast<int*>(sAcc + 4 * 4 * 64);             // [128] bit 0 finished, bit 1 terminated, bit 2 truncated
+    uint32_t* sEpi = reinterpret_cast<uint32_t*>(sFlag + RTC);          // [128] episode counter
+    int* sStep = reinterpret_cast<int*>(sEpi + RTC);                    // [128] step inside the episode
+    uint32_t* sGstep = reinterpret_cast<uint32_t*>(sStep + RTC);        // [128] total steps of the env (termination hash counter)
+    float* sSd = reinterpret_cast<float*>(sGstep + RTC);                // [3][16] sigma, 2 sigma^2, log sigma per action
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ int s_last, s_anyfin;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
-    const int net = p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y;
+    const int net = PERSIST ? (int)blockIdx.y : (p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y);
     const int env0 = blockIdx.x * RTC;
-    const int O = p.es.O, A = p.es.A, N = p.N, T = p.T, t = p.t;
+    const int O = p.es.O, A = p.es.A, N = p.N, T = p.T;
     const NetLayout L = net_layout(net, O, A);
     const float* theta = p.theta + net_offset(net, O, A);
-    const bool normalize = p.es.obs_normalize && p.ns.count[0] > 1;
-    const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
-    float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
-
-    // env bookkeeping scalars of "my" env (actor CTAs: 2 threads per env), prefetched early
-    const int e_env = tid >> 1, e_half = tid & 1;
+    const int e_env = tid >> 1, e_half = tid & 1;       // actor CTAs: 2 threads per env in the transition
     const int my_env = env0 + e_env;
     const bool my_ok = (net == 0) && my_env < N;
-    int ep_step = 0; uint32_t epi = 0, gstep = 0;
-    if (my_ok) { ep_step = p.st.ep_step[my_env]; epi = p.st.episode[my_env]; gstep = p.st.gstep[my_env]; }
 
     if constexpr (X3) {   // weights -> bf16x3 tiles (all loads first)
         float a1[8], b1[8], a2[8], b2[8], a3[2], b3[2];
@@ -611,6 +637,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     }
     if (tid < 64) { sB1[tid] = __ldg(theta + L.off_b1 + tid); sB2[tid] = __ldg(theta + L.off_b2 + tid); }
     if (tid < 16) sB3[tid] = (tid < L.out) ? __ldg(theta + L.off_b3 + tid) : 0.f;
+    if (net == 0 && tid < 16) {          // Normal(mu, sigma): sigma = exp(log_std) is state independent
+        const float sd = (tid < A) ? expf(__ldg(theta + L.off_logstd + tid)) : 1.f;
+        sSd[tid] = sd; sSd[16 + tid] = __fmul_rn(2.f, __fmul_rn(sd, sd)); sSd[32 + tid] = logf(sd);
+    }
     if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); s_anyfin = 0; }
     if (warp == 0) tmem_alloc(&tmem_slot, 128);
     tc_fence_before();
@@ -621,9 +651,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     constexpr uint32_t C_Z = 0, C_OUT = 64;
     uint32_t phase = 0;
 
+    // development aid (tools/rollout_stage_times.py): clock64 stamps of thread 0 of the first actor and reward-critic CTA
+    const bool dbg_on = PERSIST && p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y < 2 && tid == 0;
+    int dbg_n = 0;
+#define RSTAMP(id) do { if (dbg_on && dbg_n < 250) { long long* d_ = p.dbg + (blockIdx.y ? 512 : 0); d_[1 + 2 * dbg_n] = (id); d_[2 + 2 * dbg_n] = clock64(); ++dbg_n; d_[0] = dbg_n; } } while (0)
+    const int t_first = PERSIST ? 0 : p.t, t_last = PERSIST ? T : p.t;
+#pragma unroll 1
+    for (int t = t_first; t <= t_last; ++t) {
+    const bool is_tail = t == T;
+    if (PERSIST && is_tail && net == 0) break;          // the tail step is the critics' (no barrier follows it)
+    const float* eps_t = PERSIST ? (p.eps ? p.eps + (size_t)t * N * A : nullptr) : p.eps;
+    const uint32_t gstep_t = PERSIST ? p.global_step + (uint32_t)t : p.global_step;
+    const bool normalize = p.es.obs_normalize && __ldcg(p.ns.count) > 1;
+    const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
+    float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
+    if (PERSIST) { if (tid == 0) s_anyfin = 0; __syncthreads(); }
+    // which envs of this tile finish in this step (time limit / hash-driven termination): known before the forward
+    if (net == 0 && tid < RTC) {
+        const int env = env0 + tid;
+        int fl = 0, ep_step = 0; uint32_t epi = 0, gstep = 0;
+        if (env < N) {
+            ep_step = p.st.ep_step[env]; epi = p.st.episode[env]; gstep = p.st.gstep[env];
+            const bool trunc = ep_step + 1 >= p.es.max_episode_steps;
+            const bool term = p.es.term_threshold != 0u &&
+                              hash4(p.es.seed ^ 0xA5A5A5A5u, p.es.env_id_offset + env, gstep, 0xFFFFu) < p.es.term_threshold;
+            fl = ((term || trunc) ? 1 : 0) | (term ? 2 : 0) | (trunc ? 4 : 0);
+        }
+        sFlag[tid] = fl; sEpi[tid] = epi; sStep[tid] = ep_step; sGstep[tid] = gstep;
+    }
+    RSTAMP(1);
+
     // does this critic tile need bootstrap values for paths cut in the previous step?
     if (net != 0 && t > 0 && tid < RTC && env0 + tid < N) {
-        const unsigned f = p.sl.flags[(size_t)(t - 1) * N + env0 + tid];
+        const unsigned f = __ldcg(p.sl.flags + (size_t)(t - 1) * N + env0 + tid);
         if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED)) s_anyfin = 1;
     }
     __syncthreads();
@@ -635,9 +695,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         const float* raw = pass ? s_cur : p.st.final_raw + (size_t)((t - 1) & 1) * N * O;
         const float* gmean = pass ? p.ns.mean : p.ns.mean1;
         const float* gstd = pass ? p.ns.std : p.ns.std1;
-        const bool norm_on = pass ? normalize : (p.es.obs_normalize && p.ns.count[1] > 1);
+        const bool norm_on = pass ? normalize : (p.es.obs_normalize && __ldcg(p.ns.count + 1) > 1);
         float* obs_out = (pass && net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr;
-        if (tid < 64) { sMean[tid] = (tid < O) ? gmean[tid] : 0.f; sRstd[tid] = (tid < O) ? gstd[tid] : 1.f; }
+        if (tid < 64) { sMean[tid] = (tid < O) ? __ldcg(gmean + tid) : 0.f; sRstd[tid] = (tid < O) ? __ldcg(gstd + tid) : 1.f; }
         __syncthreads();
         if ((O & 3) == 0) {   // 128-bit row loads, all 8 in flight per thread
             const int kq = tid & 15, k4 = kq << 2;
@@ -645,7 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int env = env0 + (tid >> 4) + 16 * j;
-                xv[j] = (env < N && k4 < O) ? *reinterpret_cast<const float4*>(raw + (size_t)env * O + k4)
+                xv[j] = (env < N && k4 < O) ? __ldcg(reinterpret_cast<const float4*>(raw + (size_t)env * O + k4))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const float m0 = sMean[k4], m1 = sMean[k4 + 1], m2 = sMean[k4 + 2], m3 = sMean[k4 + 3];
@@ -655,6 +715,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 const int e = (tid >> 4) + 16 * j;
                 const int env = env0 + e;
                 float4 v = xv[j];
+                if (pass && net == 0 && k4 < O) { float* r = sRaw + e * SNW + k4; r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
                 if (env < N && k4 < O) {
                     if (norm_on) {
                         v.x = fminf(fmaxf(__fdiv_rn(__fadd_rn(v.x, -m0), r0), -5.f), 5.f);
@@ -687,7 +748,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 const int env = env0 + e;
                 float v = 0.f;
                 if (env < N && k < O) {
-                    v = raw[(size_t)env * O + k];
+                    v = __ldcg(raw + (size_t)env * O + k);
+                    if (pass && net == 0) sRaw[e * SNW + k] = v;
                     if (norm_on) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v, -mk), sk), -5.f), 5.f);
                     if (obs_out) obs_out[(size_t)env * O + k] = v;
                 }
@@ -697,6 +759,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         }
         fence_async_smem();
         __syncthreads();
+        RSTAMP(2);
         if constexpr (X3) {
             // three layers on bf16x3 tiles, one activation buffer: every epilogue starts after its layer's MMAs completed
             const bool leader = (warp == 0) && x3::elect_one_sync();
@@ -708,6 +771,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 __syncwarp();
             }
             mbar_wait(&bar, phase); phase ^= 1;
+            RSTAMP(3);
             tc_fence_after();
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
@@ -727,6 +791,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 __syncwarp();
             }
             mbar_wait(&bar, phase); phase ^= 1;
+            RSTAMP(4);
             tc_fence_after();
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
@@ -746,6 +811,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 __syncwarp();
             }
             mbar_wait(&bar, phase); phase ^= 1;
+            RSTAMP(5);
             tc_fence_after();
         } else {
         if (tid == 0) { tc_fence_after(); tc_gemm(tmem + C_Z, B0, RTC, sW1, 64, 128, 64, 64, false); mma_commit(&bar); }
@@ -786,14 +852,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     const float v = o16[0] + sB3[0];
                     if (pass == 0) {
                         const size_t idx = (size_t)(t - 1) * N + env;
-                        const unsigned f = p.sl.flags[idx];
+                        const unsigned f = __ldcg(p.sl.flags + idx);
                         if ((f & OSB_FLAG_TRUNCATED) && !(f & OSB_FLAG_TERMINATED))
                             (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
-                    } else if (!p.is_tail) {
+                    } else if (!is_tail) {
                         (net == 1 ? p.sl.val_r : p.sl.val_c)[(size_t)t * N + env] = v;
                     } else {
                         const size_t idx = (size_t)(T - 1) * N + env;
-                        if (p.sl.flags[idx] == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
+                        if (__ldcg(p.sl.flags + idx) == 0) (net == 1 ? p.sl.boot_r : p.sl.boot_c)[idx] = v;
                     }
                 }
             } else {
@@ -805,82 +871,135 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         __syncthreads();
     }
 
+    RSTAMP(6);
     if (net == 0) {
-        // ---- sample + log-prob: thread -> (env e = 32*g + tid/8, lane qq = tid%8) -------------------
-        const int qq = tid & 7;
+        // ---- sample + log-prob.  A <= 8: thread -> (env e = 64 g + tid / 4, action pair pr = tid % 4): one Philox block
+        //      yields both normals of the pair (Box-Muller cos / sin); the log-prob terms are summed in the tree
+        //      ((t0+t1)+(t2+t3)) + ((t4+t5)+(t6+t7)) of rollout_step_kernel.  A > 8: one action per lane as there. -----------
+        if (A <= 8) {
+            const int pr = tid & 3, a0 = 2 * pr, a1 = a0 + 1;
 #pragma unroll 1
-        for (int g = 0; g < RTC / 32; ++g) {
-            const int e = 32 * g + (tid >> 3);
-            const int env = env0 + e;
-            const bool ok = env < N;
-            float lp = 0.f;
-            for (int a = qq; a < A; a += 8) {
-                const float mu = sAct[e * OUTP + a];
-                const float sd = expf(__ldg(theta + L.off_logstd + a));
-                float eps = 0.f;
-                if (ok)
-                    eps = p.eps ? p.eps[(size_t)env * A + a]
-                                : philox_normal(p.noise_seed, p.es.env_id_offset + env, p.global_step, a);
-                const float act = __fadd_rn(mu, __fmul_rn(sd, eps));
-                const float d = __fadd_rn(act, -mu);
-                const float var = __fmul_rn(sd, sd);
-                float term = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
-                term = __fadd_rn(__fadd_rn(term, -logf(sd)), -0.9189385332046727f);
-                lp += term;
-                sAct[e * OUTP + a] = act;
-                if (ok) p.sl.act[((size_t)t * N + env) * A + a] = act;
+            for (int g = 0; g < 2; ++g) {
+                const int e = 64 * g + (tid >> 2);
+                const int env = env0 + e;
+                const bool ok = env < N;
+                float n0 = 0.f, n1 = 0.f;
+                if (ok && a0 < A) {
+                    if (eps_t) { n0 = eps_t[(size_t)env * A + a0]; n1 = (a1 < A) ? eps_t[(size_t)env * A + a1] : 0.f; }
+                    else philox_normal2(p.noise_seed, p.es.env_id_offset + env, gstep_t, pr, n0, n1);
+                }
+                float lp = 0.f;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int a = a0 + u;
+                    if (a < A) {
+                        const float mu = sAct[e * OUTP + a];
+                        const float sd = sSd[a];
+                        const float act = __fadd_rn(mu, __fmul_rn(sd, u ? n1 : n0));      // Normal.rsample: loc + eps * scale
+                        const float d = __fadd_rn(act, -mu);
+                        float term = __fdiv_rn(-__fmul_rn(d, d), sSd[16 + a]);               // / (2 var)
+                        term = __fadd_rn(__fadd_rn(term, -sSd[32 + a]), -0.9189385332046727f);
+                        lp += term;
+                        sAct[e * OUTP + a] = act;
+                        if (ok) p.sl.act[((size_t)t * N + env) * A + a] = act;
+                    }
+                }
+                lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+                lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+                if (ok && pr == 0) p.sl.logp[(size_t)t * N + env] = lp;
             }
-            lp += __shfl_xor_sync(0xffffffffu, lp, 1);
-            lp += __shfl_xor_sync(0xffffffffu, lp, 2);
-            lp += __shfl_xor_sync(0xffffffffu, lp, 4);
-            if (ok && qq == 0) p.sl.logp[(size_t)t * N + env] = lp;
+        } else {
+            const int qq = tid & 7;
+#pragma unroll 1
+            for (int g = 0; g < RTC / 32; ++g) {
+                const int e = 32 * g + (tid >> 3);
+                const int env = env0 + e;
+                const bool ok = env < N;
+                float lp = 0.f;
+                for (int a = qq; a < A; a += 8) {
+                    const float mu = sAct[e * OUTP + a];
+                    const float sd = sSd[a];
+                    float eps = 0.f;
+                    if (ok)
+                        eps = eps_t ? eps_t[(size_t)env * A + a]
+                                    : philox_normal(p.noise_seed, p.es.env_id_offset + env, gstep_t, a);
+                    const float act = __fadd_rn(mu, __fmul_rn(sd, eps));
+                    const float d = __fadd_rn(act, -mu);
+                    float term = __fdiv_rn(-__fmul_rn(d, d), sSd[16 + a]);
+                    term = __fadd_rn(__fadd_rn(term, -sSd[32 + a]), -0.9189385332046727f);
+                    lp += term;
+                    sAct[e * OUTP + a] = act;
+                    if (ok) p.sl.act[((size_t)t * N + env) * A + a] = act;
+                }
+                lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+                lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+                lp += __shfl_xor_sync(0xffffffffu, lp, 4);
+                if (ok && qq == 0) p.sl.logp[(size_t)t * N + env] = lp;
+            }
         }
         __syncthreads();
-        // ---- env transition: all 128 envs at once, 2 threads per env.  Thread `e_half` owns the
-        //      partial sums p_q, q = 4*e_half .. 4*e_half+3 (dims j = q mod 8): the summation tree is the
-        //      one of the spec ((p0+p1)+(p2+p3)) + ((p4+p5)+(p6+p7)). --------------------------------
+        RSTAMP(7);
+        // ---- env transition + normaliser sums, elementwise: thread -> (dim j = tid % 64, env quarter g = tid / 64).
+        //      The raw state comes from shared memory (kept by the obs staging), the next state goes out in whole
+        //      rows (coalesced), the fixed-point column sums accumulate in registers. ---------------------------------------
+        {
+            const int j = tid & 63, g = tid >> 6;
+            long long sx = 0, sxx = 0, fx = 0, fxx = 0;
+            if (j < O) {
+                const int ja = j % A;
+                const float bj = __ldg(p.st.bias + j);
+#pragma unroll 4
+                for (int e = 32 * g; e < 32 * g + 32; ++e) {
+                    const int env = env0 + e;
+                    if (env < N) {
+                        // ActionScale (wrapper.py:L510-512) from [-1,1] onto the env's [-1,1] box
+                        float a = sAct[e * OUTP + ja];
+                        a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
+                        a = fminf(fmaxf(a, -1.f), 1.f);
+                        const float sn = env_next_value(sRaw[e * SNW + j], a, bj);
+                        const int fl = sFlag[e];
+                        float nv = sn;
+                        if (fl & 1) {
+                            nv = env_reset_value(p.es, p.es.env_id_offset + env, sEpi[e] + 1u, j);
+                            p.st.final_raw[((size_t)(t & 1) * N + env) * O + j] = sn;
+                            fx += to_fix(sn); fxx += to_fix(__fmul_rn(sn, sn));
+                        }
+                        s_nxt[(size_t)env * O + j] = nv;
+                        sSn[e * SNW + j] = sn;
+                        sx += to_fix(nv); sxx += to_fix(__fmul_rn(nv, nv));
+                    }
+                }
+            }
+            if (p.es.obs_normalize) {
+                sAcc[(g * 4 + 0) * 64 + j] = sx; sAcc[(g * 4 + 1) * 64 + j] = sxx;
+                sAcc[(g * 4 + 2) * 64 + j] = fx; sAcc[(g * 4 + 3) * 64 + j] = fxx;
+            }
+        }
+        __syncthreads();
+        RSTAMP(8);
+        // ---- reward / cost / flags / episode bookkeeping: 2 threads per env.  Thread `e_half` owns the partial sums
+        //      p_q, q = 4*e_half .. 4*e_half+3 (dims j = q mod 8): the summation tree is the one of the spec
+        //      ((p0+p1)+(p2+p3)) + ((p4+p5)+(p6+p7)). ------------------------------------------------------------------
         {
             const int env = my_env;
             const bool ok = my_ok;
-            const uint32_t gid = p.es.env_id_offset + env;
-            const bool trunc = ok && (ep_step + 1 >= p.es.max_episode_steps);
-            const bool term = ok && p.es.term_threshold != 0u &&
-                              hash4(p.es.seed ^ 0xA5A5A5A5u, gid, gstep, 0xFFFFu) < p.es.term_threshold;
-            const bool fin = term || trunc;
             float part[4] = {0.f, 0.f, 0.f, 0.f};
-            float s0n = 0.f;
-            float* finrow = p.st.final_raw + ((size_t)(t & 1) * N + (ok ? env : 0)) * O;
 #pragma unroll 1
             for (int jb = 4 * e_half; jb < O; jb += 8) {
 #pragma unroll
                 for (int qi = 0; qi < 4; ++qi) {
                     const int j = jb + qi;
-                    if (j < O) {
-                        float nv = 0.f, fv = 0.f;
-                        if (ok) {
-                            float a = sAct[e_env * OUTP + (j % A)];
-                            a = __fadd_rn(__fadd_rn(a, 1.f), -1.f);
-                            a = fminf(fmaxf(a, -1.f), 1.f);
-                            const float s = s_cur[(size_t)env * O + j];
-                            const float sn = env_next_value(s, a, __ldg(p.st.bias + j));
-                            part[qi] = __fadd_rn(part[qi], __fmul_rn(sn, sn));
-                            if (j == 0) s0n = sn;
-                            fv = sn;
-                            nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
-                            s_nxt[(size_t)env * O + j] = nv;
-                            if (fin) finrow[j] = sn;
-                        }
-                        sNew[e_env * SNW + j] = nv;
-                        sFin[e_env * SNW + j] = fin ? fv : 0.f;
-                    }
+                    if (j < O) { const float sn = sSn[e_env * SNW + j]; part[qi] = __fadd_rn(part[qi], __fmul_rn(sn, sn)); }
                 }
             }
-            if (e_half == 0) sFlag[e_env] = fin ? 1 : 0;
             float tot = __fadd_rn(__fadd_rn(part[0], part[1]), __fadd_rn(part[2], part[3]));
             tot = __fadd_rn(tot, __shfl_xor_sync(0xffffffffu, tot, 1));
             if (ok && e_half == 0) {
+                const int fl = sFlag[e_env];
+                const bool fin = fl & 1, term = fl & 2, trunc = fl & 4;
+                const uint32_t epi = sEpi[e_env];
                 const float rew = __fadd_rn(1.f, -__fdiv_rn(tot, (float)O));
-                const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
+                const float cst = (sSn[e_env * SNW] > p.es.cost_threshold) ? 1.f : 0.f;
                 const size_t idx = (size_t)t * N + env;
                 p.sl.rew[idx] = rew;
                 p.sl.cost[idx] = cst;
@@ -898,33 +1017,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     p.st.ep_step[env] = 0;
                 } else {
                     p.st.ep_ret[env] = erv; p.st.ep_cost[env] = ecv; p.st.ep_len[env] = el;
-                    p.st.ep_step[env] = ep_step + 1;
+                    p.st.ep_step[env] = sStep[e_env] + 1;
                 }
-                p.st.gstep[env] = gstep + 1u;
+                p.st.gstep[env] = sGstep[e_env] + 1u;
             }
         }
-        __syncthreads();
         if (p.es.obs_normalize) {
-            // fixed-point column sums over the tile: thread (dim j = tid % 64, env quarter g = tid / 64)
-            const int j = tid & 63, g = tid >> 6;
-            long long sx = 0, sxx = 0, fx = 0, fxx = 0;
-            int nf = 0;
-            if (j < O) {
-#pragma unroll 4
-                for (int r = 32 * g; r < 32 * g + 32; ++r)
-                    if (env0 + r < N) {
-                        const float v = sNew[r * SNW + j];
-                        sx += to_fix(v); sxx += to_fix(__fmul_rn(v, v));
-                        if (sFlag[r]) {
-                            const float w = sFin[r * SNW + j];
-                            fx += to_fix(w); fxx += to_fix(__fmul_rn(w, w));
-                            ++nf;
-                        }
-                    }
-            }
-            sAcc[(g * 4 + 0) * 64 + j] = sx; sAcc[(g * 4 + 1) * 64 + j] = sxx;
-            sAcc[(g * 4 + 2) * 64 + j] = fx; sAcc[(g * 4 + 3) * 64 + j] = fxx;
-            __syncthreads();
             if (tid < O) {
                 long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 for (int gg = 0; gg < 4; ++gg) {
@@ -938,20 +1036,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     atomicAdd((unsigned long long*)(p.ns.acc_fin + O + tid), (unsigned long long)a3);
                 }
             }
-            if (tid == 0) {
+            if (tid == 64) {
                 int nfin = 0;
-                for (int r = 0; r < RTC; ++r) nfin += (env0 + r < N) ? sFlag[r] : 0;
+                for (int r = 0; r < RTC; ++r) nfin += (env0 + r < N) ? (sFlag[r] & 1) : 0;
                 if (nfin) atomicAdd(p.ns.fin_count, nfin);
             }
         }
     }
-    if (p.es.obs_normalize && !p.is_tail) {
+    RSTAMP(9);
+    if (PERSIST) {
+        if (!is_tail) {
+            // grid barrier; the last CTA to arrive folds the step's sums into the running statistics, then releases
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(p.bar_ctr, 1u) == gridDim.x * gridDim.y * (unsigned)(t + 1) - 1u) ? 1 : 0;
+            __syncthreads();
+            if (s_last) {
+                if (p.es.obs_normalize) norm_finalize(p.ns, O, (long long)N);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.bar_flag), "r"((unsigned)(t + 1)) : "memory");
+            } else if (tid == 0) {
+                unsigned v;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.bar_flag) : "memory"); } while (v < (unsigned)(t + 1));
+            }
+            __syncthreads();
+            RSTAMP(10);
+        }
+    } else if (p.es.obs_normalize && !is_tail) {
         __threadfence();
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(p.ns.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
         __syncthreads();
         if (s_last) norm_finalize(p.ns, O, (long long)N);
     }
+    }   // step loop
+#undef RSTAMP
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
@@ -960,7 +1080,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 static size_t rollout_tc_smem_bytes(bool x3) {
     return 1024 + (x3 ? RTC_FOFF_X3 : RTC_FOFF_TF32) +
            (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * RTC * SNW) * sizeof(float) + 4 * 4 * 64 * sizeof(long long) +
-           RTC * sizeof(int) + 64;
+           4 * RTC * sizeof(int) + 48 * sizeof(float) + 64;
 }
 
 // Window of the last <= W finished episodes in (step, env) append order: Logger deque semantics
@@ -1091,19 +1211,32 @@ int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned t
     return OSB_OK;
 }
 
+static long long* g_rollout_dbg = nullptr;
+
 static int launch_step(StepArgs& p, cudaStream_t stream) {
     if ((p.precision == 1 || p.precision == 2) && p.es.O <= 64) {
         const bool x3 = p.precision == 2;
         const size_t smem_tc = rollout_tc_smem_bytes(x3);
         static bool attr_tc = false;
         if (!attr_tc) {
-            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(false)));
-            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(true)));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(false)));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(true)));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(false)));
+            OSB_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_tc_smem_bytes(true)));
             attr_tc = true;
         }
         dim3 grid_tc((p.N + RTC - 1) / RTC, p.is_tail ? 2 : 3);
-        if (x3) rollout_step_tc_kernel<true><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
-        else rollout_step_tc_kernel<false><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
+        if (p.bar_ctr != nullptr) {
+            // the whole epoch in one cooperative launch (every CTA resident: the step barrier is a software grid barrier)
+            OSB_CUDA(cudaMemsetAsync(p.bar_ctr, 0, 2 * sizeof(unsigned int), stream));
+            void* args[] = {&p};
+            osb_count_launch();
+            OSB_CUDA(cudaLaunchCooperativeKernel(x3 ? (void*)rollout_step_tc_kernel<true, true> : (void*)rollout_step_tc_kernel<false, true>,
+                                                 dim3((p.N + RTC - 1) / RTC, 3), dim3(NTHREADS), args, smem_tc, stream));
+            return OSB_OK;
+        }
+        if (x3) rollout_step_tc_kernel<true, false><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
+        else rollout_step_tc_kernel<false, false><<<grid_tc, NTHREADS, smem_tc, stream>>>(p);
         OSB_LAUNCH_CHECK();
         return OSB_OK;
     }
@@ -1118,6 +1251,9 @@ static int launch_step(StepArgs& p, cudaStream_t stream) {
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
+
+// development aid: clock64 stamps of the persistent rollout kernel go to buf (1024 long long), NULL turns it off
+int osb_rollout_debug_buffer(long long* buf) { g_rollout_dbg = buf; return OSB_OK; }
 
 int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigned term_threshold,
                      unsigned env_id_offset, float cost_threshold, int obs_normalize, int N, int T,
@@ -1140,6 +1276,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
     p.theta = theta; p.eps = eps; p.noise_seed = noise_seed; p.global_step = global_step;
     p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0; p.precision = precision;
+    p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = nullptr;
     return launch_step(p, (cudaStream_t)stream);
 }
 
@@ -1170,6 +1307,20 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
     p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N; p.precision = precision;
+    p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = g_rollout_dbg;
+    // tensor-core modes with every CTA resident (grid = env tiles x 3 networks <= SMs): one persistent launch per epoch
+    static const bool stepwise = getenv("OSB_ROLLOUT_STEPWISE") != nullptr;
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; OSB_CUDA(cudaGetDevice(&dev)); OSB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    if (!stepwise && (precision == 1 || precision == 2) && O <= 64 && ((N + RTC - 1) / RTC) * 3 <= n_sm) {
+        static unsigned int* d_bar = nullptr;
+        if (!d_bar) OSB_CUDA(cudaMalloc(&d_bar, 64));
+        p.bar_ctr = d_bar; p.bar_flag = d_bar + 1;
+        p.t = 0; p.is_tail = 0; p.eps = eps_all; p.global_step = epoch_index * (unsigned)T;
+        rc = launch_step(p, s);
+        if (rc) return rc;
+        return osb_episode_window(flags, epfin, T, N, W, ring, meta, window_sums, stream);
+    }
     for (int t = 0; t <= T; ++t) {
         p.t = t; p.is_tail = (t == T) ? 1 : 0;
         p.eps = (eps_all && t < T) ? eps_all + (size_t)t * N * A : nullptr;
