@@ -247,6 +247,19 @@ def run_b200(args) -> dict:
         kname = 'minibatch_grad_tc_kernel' if args.precision == 'tf32' else 'minibatch_grad_kernel'
         rows_per_launch = w['batch_size']
         traffic = 14.57e6 if (args.precision == 'tf32' and O == 60) else None     # ncu --set full, profiles/r01_ncu_minibatch_grad_tc.md
+    # the GAE scan where HBM is its bound: a horizon whose 277 MB of algorithmic traffic do not fit L2 (the epoch's own
+    # T = 128 launch moves 17 MB and is latency bound)
+    from omnisafe_b200.common.buffer import VectorOnPolicyBuffer
+    T_long = 2048
+    lbuf = VectorOnPolicyBuffer(4, 2, T_long, 0.99, 0.95, 0.95, 'gae', 0.0, True, True, num_envs=N, device='cuda', keep_discounted_ret=False)
+    for k_ in ('reward', 'cost', 'value_r', 'value_c', 'boot_r', 'boot_c'):
+        lbuf.data[k_].normal_()
+    lbuf.data['flags'][w['max_episode_steps'] - 1::w['max_episode_steps']] = 2          # the bench env's time-limit truncations
+    for _ in range(3):
+        lbuf.finish_paths()
+    ms_gae_long = timed(lbuf.finish_paths, 20) / 20
+    gae_long_gbs = 33.0 * T_long * N / (ms_gae_long * 1e-3) / 1e9
+    del lbuf
     ach_tf = flop_per_sample * rows_per_launch / (ms_k * 1e-3) / 1e12
     row_bytes = 4.0 * (O + A + 5)
     gae_gbs = 33.0 * total / (ms_gae * 1e-3) / 1e9
@@ -259,10 +272,13 @@ def run_b200(args) -> dict:
                        'bf16x3 mode executes 6 bf16 MMAs per product' if x3_path else peaks['source'] + ' (cuBLAS bf16, sustained)',
         'us_per_launch': ms_k * 1e3, 'us_per_minibatch_step': ms_k * 1e3 / (rows_per_launch // w['batch_size']),
         'mma_executed_tflops': ach_tf * 6.0 if x3_path else None,
-        'gae': {'kernel': 'gae_dual_kernel', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
+        'gae': {'kernel': 'gae_stream_kernel<TMA>', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': gae_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae * 1e3, 'bytes_per_sample': 33,
-                'note': 'T = 128: 17 MB, latency bound (one wave); the long-horizon figure is in profiles/'},
-        'rollout_step': {'kernel': 'rollout_step_tc_kernel<bf16x3>' if x3_path else ('rollout_step_tc_kernel<tf32>' if args.precision == 'tf32' and O <= 64 else 'rollout_step_kernel'),
+                'note': 'T = 128: 17 MB, latency bound (one wave of 128 CTAs, one tile each)'},
+        'gae_long_horizon': {'kernel': 'gae_stream_kernel<TMA>', 'bound': 'hbm', 'achieved': gae_long_gbs, 'peak': peaks['hbm_gbs'],
+                             'unit': 'GB/s', 'frac': gae_long_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae_long * 1e3,
+                             'bytes_per_sample': 33, 'workload': f'T = {T_long} x {N} envs = {33 * T_long * N / 1e6:.0f} MB algorithmic (> L2), timed live with CUDA events'},
+        'rollout_step': {'kernel': 'rollout_step_tc_kernel<bf16x3, persistent> (1 launch = 1 epoch)' if x3_path else ('rollout_step_tc_kernel<tf32, persistent> (1 launch = 1 epoch)' if args.precision == 'tf32' and O <= 64 else 'rollout_step_kernel'),
                          'bound': 'latency', 'us_per_step': ms_roll * 1e3 / (T + 1),
                          'achieved_tflops': (2 * (O * 64 + 64 * 64 + 64 * A) + 4 * (O * 64 + 64 * 64 + 64)) * N / (ms_roll * 1e-3 / (T + 1)) / 1e12,
                          'appended_bytes_per_step': row_bytes * N},

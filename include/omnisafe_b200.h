@@ -117,6 +117,13 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
                       const float* theta, const float* eps_all, unsigned noise_seed,
                       unsigned epoch_index, int W, float* ring, int* meta, double* window_sums,
                       int precision, void* stream);
+/* Saute / Simmer mode of the following osb_env_reset / osb_rollout_* calls (SauteAdapter.step / reset,
+ * adapter/saute_adapter.py:L135-217; SimmerAdapter.reset, simmer_adapter.py:L97-111): safety = [2][N] device floats (the
+ * safety state z by step parity) or NULL for the plain OnPolicyAdapter.  The networks then take O + 1 inputs
+ * ([normalised obs | z], theta sized accordingly) and the obs slab rows are O + 1 wide; z starts an epoch at safety_init,
+ * z <- (z - cost / safety_budget) / saute_gamma per step, the stored reward is unsafe_reward once z <= 0, z <- 1 at
+ * episode ends.  Process-wide until changed. */
+int osb_rollout_set_saute(float* safety, float safety_budget, float saute_gamma, float unsafe_reward, float safety_init);
 /* Logger window of the last <= W finished episodes in (step, env) order
  * (common/logger.py:L253-282, adapter/onpolicy_adapter.py:L159-175).  ring[3][W], meta[2] persist
  * across epochs; window_sums[4] <- {sum EpRet, sum EpCost, sum EpLen, count} (fp64). */
@@ -224,6 +231,12 @@ int osb_fvp_partials(const float* theta_actor, const float* vec, int O, int A, c
  * gpart: osb_tc_grid_blocks(rows, 1) rows of P_actor floats, rows = ceil(total / stride);
  * stats_scratch: that many * 24 floats.  Reduce with osb_reduce_partials. */
 int osb_fvp_partials_tc(const float* theta_actor, const float* vec, int O, int A, const float* obs,
+                        long long total, int stride, float* dmu, float* gpart, float* stats_scratch,
+                        void* stream);
+/* Split-bf16 ("bf16x3") variant of osb_fvp_partials_tc (O <= 64): forward-mode tangent kernel on bf16x3 tiles
+ * (csrc/fvp_x3.cu) + the bf16x3 actor backward with the tangent as output gradient: fp32-level F v on the tensor
+ * cores.  NaturalPG._fvp, natural_pg.py:L74-119. */
+int osb_fvp_partials_x3(const float* theta_actor, const float* vec, int O, int A, const float* obs,
                         long long total, int stride, float* dmu, float* gpart, float* stats_scratch,
                         void* stream);
 

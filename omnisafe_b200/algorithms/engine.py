@@ -125,7 +125,12 @@ class UpdateEngine:
     def fvp(self, vec: torch.Tensor, out: torch.Tensor, damping: float, stride: int = 1) -> None:
         """NaturalPG._fvp (natural_pg.py:L74-119): out <- avg_ranks(F vec) + damping * vec."""
         a = self.agent
-        if self._tc():
+        if self._x3():
+            nb = lib().osb_tc_grid_blocks((self.total + stride - 1) // stride, NET_ACTOR)
+            lib().osb_fvp_partials_x3(ptr(a.theta), ptr(vec), self.O, self.A, ptr(self.buf.data['obs']),
+                                      self.total, stride, ptr(self.fvp_dmu), ptr(self.fvp_part),
+                                      ptr(self.stats_part), current_stream())
+        elif self._tc():
             nb = lib().osb_tc_grid_blocks((self.total + stride - 1) // stride, NET_ACTOR)
             lib().osb_fvp_partials_tc(ptr(a.theta), ptr(vec), self.O, self.A, ptr(self.buf.data['obs']),
                                       self.total, stride, ptr(self.fvp_dmu), ptr(self.fvp_part),

@@ -15,6 +15,8 @@ import time
 import torch
 
 from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
+from omnisafe_b200.adapter.saute_adapter import SauteAdapter
+from omnisafe_b200.adapter.simmer_adapter import SimmerAdapter
 from omnisafe_b200.algorithms import registry
 from omnisafe_b200.algorithms.base_algo import BaseAlgo
 from omnisafe_b200.algorithms.engine import (LOSS_COST, LOSS_FOCOPS, LOSS_P3O, LOSS_PPO_CLIP, LOSS_RATIO,
@@ -585,5 +587,57 @@ class OnCRPO(TRPO):
         self._logger.store({'Misc/RewUpdate': self._rew_update, 'Misc/CostUpdate': self._cost_update})
 
 
+class _SauteMixin:
+    """saute/ppo_saute.py:L43-83, saute/trpo_saute.py: the Saute adapter instead of the plain one + Metrics/EpBudget."""
+
+    _adapter_cls = SauteAdapter
+
+    def _init_env(self) -> None:
+        t, a = self._cfgs.train_cfgs, self._cfgs.algo_cfgs
+        rank = distributed.get_rank()
+        self._env = self._adapter_cls(self._env_id, t.vector_env_nums, self._seed, self._cfgs, device=self._device,
+                                      env_id_offset=rank * t.vector_env_nums)
+        self._steps_per_epoch = distributed.local_steps(a.steps_per_epoch, t.vector_env_nums)
+
+    def _init_log(self) -> None:
+        super()._init_log()
+        self._logger.register_key('Metrics/EpBudget')
+
+    def _log_epoch(self, epoch, start, epoch_time, roll):
+        self._logger.store({'Metrics/EpBudget': self._env.ep_budget_mean()})
+        return super()._log_epoch(epoch, start, epoch_time, roll)
+
+
+class _SimmerMixin(_SauteMixin):
+    """simmer/ppo_simmer_pid.py:L48-95: the budget controller acts on the windowed mean episode cost before every update."""
+
+    _adapter_cls = SimmerAdapter
+
+    def _update(self) -> None:
+        ws = self._env.window_sums.tolist()                    # {sum EpRet, sum EpCost, sum EpLen, count}, all ranks
+        self._env.control_budget(ws[1] / ws[3] if ws[3] > 0 else 0.0)
+        super()._update()
+
+
+@registry.register
+class PPOSaute(_SauteMixin, PPO):
+    """saute/ppo_saute.py:L28-83."""
+
+
+@registry.register
+class TRPOSaute(_SauteMixin, TRPO):
+    """saute/trpo_saute.py."""
+
+
+@registry.register
+class PPOSimmerPID(_SimmerMixin, PPO):
+    """simmer/ppo_simmer_pid.py:L30-95."""
+
+
+@registry.register
+class TRPOSimmerPID(_SimmerMixin, TRPO):
+    """simmer/trpo_simmer_pid.py."""
+
+
 ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'PDO', 'IPO', 'P3O', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO',
-             'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO']
+             'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO', 'PPOSaute', 'TRPOSaute', 'PPOSimmerPID', 'TRPOSimmerPID']

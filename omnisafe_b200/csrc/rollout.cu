@@ -47,6 +47,17 @@ struct EnvState {
     const float* bias;   // [O]
 };
 
+// Saute / Simmer safety state (adapter/saute_adapter.py:L135-217, simmer_adapter.py:L97-131): the networks see
+// [normalised obs | z]; z starts an epoch at `init`, z <- (z - cost / budget) / gamma after every step, the stored reward
+// becomes `unsafe_reward` once z <= 0, z returns to 1 when the episode ends (final observations carry z = 1).
+struct SauteSpec {
+    float* safety;       // [2][N] by step parity (like s_raw), or null: plain OnPolicyAdapter
+    float budget;        // per-step safety budget (saute_adapter.py:L62-68)
+    float gamma;         // saute_gamma
+    float unsafe_reward;
+    float init;          // z at the epoch's reset: 1 (Saute) or the relative budget (Simmer)
+};
+
 struct NormState {
     float* mean;    // [O] running mean            (Normalizer._mean)
     float* sumsq;   // [O] running sum of squares  (Normalizer._sumsq)
@@ -146,7 +157,7 @@ __device__ __forceinline__ long long to_fix(float x) { return __float2ll_rn(x * 
 // ---------------------------------------------------------------------------------------------
 // reset of all envs (OnPolicyAdapter.rollout resets every epoch: onpolicy_adapter.py:L80) and the
 // normaliser push of the reset observations (ObsNormalize.reset, wrapper.py:L243-261).
-__global__ void __launch_bounds__(NTHREADS) env_reset_kernel(EnvSpec es, EnvState st, NormState ns,
+__global__ void __launch_bounds__(NTHREADS) env_reset_kernel(EnvSpec es, EnvState st, NormState ns, SauteSpec sa,
                                                              int N) {
     __shared__ float sNew[RT][KC + 1];
     __shared__ int s_last;
@@ -189,6 +200,7 @@ __global__ void __launch_bounds__(NTHREADS) env_reset_kernel(EnvSpec es, EnvStat
         st.ep_ret[env] = 0.f;
         st.ep_cost[env] = 0.f;
         st.ep_len[env] = 0;
+        if (sa.safety) sa.safety[env] = sa.init;   // buffer 0: step 0 reads parity 0
     }
     if (es.obs_normalize) {
         __threadfence();
@@ -246,6 +258,7 @@ struct StepArgs {
     EnvState st;
     NormState ns;
     Slabs sl;
+    SauteSpec sa;
     const float* theta;   // flat [actor | critic_r | critic_c]
     const float* eps;     // [N][A] noise of this step (parity mode) or null (Philox fast mode)
     uint32_t noise_seed;
@@ -259,10 +272,14 @@ struct StepArgs {
 };
 
 // normalise (or copy) a tile of raw observations into sX (chunk kc), zero padded.
+// z = per-env safety state (Saute) appended as column O of the network input (rows are On = O + 1 wide then), or null;
+// z_one: the final observations of finished episodes carry z = 1 (the state was reset before the augmentation).
 __device__ __forceinline__ void load_obs_tile(const float* __restrict__ raw, int env0, int N, int O,
                                               int kc, const float* sMean, const float* sStd,
-                                              bool normalize, float* sX, float* obs_out) {
+                                              bool normalize, float* sX, float* obs_out,
+                                              const float* z = nullptr, bool z_one = false) {
     const int c0 = kc * KC;
+    const int On = O + (z ? 1 : 0);
     for (int i = threadIdx.x; i < RT * KC; i += NTHREADS) {
         const int e = i / KC, k = i % KC;
         const int env = env0 + e, j = c0 + k;
@@ -273,10 +290,24 @@ __device__ __forceinline__ void load_obs_tile(const float* __restrict__ raw, int
                 v = __fdiv_rn(__fadd_rn(v, -sMean[j]), sStd[j]);
                 v = fminf(fmaxf(v, -5.f), 5.f);
             }
-            if (obs_out) obs_out[(size_t)env * O + j] = v;
+            if (obs_out) obs_out[(size_t)env * On + j] = v;
+        } else if (env < N && j == O && z) {
+            v = z_one ? 1.f : __ldcg(z + env);
+            if (obs_out) obs_out[(size_t)env * On + j] = v;
         }
         sX[e * LD + k] = v;
     }
+}
+
+// SauteAdapter.step (saute_adapter.py:L172-217) for one env: z <- (z - cost / budget) / gamma, reward override once
+// z <= 0, z <- 1 when the episode ends.  Returns the reward to store (episode returns keep the original one).
+__device__ __forceinline__ float saute_step(const SauteSpec& sa, int t, int N, int env, float rew, float cost, bool fin) {
+    if (!sa.safety) return rew;
+    float z = __ldcg(sa.safety + (size_t)(t & 1) * N + env);
+    z = __fdiv_rn(__fadd_rn(z, -__fdiv_rn(cost, sa.budget)), sa.gamma);
+    const float out = (z > 0.f) ? rew : sa.unsafe_reward;
+    sa.safety[(size_t)((t + 1) & 1) * N + env] = fin ? 1.f : z;
+    return out;
 }
 
 __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
@@ -300,9 +331,11 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
     const int net = p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y;
     const int env0 = blockIdx.x * RT;
     const int O = p.es.O, A = p.es.A, N = p.N, T = p.T, t = p.t;
-    const int nchunks = (O + KC - 1) / KC;
-    const NetLayout L = net_layout(net, O, A);
-    const float* theta = p.theta + net_offset(net, O, A);
+    const int On = O + (p.sa.safety ? 1 : 0);            // network input width (Saute: [obs | z])
+    const float* z_cur = p.sa.safety ? p.sa.safety + (size_t)(t & 1) * N : nullptr;
+    const int nchunks = (On + KC - 1) / KC;
+    const NetLayout L = net_layout(net, On, A);
+    const float* theta = p.theta + net_offset(net, On, A);
     const bool normalize = p.es.obs_normalize && p.ns.count[0] > 1;
     const float* s_cur = p.st.s_raw + (size_t)(t & 1) * N * O;
     float* s_nxt = p.st.s_raw + (size_t)((t + 1) & 1) * N * O;
@@ -312,7 +345,7 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
     auto load_chunk_cur = [&](int kc) {
         load_w1_chunk(theta, L, kc, W);
         for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean[j]; sStd[j] = p.ns.std[j]; }
-        load_obs_tile(s_cur, env0, N, O, kc, sMean, sStd, normalize, sX, nullptr);
+        load_obs_tile(s_cur, env0, N, O, kc, sMean, sStd, normalize, sX, nullptr, z_cur);
     };
 
     // ---- bootstrap values of paths that ended in the previous step (critic CTAs only) --------
@@ -330,11 +363,11 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
             auto load_chunk_fin = [&](int kc) {
                 load_w1_chunk(theta, L, kc, W);
                 for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean1[j]; sStd[j] = p.ns.std1[j]; }
-                load_obs_tile(fin, env0, N, O, kc, sMean, sStd, norm1, sX, nullptr);
+                load_obs_tile(fin, env0, N, O, kc, sMean, sStd, norm1, sX, nullptr, z_cur, true);
             };
             for (int j = threadIdx.x; j < O; j += NTHREADS) { sMean[j] = p.ns.mean1[j]; sStd[j] = p.ns.std1[j]; }
             __syncthreads();
-            load_obs_tile(fin, env0, N, O, 0, sMean, sStd, norm1, sX, nullptr);
+            load_obs_tile(fin, env0, N, O, 0, sMean, sStd, norm1, sX, nullptr, z_cur, true);
             __syncthreads();
             mlp_hidden<RT>(sX, sH1, sH2, W, nchunks, load_chunk_fin);
             mlp_out<RT>(sH2, sO, W, 1);
@@ -356,11 +389,11 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
         // write the whole normalised observation row once (chunks > 0 are not revisited below)
         for (int kc = 1; kc < nchunks; ++kc)
             load_obs_tile(s_cur, env0, N, O, kc, sMean, sStd, normalize, sX,
-                          p.sl.obs + (size_t)t * N * O);
+                          p.sl.obs + (size_t)t * N * On, z_cur);
         __syncthreads();
     }
     load_obs_tile(s_cur, env0, N, O, 0, sMean, sStd, normalize, sX,
-                  (net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr);
+                  (net == 0) ? p.sl.obs + (size_t)t * N * On : nullptr, z_cur);
     __syncthreads();
     mlp_hidden<RT>(sX, sH1, sH2, W, nchunks, load_chunk_cur);
     mlp_out<RT>(sH2, sO, W, L.out);
@@ -476,7 +509,7 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
             const float rew = __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
             const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
             const size_t idx = (size_t)t * N + env;
-            p.sl.rew[idx] = rew;
+            p.sl.rew[idx] = saute_step(p.sa, t, N, env, rew, cst, fin);
             p.sl.cost[idx] = cst;
             p.sl.flags[idx] = (uint8_t)((term ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
             // adapter bookkeeping: _log_value, _log_metrics, _reset_log (onpolicy_adapter.py:L138-175)
@@ -566,8 +599,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     const int net = PERSIST ? (int)blockIdx.y : (p.is_tail ? (int)blockIdx.y + 1 : (int)blockIdx.y);
     const int env0 = blockIdx.x * RTC;
     const int O = p.es.O, A = p.es.A, N = p.N, T = p.T;
-    const NetLayout L = net_layout(net, O, A);
-    const float* theta = p.theta + net_offset(net, O, A);
+    const int On = O + (p.sa.safety ? 1 : 0);            // network input width (Saute: [obs | z]), <= 64 here
+    const NetLayout L = net_layout(net, On, A);
+    const float* theta = p.theta + net_offset(net, On, A);
     const int e_env = tid >> 1, e_half = tid & 1;       // actor CTAs: 2 threads per env in the transition
     const int my_env = env0 + e_env;
     const bool my_ok = (net == 0) && my_env < N;
@@ -577,8 +611,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = tid + j * NTHREADS, n = i >> 5, k = (i & 31) << 1;
-            a1[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
-            b1[j] = (k + 1 < O) ? __ldg(theta + L.off_w1 + n * O + k + 1) : 0.f;
+            a1[j] = (k < On) ? __ldg(theta + L.off_w1 + n * On + k) : 0.f;
+            b1[j] = (k + 1 < On) ? __ldg(theta + L.off_w1 + n * On + k + 1) : 0.f;
             a2[j] = __ldg(theta + L.off_w2 + n * 64 + k); b2[j] = __ldg(theta + L.off_w2 + n * 64 + k + 1);
         }
 #pragma unroll
@@ -618,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int n = (tid >> 6) + 4 * j;
-            w1v[j] = (k < O) ? __ldg(theta + L.off_w1 + n * O + k) : 0.f;
+            w1v[j] = (k < On) ? __ldg(theta + L.off_w1 + n * On + k) : 0.f;
             w2v[j] = __ldg(theta + L.off_w2 + n * 64 + k);
         }
 #pragma unroll
@@ -696,10 +730,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         const float* gmean = pass ? p.ns.mean : p.ns.mean1;
         const float* gstd = pass ? p.ns.std : p.ns.std1;
         const bool norm_on = pass ? normalize : (p.es.obs_normalize && __ldcg(p.ns.count + 1) > 1);
-        float* obs_out = (pass && net == 0) ? p.sl.obs + (size_t)t * N * O : nullptr;
+        float* obs_out = (pass && net == 0) ? p.sl.obs + (size_t)t * N * On : nullptr;
         if (tid < 64) { sMean[tid] = (tid < O) ? __ldcg(gmean + tid) : 0.f; sRstd[tid] = (tid < O) ? __ldcg(gstd + tid) : 1.f; }
         __syncthreads();
-        if ((O & 3) == 0) {   // 128-bit row loads, all 8 in flight per thread
+        if ((O & 3) == 0 && On == O) {   // 128-bit row loads, all 8 in flight per thread
             const int kq = tid & 15, k4 = kq << 2;
             float4 xv[8];
 #pragma unroll
@@ -751,10 +785,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     v = __ldcg(raw + (size_t)env * O + k);
                     if (pass && net == 0) sRaw[e * SNW + k] = v;
                     if (norm_on) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v, -mk), sk), -5.f), 5.f);
-                    if (obs_out) obs_out[(size_t)env * O + k] = v;
+                    if (obs_out) obs_out[(size_t)env * On + k] = v;
                 }
                 if constexpr (X3) x3::store1_x3(B0, RX_SUB, x3::off128(e, k), v);
                 else sts(tile_addr(B0, e, k, RTC), tf32r(v));
+            }
+        }
+        if (On != O) {          // Saute: column O of the tile = the safety state (1 on final observations)
+            __syncthreads();    // the staging loop above zero-filled that column
+            if (tid < RTC) {
+                const int env = env0 + tid;
+                float z = 0.f;
+                if (env < N) {
+                    z = pass ? __ldcg(p.sa.safety + (size_t)(t & 1) * N + env) : 1.f;
+                    if (obs_out) obs_out[(size_t)env * On + O] = z;
+                }
+                if constexpr (X3) x3::store1_x3(B0, RX_SUB, x3::off128(tid, O), z);
+                else sts(tile_addr(B0, tid, O, RTC), tf32r(z));
             }
         }
         fence_async_smem();
@@ -1001,7 +1048,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 const float rew = __fadd_rn(1.f, -__fdiv_rn(tot, (float)O));
                 const float cst = (sSn[e_env * SNW] > p.es.cost_threshold) ? 1.f : 0.f;
                 const size_t idx = (size_t)t * N + env;
-                p.sl.rew[idx] = rew;
+                p.sl.rew[idx] = saute_step(p.sa, t, N, env, rew, cst, fin);
                 p.sl.cost[idx] = cst;
                 p.sl.flags[idx] = (uint8_t)((term ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
                 const float erv = __fadd_rn(p.st.ep_ret[env], rew);
@@ -1182,7 +1229,9 @@ __global__ void window_sums_kernel(const float* __restrict__ ring, const int* __
 
 using namespace osb;
 
-static size_t rollout_smem_bytes(int O) {
+static SauteSpec g_saute = {nullptr, 1.f, 1.f, 0.f, 1.f};
+
+static size_t rollout_smem_bytes(int O) {   // O = network input width
     size_t f = NETSMEM_FLOATS_FWD + 3 * RT * LD + RT * LDO + 2 * (size_t)O + RT * OUTP +
                2 * RT * (KC + 1) + 3 * RT;
     return f * sizeof(float);
@@ -1206,7 +1255,7 @@ int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned t
     EnvState st{s_raw, final_raw, ep_step, episode, gstep, ep_ret, ep_cost, ep_len, bias};
     NormState ns{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                  acc_fin, fin_count, had_fin, ticket};
-    env_reset_kernel<<<(N + RT - 1) / RT, NTHREADS, 0, (cudaStream_t)stream>>>(es, st, ns, N);
+    env_reset_kernel<<<(N + RT - 1) / RT, NTHREADS, 0, (cudaStream_t)stream>>>(es, st, ns, g_saute, N);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }
@@ -1214,7 +1263,8 @@ int osb_env_reset(int O, int A, int max_episode_steps, unsigned seed, unsigned t
 static long long* g_rollout_dbg = nullptr;
 
 static int launch_step(StepArgs& p, cudaStream_t stream) {
-    if ((p.precision == 1 || p.precision == 2) && p.es.O <= 64) {
+    const int On = p.es.O + (p.sa.safety ? 1 : 0);
+    if ((p.precision == 1 || p.precision == 2) && On <= 64) {
         const bool x3 = p.precision == 2;
         const size_t smem_tc = rollout_tc_smem_bytes(x3);
         static bool attr_tc = false;
@@ -1240,7 +1290,7 @@ static int launch_step(StepArgs& p, cudaStream_t stream) {
         OSB_LAUNCH_CHECK();
         return OSB_OK;
     }
-    const size_t smem = rollout_smem_bytes(p.es.O);
+    const size_t smem = rollout_smem_bytes(On);
     static size_t attr = 0;
     if (smem > attr) {
         OSB_CUDA(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1249,6 +1299,15 @@ static int launch_step(StepArgs& p, cudaStream_t stream) {
     dim3 grid((p.N + RT - 1) / RT, p.is_tail ? 2 : 3);
     rollout_step_kernel<<<grid, NTHREADS, smem, stream>>>(p);
     OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+// Saute / Simmer mode of the following osb_env_reset / osb_rollout_* calls (process-wide until changed): safety = [2][N]
+// device floats (the safety state z by step parity), or NULL for the plain OnPolicyAdapter semantics.  The networks then
+// take O + 1 inputs ([normalised obs | z]) and the obs slab rows are O + 1 wide.  saute_adapter.py:L135-217.
+int osb_rollout_set_saute(float* safety, float safety_budget, float saute_gamma, float unsafe_reward, float safety_init) {
+    OSB_CHECK_ARG(safety == nullptr || (safety_budget > 0.f && saute_gamma > 0.f), "safety_budget and saute_gamma must be positive");
+    g_saute = SauteSpec{safety, safety_budget, saute_gamma, unsafe_reward, safety_init};
     return OSB_OK;
 }
 
@@ -1274,6 +1333,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
     p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
+    p.sa = g_saute;
     p.theta = theta; p.eps = eps; p.noise_seed = noise_seed; p.global_step = global_step;
     p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0; p.precision = precision;
     p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = nullptr;
@@ -1306,13 +1366,14 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
     p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
+    p.sa = g_saute;
     p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N; p.precision = precision;
     p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = g_rollout_dbg;
     // tensor-core modes with every CTA resident (grid = env tiles x 3 networks <= SMs): one persistent launch per epoch
     static const bool stepwise = getenv("OSB_ROLLOUT_STEPWISE") != nullptr;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; OSB_CUDA(cudaGetDevice(&dev)); OSB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
-    if (!stepwise && (precision == 1 || precision == 2) && O <= 64 && ((N + RTC - 1) / RTC) * 3 <= n_sm) {
+    if (!stepwise && (precision == 1 || precision == 2) && O + (g_saute.safety ? 1 : 0) <= 64 && ((N + RTC - 1) / RTC) * 3 <= n_sm) {
         static unsigned int* d_bar = nullptr;
         if (!d_bar) OSB_CUDA(cudaMalloc(&d_bar, 64));
         p.bar_ctr = d_bar; p.bar_flag = d_bar + 1;

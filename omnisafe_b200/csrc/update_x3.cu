@@ -30,7 +30,7 @@ using namespace x3;
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }      // epilogue warps only
 __device__ __forceinline__ void loss_bar_sync() { asm volatile("bar.sync 2, 128;\n" ::: "memory"); }     // loss warps (h == 0)
 
-enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_COST = 3 };
+enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_COST = 3, X3_FVP = 4 };   // X3_FVP: dOUT supplied (Fisher-vector product)
 
 struct X3Batch {
     const float* obs; const float* act; const float* logp; const float* adv_r; const float* adv_c;
@@ -60,6 +60,9 @@ struct X3Args {
     int world, rank;
     unsigned int step_base;      // exchange step id of this launch's first minibatch (identical on all ranks)
     int* error_flag;
+    const float* fvp_dmu;        // X3_FVP: tangent of mu per slab row [total][A] (fvp_tangent_x3_kernel)
+    const float* fvp_vec;        // X3_FVP: direction v (its log_std block gives the log_std block of F v)
+    float fvp_scale;             // X3_FVP: 1 / (rows * A)
     long long* dbg;              // optional clock64 stamps of CTA (0, 0): [0] = count, then (id, clock) pairs (tools/x3_stage_times.py)
 };
 
@@ -185,6 +188,8 @@ constexpr int PSTR = 9472;          // FUSED: row stride of the private partial-
 //   distributed.py:L193-198), apply torch-Adam and re-stage the new weights: no relaunch, no separate
 //   optimiser kernel.
 // AP = padded action width of the loss epilogue (8 or 16).
+// (17 warps: registers are allocated per 4 warps, so a 544-thread block is sized like 640 threads: 96 registers each;
+//  __maxnreg__(120) compiles but cannot launch)
 template <bool FUSED, int AP>
 __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     if (p.stop_flag && *p.stop_flag) return;
@@ -442,6 +447,30 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 }
                 epi_bar_sync();                                            // next tile's row list is complete
                 stamp(2);
+                // loss warps: this tile's per-sample inputs (used in E3) fly under the forward phases
+                float pf_act[AP], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
+                long long prow = -1;
+                if (h == 0) {
+                    prow = sRow[s_row];
+#pragma unroll
+                    for (int a = 0; a < AP; ++a) pf_act[a] = 0.f;
+                    if (prow >= 0) {
+                        if (net == 0 && p.kind == X3_FVP) {
+#pragma unroll
+                            for (int a = 0; a < AP; ++a)
+                                if (a < A) pf_act[a] = __ldg(p.fvp_dmu + prow * A + a);
+                        } else if (net == 0) {
+#pragma unroll
+                            for (int a = 0; a < AP; ++a)
+                                if (a < A) pf_act[a] = __ldg(p.b.act + prow * A + a);
+                            pf_logp = __ldg(p.b.logp + prow);
+                            pf_advr = __ldg(p.b.adv_r + prow);
+                            pf_advc = __ldg(p.b.adv_c + prow);
+                        } else {
+                            pf_tv = __ldg((net == 1 ? p.b.tv_r : p.b.tv_c) + prow);
+                        }
+                    }
+                }
                 // ---- E1: H1 = tanh(Z1 + b1) -------------------------------------------------------------------
                 mbar_wait_a(bar(DONE_C1), par);
                 tc_fence_after();
@@ -474,22 +503,6 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 stamp(6);
                 // ---- E3: OUT -> loss -> dOUT (warps with h == 0: one thread per sample) -------------------------
                 if (h == 0) {
-                    float pf_act[AP], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
-                    const long long prow = sRow[s_row];
-#pragma unroll
-                    for (int a = 0; a < AP; ++a) pf_act[a] = 0.f;
-                    if (prow >= 0) {
-                        if (net == 0) {
-#pragma unroll
-                            for (int a = 0; a < AP; ++a)
-                                if (a < A) pf_act[a] = __ldg(p.b.act + prow * A + a);
-                            pf_logp = __ldg(p.b.logp + prow);
-                            pf_advr = __ldg(p.b.adv_r + prow);
-                            pf_advc = __ldg(p.b.adv_c + prow);
-                        } else {
-                            pf_tv = __ldg((net == 1 ? p.b.tv_r : p.b.tv_c) + prow);
-                        }
-                    }
                     mbar_wait_a(bar(DONE_C3), par);
                     tc_fence_after();
                     stamp(7);
@@ -513,6 +526,16 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                             acc_st[0] += d * d; acc_st[3] += 1.f;
                             d16[0] = 2.f * d * inv_b;
                             acc_db[0] += d16[0];
+                        } else if (p.kind == X3_FVP) {
+                            // J^T diag(sigma^-2) dmu / (B A): the supplied tangent is the output gradient
+                            acc_st[3] += 1.f;
+#pragma unroll
+                            for (int a = 0; a < AP; ++a)
+                                if (a < A) {
+                                    const float dm = pf_act[a] * sLs[32 + a] * p.fvp_scale;
+                                    d16[a] = dm;
+                                    acc_db[a] += dm;
+                                }
                         } else {
                             float logp_new = 0.f, diff[AP];
 #pragma unroll
@@ -693,6 +716,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     const int a = tid - 32;
                     float g = (sRed[32 + a] + sRed[48 + a]) + (sRed[64 + a] + sRed[80 + a]);
                     if (blockIdx.x == 0 && p.kind == X3_PPO_CLIP) g -= p.entropy_coef / (float)A;
+                    if (p.kind == X3_FVP) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + a) : 0.f;
                     __stcg(gout + L.off_logstd + a, g);
                 }
                 if (tid >= 64 && tid < 72) {
@@ -915,6 +939,25 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
     const bool single = (net_mask & (net_mask - 1)) == 0;
     if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
     else minibatch_grad_x3_kernel<false, 16><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
+    OSB_LAUNCH_CHECK();
+    return OSB_OK;
+}
+
+// backward half of the bf16x3 Fisher-vector product (called by osb_fvp_partials_x3, csrc/fvp_x3.cu)
+int osb_x3_fvp_backward(const float* theta_actor, const float* vec, int O, int A, const float* obs, long long total, int stride,
+                        const float* dmu, float* gpart, float* stats_scratch, void* stream) {
+    const long long nrows = (total + stride - 1) / stride;
+    X3Args p = {};
+    p.b = X3Batch{obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, total, 0u, 0, (int)nrows, stride};
+    p.kind = X3_FVP; p.theta = theta_actor; p.gpart = gpart; p.stats_part = stats_scratch;
+    p.O = O; p.A = A; p.P = actor_layout(O, A).size; p.net_mask = 1;
+    p.batch_size = (int)nrows; p.world = 1; p.dbg = nullptr;
+    p.fvp_dmu = dmu; p.fvp_vec = vec; p.fvp_scale = 1.0f / ((float)nrows * (float)A);
+    const int nb = osb_tc_grid_blocks(nrows, 1);
+    int rc = x3_set_attr();
+    if (rc) return rc;
+    if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
+    else minibatch_grad_x3_kernel<false, 16><<<dim3(nb, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();
     return OSB_OK;
 }

@@ -91,3 +91,16 @@ def check_all_configs(cfgs: Config) -> None:
     assert isinstance(t.vector_env_nums, int) and t.vector_env_nums >= 1
     assert isinstance(t.parallel, int) and t.parallel >= 1
     assert t.total_steps >= a.steps_per_epoch, 'total_steps must cover at least one epoch'
+    # upstream keys the fused path does not implement: refuse the settings that would change behaviour, say so for the rest
+    m = getattr(cfgs, 'model_cfgs', None)
+    if m is not None and getattr(m, 'exploration_noise_anneal', False):
+        raise NotImplementedError('model_cfgs.exploration_noise_anneal=True is not implemented on the fused path '
+                                  '(the Gaussian actor keeps its learned log_std)')
+    if getattr(a, 'fvp_sample_freq', 1) != 1:
+        # the reference subsamples the env-major batch (obs[::freq]); the slabs are time-major, so a stride would pick a
+        # different sample set
+        raise NotImplementedError('algo_cfgs.fvp_sample_freq != 1 is not implemented on the fused path')
+    lg = getattr(cfgs, 'logger_cfgs', None)
+    if lg is not None and (getattr(lg, 'use_wandb', False)):
+        import warnings
+        warnings.warn('logger_cfgs.use_wandb is ignored by omnisafe_b200 (progress.csv / config.json / torch_save only)', stacklevel=2)

@@ -177,11 +177,13 @@ def test_update_epoch_vs_oracle_early_stop_and_feistel(cuda):
     np.testing.assert_allclose(a1.theta.cpu().numpy(), a2.theta.cpu().numpy(), rtol=1e-4, atol=1e-6)
 
 
-def test_fvp_cg_eval_golden(cuda, golden_dir):
+@pytest.mark.parametrize('precision', [0, 2])      # exact fp32 FMA tiles / split-bf16 tensor-core tiles: same bar
+def test_fvp_cg_eval_golden(cuda, golden_dir, precision):
     g = np.load(os.path.join(golden_dir, 'update_cpo.npz'))
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
     N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
     agent, buf, eng = _setup(cuda, data, N, T, O, A, g['theta0'], lr_actor=None, lr_critic=1e-3)
+    eng.precision = precision
     vec = torch.as_tensor(g['vec']).to(cuda)
     out = torch.zeros_like(vec)
     eng.fvp(vec, out, float(g['cg_damping']))
