@@ -84,7 +84,9 @@ constexpr uint32_t OFF_BARS = OFF_ROWS + 2 * XT * 8;                 // uint64 [
 enum Bar { RDY_X0 = 0, RDY_X1, RDY_H1_0, RDY_H1_1, RDY_H2_0, RDY_H2_1, RDY_D, RDY_DZ2_0, RDY_DZ2_1, RDY_DZ1,
            DONE_C1, DONE_C2, DONE_C3, DONE_C4A, DONE_C4B, DONE_C5A, DONE_C5B, DONE_C6, NBAR };
 constexpr uint32_t OFF_TMEMSLOT = OFF_BARS + NBAR * 8;
-constexpr uint32_t X3_SMEM = OFF_TMEMSLOT + 16;
+constexpr uint32_t OFF_PF = OFF_TMEMSLOT + 16;                        // float [128][12]: per-sample loss inputs (AP == 8), copied asynchronously
+constexpr int PF_LD = 12;
+constexpr uint32_t X3_SMEM = OFF_PF + XT * PF_LD * 4;
 // TMEM columns
 constexpr uint32_t T_ZA = 0, T_ZB = 64, T_OUT = 128, T_DW1 = 144, T_DW2 = 208, T_DW3 = 272, T_DB1 = 288, T_DB2 = 304, T_COLS = 512;
 
@@ -447,7 +449,8 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 }
                 epi_bar_sync();                                            // next tile's row list is complete
                 stamp(2);
-                // loss warps: this tile's per-sample inputs (used in E3) fly under the forward phases
+                // loss warps: this tile's per-sample inputs (used in E3) fly under the forward phases -- asynchronously into
+                // shared memory when they fit (AP == 8), so that no register has to wait for them
                 float pf_act[AP], pf_logp = 0.f, pf_advr = 0.f, pf_advc = 0.f, pf_tv = 0.f;
                 long long prow = -1;
                 if (h == 0) {
@@ -455,17 +458,25 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
 #pragma unroll
                     for (int a = 0; a < AP; ++a) pf_act[a] = 0.f;
                     if (prow >= 0) {
-                        if (net == 0 && p.kind == X3_FVP) {
+                        const float* asrc = (p.kind == X3_FVP) ? p.fvp_dmu : p.b.act;
+                        if (AP == 8) {
+                            const uint32_t dst = sbase + OFF_PF + (uint32_t)(s_row * PF_LD) * 4u;
+                            auto cp4 = [&](uint32_t d, const float* src) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+                            };
+                            if (net == 0) {
 #pragma unroll
-                            for (int a = 0; a < AP; ++a)
-                                if (a < A) pf_act[a] = __ldg(p.fvp_dmu + prow * A + a);
+                                for (int a = 0; a < AP; ++a)
+                                    if (a < A) cp4(dst + 4u * a, asrc + prow * A + a);
+                                if (p.kind != X3_FVP) { cp4(dst + 32u, p.b.logp + prow); cp4(dst + 36u, p.b.adv_r + prow); cp4(dst + 40u, p.b.adv_c + prow); }
+                            } else {
+                                cp4(dst + 32u, (net == 1 ? p.b.tv_r : p.b.tv_c) + prow);
+                            }
                         } else if (net == 0) {
 #pragma unroll
                             for (int a = 0; a < AP; ++a)
-                                if (a < A) pf_act[a] = __ldg(p.b.act + prow * A + a);
-                            pf_logp = __ldg(p.b.logp + prow);
-                            pf_advr = __ldg(p.b.adv_r + prow);
-                            pf_advc = __ldg(p.b.adv_c + prow);
+                                if (a < A) pf_act[a] = __ldg(asrc + prow * A + a);
+                            if (p.kind != X3_FVP) { pf_logp = __ldg(p.b.logp + prow); pf_advr = __ldg(p.b.adv_r + prow); pf_advc = __ldg(p.b.adv_c + prow); }
                         } else {
                             pf_tv = __ldg((net == 1 ? p.b.tv_r : p.b.tv_c) + prow);
                         }
@@ -503,6 +514,20 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 stamp(6);
                 // ---- E3: OUT -> loss -> dOUT (warps with h == 0: one thread per sample) -------------------------
                 if (h == 0) {
+                    if (AP == 8) {
+                        asm volatile("cp.async.wait_all;\n" ::: "memory");
+                        const float* pf = reinterpret_cast<const float*>(gbase + OFF_PF) + s_row * PF_LD;
+                        if (prow >= 0) {
+                            if (net == 0) {
+#pragma unroll
+                                for (int a = 0; a < AP; ++a)
+                                    if (a < A) pf_act[a] = pf[a];
+                                pf_logp = pf[8]; pf_advr = pf[9]; pf_advc = pf[10];
+                            } else {
+                                pf_tv = pf[8];
+                            }
+                        }
+                    }
                     mbar_wait_a(bar(DONE_C3), par);
                     tc_fence_after();
                     stamp(7);
