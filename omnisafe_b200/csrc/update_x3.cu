@@ -55,7 +55,7 @@ struct X3Args {
     float* sumsq_part;           // [3][2][gridDim.x]
     float* train_stats;          // [3][8]
     unsigned int* bar_ctr;       // [3] per-network grid barrier counters, zero at launch
-    float* const* peer_buf;      // [world] receive buffers, each [2][world][P] (pushed over NVLink), or null
+    float* const* peer_buf;      // [world] receive buffers, each [2][world][P] 8-byte words {step tag, value} (pushed over NVLink), or null
     unsigned int* const* peer_flag;   // [world] flag arrays, each [2 * world + 2 * world * 160]
     int world, rank;
     unsigned int step_base;      // exchange step id of this launch's first minibatch (identical on all ranks)
@@ -840,51 +840,42 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
             const float clipc = sScal[0], step_size = sScal[8], bc2_sqrt = sScal[9];
             const unsigned int xstep = p.step_base + (unsigned int)mb;
             const int xpar = (int)(xstep & 1u);
-            const int cta_g = (gridDim.y == 1 ? 0 : net) * G + (int)blockIdx.x;
-            bool xfail = false;
-            if (p.world > 1) {
-                // push the clipped slice into every rank's receive buffer [parity][source rank][P], then raise this
-                // CTA's flag on every rank; the slices of different CTAs travel independently (no grid barrier)
-                for (int base = 0; base < S; base += NEPI) {
-                    const int pi = base + tid;
-                    if (pi < S && p0 + pi < L.size) {
-                        const int qg = noff + p0 + pi;
-                        const float gc = __ldcg(p.grad + qg) * clipc;
+                    // clip -> average over ranks -> Adam (policy_gradient.py:L437-443, distributed.py:L193-198).  world > 1: every
+            // parameter of the slice travels as ONE 8-byte word {step tag, clipped gradient} stored straight into every peer's
+            // receive buffer [parity][source rank][P] over NVLink; the receiver spins on the tag of each word -- data and
+            // flag arrive together, so there is no fence, no flag round and no barrier in the exchange.
+            for (int base = 0; base < S; base += NEPI) {
+                const int pi = base + tid;
+                if (pi < S && p0 + pi < L.size) {
+                    const int qg = noff + p0 + pi;
+                    float g = __ldcg(p.grad + qg) * clipc;
+                    bool fail = false;
+                    if (p.world > 1) {
+                        const unsigned long long word = ((unsigned long long)xstep << 32) | (unsigned long long)__float_as_uint(g);
+                        const size_t slot = ((size_t)(xpar * p.world + p.rank)) * p.P + qg;
                         for (int r = 0; r < p.world; ++r)
-                            asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peer_buf[r] + ((size_t)(xpar * p.world + p.rank)) * p.P + qg), "f"(gc) : "memory");
-                    }
-                }
-                __threadfence_system();
-                epi_bar_sync();
-                if (tid < p.world) {
-                    const int fbase = 2 * p.world + (xpar * p.world) * 160;
-                    st_release_sys_u32(p.peer_flag[tid] + fbase + p.rank * 160 + cta_g, xstep);
-                    const unsigned int* f = p.peer_flag[p.rank] + fbase + tid * 160 + cta_g;
-                    const long long t0 = clock64();
-                    while (ld_acquire_sys_u32(f) != xstep) {
-                        if (clock64() - t0 > 20000000000LL) { *p.error_flag = 1; sScal[0] = -1.f; break; }   // ~10 s: fail loudly, never hang the GPU
-                    }
-                }
-                epi_bar_sync();
-                xfail = sScal[0] < 0.f;
-            }
-            if (!xfail) {
-                for (int base = 0; base < S; base += NEPI) {
-                    const int pi = base + tid;
-                    if (pi < S && p0 + pi < L.size) {
-                        const int qg = noff + p0 + pi;
-                        float g;
-                        if (p.world > 1) {
-                            float sum = 0.f;
-                            for (int r = 0; r < p.world; ++r) {
-                                float v;
-                                asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p.peer_buf[p.rank] + ((size_t)(xpar * p.world + r)) * p.P + qg) : "memory");
-                                sum += v;
+                            if (r != p.rank)
+                                asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(p.peer_buf[r]) + slot), "l"(word) : "memory");
+                        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.peer_buf[p.rank]);
+                        float sum = 0.f;
+                        const long long t0 = clock64();
+                        for (int r = 0; r < p.world; ++r) {
+                            float v = g;
+                            if (r != p.rank) {
+                                const unsigned long long* src = mine + ((size_t)(xpar * p.world + r)) * p.P + qg;
+                                unsigned long long w64;
+                                for (;;) {
+                                    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w64) : "l"(src) : "memory");
+                                    if ((unsigned int)(w64 >> 32) == xstep) break;
+                                    if (clock64() - t0 > 20000000000LL) { *p.error_flag = 1; fail = true; break; }   // ~10 s: fail loudly, never hang the GPU
+                                }
+                                v = __uint_as_float((unsigned int)w64);
                             }
-                            g = sum / (float)p.world;
-                        } else {
-                            g = __ldcg(p.grad + qg) * clipc;
+                            sum += v;
                         }
+                        g = sum / (float)p.world;
+                    }
+                    if (!fail) {
                         __stcg(p.grad + qg, g);
                         const bool pre = base == 0;                     // first chunk: state prefetched before the barrier
                         const float th = pre ? pre_th : __ldcg(p.theta_rw + qg);

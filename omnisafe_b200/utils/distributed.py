@@ -97,7 +97,8 @@ def p2p_exchange(n_params: int):
     ptrs = []
     # receive buffers [2][world][P] (the persistent bf16x3 kernel pushes slices; the per-step kernel uses the first
     # [2][P]); flags: [2][world] (per-step kernel) + [2][world][160] (one flag per CTA of the persistent kernel)
-    for nbytes in (2 * w * n_params * 4, (2 * w + 2 * w * 160) * 4):
+    # (8 bytes per parameter slot: the persistent kernel sends {step tag, value} words)
+    for nbytes in (2 * w * n_params * 8, (2 * w + 2 * w * 160) * 4):
         mine = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         lib().osb_p2p_alloc(nbytes, ctypes.byref(mine), handle)
