@@ -124,6 +124,11 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
  * z <- (z - cost / safety_budget) / saute_gamma per step, the stored reward is unsafe_reward once z <= 0, z <- 1 at
  * episode ends.  Process-wide until changed. */
 int osb_rollout_set_saute(float* safety, float safety_budget, float saute_gamma, float unsafe_reward, float safety_init);
+/* EarlyTerminated mode of the following osb_rollout_* calls (EarlyTerminatedAdapter.step,
+ * adapter/early_terminated_adapter.py:L56-98, per env): cost_acc = [N] device floats holding the accumulated cost (not cleared
+ * by ordinary episode ends) or NULL; once it exceeds cost_limit the step stores reward 0 and terminated = 1, the env is reset
+ * and the accumulator cleared.  Process-wide until changed. */
+int osb_rollout_set_early_termination(float* cost_acc, float cost_limit);
 /* Logger window of the last <= W finished episodes in (step, env) order
  * (common/logger.py:L253-282, adapter/onpolicy_adapter.py:L159-175).  ring[3][W], meta[2] persist
  * across epochs; window_sums[4] <- {sum EpRet, sum EpCost, sum EpLen, count} (fp64). */

@@ -15,6 +15,7 @@ import time
 import torch
 
 from omnisafe_b200.adapter.onpolicy_adapter import OnPolicyAdapter
+from omnisafe_b200.adapter.early_terminated_adapter import EarlyTerminatedAdapter
 from omnisafe_b200.adapter.saute_adapter import SauteAdapter
 from omnisafe_b200.adapter.simmer_adapter import SimmerAdapter
 from omnisafe_b200.algorithms import registry
@@ -639,5 +640,27 @@ class TRPOSimmerPID(_SimmerMixin, TRPO):
     """simmer/trpo_simmer_pid.py."""
 
 
+class _EarlyTerminatedMixin:
+    """early_terminated/ppo_early_terminated.py:L43-66, early_terminated/trpo_early_terminated.py."""
+
+    def _init_env(self) -> None:
+        t, a = self._cfgs.train_cfgs, self._cfgs.algo_cfgs
+        rank = distributed.get_rank()
+        self._env = EarlyTerminatedAdapter(self._env_id, t.vector_env_nums, self._seed, self._cfgs, device=self._device,
+                                           env_id_offset=rank * t.vector_env_nums)
+        self._steps_per_epoch = distributed.local_steps(a.steps_per_epoch, t.vector_env_nums)
+
+
+@registry.register
+class PPOEarlyTerminated(_EarlyTerminatedMixin, PPO):
+    """early_terminated/ppo_early_terminated.py:L28-66."""
+
+
+@registry.register
+class TRPOEarlyTerminated(_EarlyTerminatedMixin, TRPO):
+    """early_terminated/trpo_early_terminated.py."""
+
+
 ON_POLICY = ['PolicyGradient', 'PPO', 'PPOLag', 'PDO', 'IPO', 'P3O', 'NaturalPG', 'RCPO', 'TRPO', 'TRPOLag', 'CPO', 'PCPO',
-             'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO', 'PPOSaute', 'TRPOSaute', 'PPOSimmerPID', 'TRPOSimmerPID']
+             'FOCOPS', 'CPPOPID', 'TRPOPID', 'OnCRPO', 'PPOSaute', 'TRPOSaute', 'PPOSimmerPID', 'TRPOSimmerPID',
+             'PPOEarlyTerminated', 'TRPOEarlyTerminated']

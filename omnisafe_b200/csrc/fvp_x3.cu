@@ -107,28 +107,39 @@ __global__ void __launch_bounds__(FNT, 1) fvp_tangent_x3_kernel(FvpX3Args p) {
     const bool vec4 = (O & 3) == 0;
     const int s_row = 32 * q + lane;
 
+    // the rows of a tile are gathered into registers one tile ahead (under the layer-2 / layer-3 phases of the previous tile)
+    float xpre[32];
+    long long row_pre = -1;
+    auto gather = [&](long long tile) {
+        const long long k = tile * FT + xm;
+        row_pre = (tile < ntiles && k < nrows) ? k * p.stride : -1;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const int c0 = xh + 8 * c8;
+            if (vec4) {
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4) {
+                    const int c = c0 + 4 * v4;
+                    const float4 x = (row_pre >= 0 && c < O) ? __ldg(reinterpret_cast<const float4*>(p.obs + row_pre * O + c))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xpre[8 * c8 + 4 * v4] = x.x; xpre[8 * c8 + 4 * v4 + 1] = x.y; xpre[8 * c8 + 4 * v4 + 2] = x.z; xpre[8 * c8 + 4 * v4 + 3] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xpre[8 * c8 + i] = (row_pre >= 0 && c0 + i < O) ? __ldg(p.obs + row_pre * O + c0 + i) : 0.f;
+            }
+        }
+    };
+    gather(blockIdx.x);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         {   // X tile (the previous tile's MMAs have completed: both buffers are free)
-            const long long k = tile * FT + xm;
-            const long long row = (k < nrows) ? k * p.stride : -1;
-            if ((tid & 1) == 0) sRow[xm] = row;
+            if ((tid & 1) == 0) sRow[xm] = row_pre;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 float v[8];
-                const int c0 = xh + 8 * c8;
-                if (vec4) {
 #pragma unroll
-                    for (int v4 = 0; v4 < 2; ++v4) {
-                        const int c = c0 + 4 * v4;
-                        const float4 x = (row >= 0 && c < O) ? __ldg(reinterpret_cast<const float4*>(p.obs + row * O + c))
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[4 * v4] = x.x; v[4 * v4 + 1] = x.y; v[4 * v4 + 2] = x.z; v[4 * v4 + 3] = x.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (row >= 0 && c0 + i < O) ? __ldg(p.obs + row * O + c0 + i) : 0.f;
-                }
-                store8_x3(sbase + FO_A0, F_SUB, xm, c0, v);
+                for (int i = 0; i < 8; ++i) v[i] = xpre[8 * c8 + i];
+                store8_x3(sbase + FO_A0, F_SUB, xm, xh + 8 * c8, v);
             }
         }
         fence_async_smem();
@@ -169,6 +180,7 @@ __global__ void __launch_bounds__(FNT, 1) fvp_tangent_x3_kernel(FvpX3Args p) {
             if (leader) mma_commit_a(bar);
             __syncwarp();
         }
+        gather(tile + gridDim.x);                            // next tile's rows fly under layers 2 and 3
         mbar_wait_a(bar, phase); phase ^= 1;
         tc_fence_after();
 #pragma unroll

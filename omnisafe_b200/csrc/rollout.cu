@@ -58,6 +58,14 @@ struct SauteSpec {
     float init;          // z at the epoch's reset: 1 (Saute) or the relative budget (Simmer)
 };
 
+// EarlyTerminatedAdapter.step (adapter/early_terminated_adapter.py:L56-98), per env: the accumulated cost (never cleared
+// by ordinary episode ends) exceeding cost_limit terminates the episode: reward 0, terminated = 1, the env is reset and
+// the accumulator cleared.
+struct EarlySpec {
+    float* cost_acc;     // [N] or null
+    float cost_limit;
+};
+
 struct NormState {
     float* mean;    // [O] running mean            (Normalizer._mean)
     float* sumsq;   // [O] running sum of squares  (Normalizer._sumsq)
@@ -259,6 +267,7 @@ struct StepArgs {
     NormState ns;
     Slabs sl;
     SauteSpec sa;
+    EarlySpec et;
     const float* theta;   // flat [actor | critic_r | critic_c]
     const float* eps;     // [N][A] noise of this step (parity mode) or null (Philox fast mode)
     uint32_t noise_seed;
@@ -297,6 +306,13 @@ __device__ __forceinline__ void load_obs_tile(const float* __restrict__ raw, int
         }
         sX[e * LD + k] = v;
     }
+}
+
+// cost of this step (indicator on the next value of state dim 0) from the current raw state and the sampled action
+__device__ __forceinline__ float env_step_cost(const EnvSpec& es, float s0, float act0, float bias0) {
+    float a = __fadd_rn(__fadd_rn(act0, 1.f), -1.f);
+    a = fminf(fmaxf(a, -1.f), 1.f);
+    return (env_next_value(s0, a, bias0) > es.cost_threshold) ? 1.f : 0.f;
 }
 
 // SauteAdapter.step (saute_adapter.py:L172-217) for one env: z <- (z - cost / budget) / gamma, reward override once
@@ -453,7 +469,15 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
         const bool trunc = ok && (ep_step + 1 >= p.es.max_episode_steps);
         const bool term = ok && p.es.term_threshold != 0u &&
                           hash4(p.es.seed ^ 0xA5A5A5A5u, gid, gstep, 0xFFFFu) < p.es.term_threshold;
-        const bool fin = term || trunc;
+        const bool fin_env = term || trunc;               // the env's own episode end
+        bool early = false;                               // EarlyTerminated: accumulated cost over the limit
+        float acc_cost = 0.f;
+        if (ok && p.et.cost_acc) {
+            acc_cost = __fadd_rn(p.et.cost_acc[env], env_step_cost(p.es, s_cur[(size_t)env * O], sAct[e * OUTP], __ldg(p.st.bias)));
+            early = acc_cost > p.et.cost_limit;
+        }
+        const bool fin = fin_env || early;
+        const uint32_t epi_inc = (fin_env && early) ? 2u : 1u;   // the env's auto-reset and then the adapter's reset
         float part = 0.f, s0n = 0.f;
         float* finrow = p.st.final_raw + ((size_t)(t & 1) * N + (ok ? env : 0)) * O;
         for (int c0 = 0; c0 < O; c0 += KC) {
@@ -469,7 +493,7 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
                     part = __fadd_rn(part, __fmul_rn(sn, sn));
                     if (j == 0) s0n = sn;
                     fv = sn;
-                    nv = fin ? env_reset_value(p.es, gid, epi + 1u, j) : sn;
+                    nv = fin ? env_reset_value(p.es, gid, epi + epi_inc, j) : sn;
                     s_nxt[(size_t)env * O + j] = nv;
                     if (fin) finrow[j] = sn;
                 }
@@ -506,12 +530,13 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
         part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 2));
         part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 4));
         if (ok && q == 0) {
-            const float rew = __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
+            const float rew = early ? 0.f : __fadd_rn(1.f, -__fdiv_rn(part, (float)O));
             const float cst = (s0n > p.es.cost_threshold) ? 1.f : 0.f;
             const size_t idx = (size_t)t * N + env;
             p.sl.rew[idx] = saute_step(p.sa, t, N, env, rew, cst, fin);
             p.sl.cost[idx] = cst;
-            p.sl.flags[idx] = (uint8_t)((term ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
+            p.sl.flags[idx] = (uint8_t)(((term || early) ? OSB_FLAG_TERMINATED : 0u) | (trunc ? OSB_FLAG_TRUNCATED : 0u));
+            if (p.et.cost_acc) p.et.cost_acc[env] = early ? 0.f : acc_cost;
             // adapter bookkeeping: _log_value, _log_metrics, _reset_log (onpolicy_adapter.py:L138-175)
             const float er = __fadd_rn(p.st.ep_ret[env], rew);
             const float ec = __fadd_rn(p.st.ep_cost[env], cst);
@@ -522,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS) rollout_step_kernel(StepArgs p) {
                 p.sl.epfin[TN + idx] = ec;
                 p.sl.epfin[2 * TN + idx] = (float)el;
                 p.st.ep_ret[env] = 0.f; p.st.ep_cost[env] = 0.f; p.st.ep_len[env] = 0;
-                p.st.episode[env] = epi + 1u;
+                p.st.episode[env] = epi + epi_inc;
                 p.st.ep_step[env] = 0;
             } else {
                 p.st.ep_ret[env] = er; p.st.ep_cost[env] = ec; p.st.ep_len[env] = el;
@@ -590,6 +615,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
     int* sStep = reinterpret_cast<int*>(sEpi + RTC);                    // [128] step inside the episode
     uint32_t* sGstep = reinterpret_cast<uint32_t*>(sStep + RTC);        // [128] total steps of the env (termination hash counter)
     float* sSd = reinterpret_cast<float*>(sGstep + RTC);                // [3][16] sigma, 2 sigma^2, log sigma per action
+    float* sEarlyAcc = sSd + 48;                                        // [128] accumulated cost incl. this step (EarlyTerminated)
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ int s_last, s_anyfin;
@@ -985,6 +1011,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
             }
         }
         __syncthreads();
+        if (p.et.cost_acc) {      // EarlyTerminated: the step's cost is known from state dim 0 -> finish flags before the transition
+            if (tid < RTC && env0 + tid < N) {
+                const int env = env0 + tid;
+                const float acc = __fadd_rn(p.et.cost_acc[env], env_step_cost(p.es, sRaw[tid * SNW], sAct[tid * OUTP], __ldg(p.st.bias)));
+                if (acc > p.et.cost_limit) sFlag[tid] |= ((sFlag[tid] & 1) ? 16 : 0) | 1 | 2 | 8;   // bit 3 early, bit 4 both ends at once
+                sEarlyAcc[tid] = acc;
+            }
+            __syncthreads();
+        }
         RSTAMP(7);
         // ---- env transition + normaliser sums, elementwise: thread -> (dim j = tid % 64, env quarter g = tid / 64).
         //      The raw state comes from shared memory (kept by the obs staging), the next state goes out in whole
@@ -1007,7 +1042,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                         const int fl = sFlag[e];
                         float nv = sn;
                         if (fl & 1) {
-                            nv = env_reset_value(p.es, p.es.env_id_offset + env, sEpi[e] + 1u, j);
+                            nv = env_reset_value(p.es, p.es.env_id_offset + env, sEpi[e] + ((fl & 16) ? 2u : 1u), j);
                             p.st.final_raw[((size_t)(t & 1) * N + env) * O + j] = sn;
                             fx += to_fix(sn); fxx += to_fix(__fmul_rn(sn, sn));
                         }
@@ -1045,8 +1080,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 const int fl = sFlag[e_env];
                 const bool fin = fl & 1, term = fl & 2, trunc = fl & 4;
                 const uint32_t epi = sEpi[e_env];
-                const float rew = __fadd_rn(1.f, -__fdiv_rn(tot, (float)O));
+                const bool early = fl & 8;
+                const float rew = early ? 0.f : __fadd_rn(1.f, -__fdiv_rn(tot, (float)O));
                 const float cst = (sSn[e_env * SNW] > p.es.cost_threshold) ? 1.f : 0.f;
+                if (p.et.cost_acc) p.et.cost_acc[env] = early ? 0.f : sEarlyAcc[e_env];
                 const size_t idx = (size_t)t * N + env;
                 p.sl.rew[idx] = saute_step(p.sa, t, N, env, rew, cst, fin);
                 p.sl.cost[idx] = cst;
@@ -1060,7 +1097,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                     p.sl.epfin[TN + idx] = ecv;
                     p.sl.epfin[2 * TN + idx] = (float)el;
                     p.st.ep_ret[env] = 0.f; p.st.ep_cost[env] = 0.f; p.st.ep_len[env] = 0;
-                    p.st.episode[env] = epi + 1u;
+                    p.st.episode[env] = epi + ((fl & 16) ? 2u : 1u);
                     p.st.ep_step[env] = 0;
                 } else {
                     p.st.ep_ret[env] = erv; p.st.ep_cost[env] = ecv; p.st.ep_len[env] = el;
@@ -1127,7 +1164,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 static size_t rollout_tc_smem_bytes(bool x3) {
     return 1024 + (x3 ? RTC_FOFF_X3 : RTC_FOFF_TF32) +
            (64 + 64 + 16 + 64 + 64 + RTC * OUTP + 2 * RTC * SNW) * sizeof(float) + 4 * 4 * 64 * sizeof(long long) +
-           4 * RTC * sizeof(int) + 48 * sizeof(float) + 64;
+           5 * RTC * sizeof(int) + 48 * sizeof(float) + 64;
 }
 
 // Window of the last <= W finished episodes in (step, env) append order: Logger deque semantics
@@ -1230,6 +1267,7 @@ __global__ void window_sums_kernel(const float* __restrict__ ring, const int* __
 using namespace osb;
 
 static SauteSpec g_saute = {nullptr, 1.f, 1.f, 0.f, 1.f};
+static EarlySpec g_early = {nullptr, 0.f};
 
 static size_t rollout_smem_bytes(int O) {   // O = network input width
     size_t f = NETSMEM_FLOATS_FWD + 3 * RT * LD + RT * LDO + 2 * (size_t)O + RT * OUTP +
@@ -1311,6 +1349,13 @@ int osb_rollout_set_saute(float* safety, float safety_budget, float saute_gamma,
     return OSB_OK;
 }
 
+// EarlyTerminated mode of the following osb_rollout_* calls (process-wide until changed): cost_acc = [N] device floats
+// (per-env accumulated cost, persistent across episodes and epochs) or NULL.  early_terminated_adapter.py:L56-98.
+int osb_rollout_set_early_termination(float* cost_acc, float cost_limit) {
+    g_early = EarlySpec{cost_acc, cost_limit};
+    return OSB_OK;
+}
+
 // development aid: clock64 stamps of the persistent rollout kernel go to buf (1024 long long), NULL turns it off
 int osb_rollout_debug_buffer(long long* buf) { g_rollout_dbg = buf; return OSB_OK; }
 
@@ -1333,7 +1378,7 @@ int osb_rollout_step(int O, int A, int max_episode_steps, unsigned seed, unsigne
     p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
-    p.sa = g_saute;
+    p.sa = g_saute; p.et = g_early;
     p.theta = theta; p.eps = eps; p.noise_seed = noise_seed; p.global_step = global_step;
     p.t = t; p.T = T; p.N = N; p.is_tail = (t == T) ? 1 : 0; p.precision = precision;
     p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = nullptr;
@@ -1366,7 +1411,7 @@ int osb_rollout_epoch(int O, int A, int max_episode_steps, unsigned seed, unsign
     p.ns = NormState{norm_mean, norm_sumsq, norm_std, norm_mean1, norm_std1, norm_count, acc_all,
                      acc_fin, fin_count, had_fin, ticket};
     p.sl = Slabs{obs, act, logp, rew, cost, val_r, val_c, boot_r, boot_c, flags, epfin};
-    p.sa = g_saute;
+    p.sa = g_saute; p.et = g_early;
     p.theta = theta; p.noise_seed = noise_seed; p.T = T; p.N = N; p.precision = precision;
     p.bar_ctr = nullptr; p.bar_flag = nullptr; p.dbg = g_rollout_dbg;
     // tensor-core modes with every CTA resident (grid = env tiles x 3 networks <= SMs): one persistent launch per epoch

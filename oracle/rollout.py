@@ -24,7 +24,7 @@ def action_scale(act, lo=-1.0, hi=1.0, mn=-1.0, mx=1.0):
     return (F32(lo) + t).astype(F32)
 
 
-def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_state=None, saute=None):
+def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_state=None, saute=None, early=None):
     """Returns time-major slabs (dict of [T, N, ...] float32 arrays + uint8 flags).
 
     `eps` is the [T, N, A] standard-normal stream; `window` (list) receives (EpRet, EpCost, EpLen)
@@ -35,7 +35,12 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
     state z], z starts at 1, z <- (z - cost / budget) / gamma after every step, the stored reward becomes
     `unsafe_reward` once z <= 0, z returns to 1 when the episode ends (so final observations carry z = 1,
     as in the reference); episode returns keep the original reward.  'z0' (Simmer, adapter/simmer_adapter.py:L97-111)
-    is the value z takes at the epoch's reset, the relative safety budget; episode ends still reset it to 1.  `theta` is then sized for O + 1 inputs."""
+    is the value z takes at the epoch's reset, the relative safety budget; episode ends still reset it to 1.  `theta` is then sized for O + 1 inputs.
+
+    `early` = {'cost_limit': c, 'acc': float32 array [N]} switches on EarlyTerminatedAdapter.step
+    (adapter/early_terminated_adapter.py:L56-98; upstream single env, here per env): the accumulated cost -- never cleared by
+    ordinary episode ends -- exceeding the limit stores reward 0, terminates the episode and resets the env (a second reset
+    when the env's own episode ended in the same step); the normaliser sees the pre-reset state and then the reset one."""
     N, O, A = env.N, env.O, env.A
     On = O + (1 if saute else 0)                     # network input width
     z = np.full((N, 1), F32(saute.get('z0', 1.0)) if saute else F32(1), F32)   # Simmer starts an epoch at the relative budget
@@ -53,6 +58,21 @@ def rollout_epoch(env, norm, theta, T, eps, obs_normalize=True, window=None, ep_
     for t in range(T):
         act, v_r, v_c, logp = ac.step(theta, obs, eps[t], On, A)
         nraw, rew, cost, term, trunc, final_raw, fin = env.step(action_scale(act))
+        if early is not None:
+            early['acc'] = (early['acc'] + cost).astype(F32)
+            ex = early['acc'] > F32(early['cost_limit'])
+            if ex.any():
+                rew = np.where(ex, F32(0), rew).astype(F32)
+                only = ex & ~fin                                  # the env itself did not end: its next obs is the pre-reset state
+                final_raw = np.where(only[:, None], nraw, final_raw).astype(F32)
+                with np.errstate(over='ignore'):
+                    env.episode = np.where(ex, env.episode + np.uint32(1), env.episode).astype(np.uint32)
+                env.ep_step = np.where(ex, 0, env.ep_step).astype(np.int32)
+                env.s = np.where(ex[:, None], env._reset_values(env.episode), env.s).astype(F32)
+                nraw = env.s.copy()
+                term = term | ex
+                fin = fin | ex
+                early['acc'] = np.where(ex, F32(0), early['acc']).astype(F32)
         final_norm = np.zeros((N, O), F32)
         if fin.any():
             final_norm[fin] = norm.normalize(final_raw[fin]) if obs_normalize else final_raw[fin]

@@ -126,7 +126,8 @@ class RefSyntheticBox(CMDP):
     def reset(self, seed=None, options=None):
         if self._env is None:
             self.set_seed(self._seed)
-        return torch.as_tensor(self._env.reset()), {}
+        obs = torch.as_tensor(self._env.reset())
+        return (obs[0] if self._num_envs == 1 else obs), {}     # a single env is unbatched (the reference adds Unsqueeze)
 
     def step(self, action):
         if action.dim() == 1:      # the Evaluator drives a single env with an unbatched action
@@ -136,8 +137,11 @@ class RefSyntheticBox(CMDP):
         if fin.any():
             info['final_observation'] = torch.as_tensor(final.copy())
             info['_final_observation'] = torch.as_tensor(fin)
-        return (torch.as_tensor(nobs), torch.as_tensor(rew), torch.as_tensor(cost),
-                torch.as_tensor(term), torch.as_tensor(trunc), info)
+        out = (torch.as_tensor(nobs), torch.as_tensor(rew), torch.as_tensor(cost), torch.as_tensor(term), torch.as_tensor(trunc))
+        if self._num_envs == 1:
+            out = tuple(x[0] for x in out)
+            info = {k: v[0] for k, v in info.items()}
+        return (*out, info)
 
     def render(self):
         return None
@@ -182,13 +186,13 @@ def _flat_theta(ac):
     return torch.cat(parts).numpy().copy()
 
 
-def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled=1, extra_algo=None):
+def gen_rollout(name='PPOLag', fname='rollout_ppolag.npz', seed=5, epochs_rolled=1, extra_algo=None, N=8, T=24):
     """Epoch(s) of the unmodified OnPolicyAdapter.rollout + buffer on the synthetic env.  PDO's defaults
     switch RewardNormalize / CostNormalize on (PDO.yaml:L44-46): the slabs then hold normalised values."""
     import torch.distributions.normal as tdn
     import torch.distributions.utils as tdu
 
-    N, T, O, A = 8, 24, 12, 3
+    O, A = 12, 3
     algo = _build_algo(name, N, T, O, A, seed, epochs=2, extra_algo=extra_algo)
     theta = _flat_theta(algo._actor_critic)
     drawn = []

@@ -393,6 +393,29 @@ def test_simmer_controller_and_rollout_golden(golden_dir):
     np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], rtol=1e-5, atol=1e-5)
 
 
+def test_rollout_early_terminated_golden(golden_dir):
+    """Oracle rollout with the EarlyTerminatedAdapter semantics (accumulated cost over the limit: reward 0, terminated,
+    env reset; the accumulator survives ordinary episode ends) == unmodified PPOEarlyTerminated rollout on the synthetic
+    env with one env, as upstream requires (adapter/early_terminated_adapter.py:L42, L56-98)."""
+    g = np.load(os.path.join(golden_dir, 'rollout_ppoearly.npz'))
+    N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
+    assert N == 1
+    env = SyntheticBoxEnv(N, O, A, max_episode_steps=int(g['tmax']), seed=int(g['seed']), term_prob=float(g['term_prob']))
+    window = []
+    sl = orollout.rollout_epoch(env, Normalizer((O,)), g['theta'], T, g['eps'], window=window,
+                                early={'cost_limit': float(g['algo_cost_limit']), 'acc': np.zeros(N, np.float32)})
+    tol = dict(rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sl['obs'], g['slab_obs'], **tol)
+    np.testing.assert_allclose(sl['act'], g['slab_act'], **tol)
+    assert np.array_equal(sl['rew'] == 0, g['slab_reward'] == 0) and (sl['rew'] == 0).sum() >= 10     # early terminations happen
+    np.testing.assert_allclose(sl['rew'], g['slab_reward'], **tol)
+    assert np.array_equal(sl['cost'], g['slab_cost'])
+    np.testing.assert_allclose(sl['val_r'], g['slab_value_r'], **tol)
+    w = np.array(window[-10:], np.float32)
+    np.testing.assert_allclose(w[:, 0], g['win_ret'], rtol=1e-5, atol=1e-5)
+    assert np.array_equal(w[:, 1], g['win_cost']) and np.array_equal(w[:, 2], g['win_len'])
+
+
 def test_cup_update_golden(golden_dir):
     """Oracle CUP (PPO stage on adv_r, then the KL-regularised cost projection stage, first_order/cup.py:L93-215)
     == unmodified CUP._update.  Pins the specification before the CUDA loss kind exists."""
