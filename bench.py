@@ -236,7 +236,8 @@ def run_b200(args) -> dict:
                                          ptr(eng.gpart), ptr(eng.stats_part), ptr(eng.train_stats), 0, 0, 0, 1, 0, 0, current_stream())
         ms_k = timed(iter_launch, 10) / 10          # learning rates 0: the parameters stay put
         kname, rows_per_launch = 'minibatch_grad_x3_kernel<fused> (persistent: 1 launch = 1 update iteration)', total
-        traffic = None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_ncu_update_x3.md)
+        traffic = 221.7e6 if (O == 60 and A == 8 and total == 524288 and args.algo == 'PPOLag') else None
     else:
         fn = lib().osb_minibatch_grad_tc if args.precision == 'tf32' else lib().osb_minibatch_grad
 

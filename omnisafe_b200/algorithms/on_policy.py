@@ -100,6 +100,10 @@ class PolicyGradient(BaseAlgo):
         self._update()
         self._actor_critic.actor_scheduler_step()
         if not log:
+            self._epochs_unchecked = getattr(self, '_epochs_unchecked', 0) + 1
+            if distributed.world_size() > 1 and self._epochs_unchecked >= 16:     # the NVLink exchange reports time-outs through a flag
+                self._epochs_unchecked = 0
+                distributed.p2p_check()
             return None
         if epoch is None:
             epoch = self._logger.current_epoch
@@ -333,7 +337,15 @@ class NaturalPG(PolicyGradient):
         self._update_actor()
         final_kl = self._engine.kl_state[0].clone()
         super()._update(net_mask=6, perm=perm)   # critics only, update_iters passes (natural_pg.py:L209-223)
-        self._engine.kl_state[0] = final_kl      # Train/KL = KL of the accepted actor step
+        # what the reference logs after the actor step (natural_pg.py:L168-186, trpo.py:L196-222): loss / ratio / KL of
+        # the accepted policy on the full batch, StopIter = update_iters
+        ev = self._engine.evaluate(self._actor_critic.theta, self._adv_lagrange())
+        ts = self._engine.train_stats.view(3, 8)
+        ts[0, 0] = ev['loss_c'] if self._kind == LOSS_COST else ev['loss']
+        ts[0, 1] = ev['ratio']
+        ts[0, 3] = 1.0
+        self._engine.kl_state[0] = final_kl if float(final_kl) != 0.0 else ev['kl']
+        self._engine.kl_state[1] = float(self._cfgs.algo_cfgs.update_iters)
 
 
 @registry.register
