@@ -366,7 +366,9 @@ __device__ __forceinline__ void s_cp_arrive(uint32_t bar) {
 // TMA = true (default): one elected thread issues cp.async.bulk.tensor.2d boxes {32 envs x 128 (129) steps}.
 //   Measured on B200: boxes with 128-byte rows 4N bytes apart stream at only ~21 GB/s per SM (one row request per
 //   ~10 cycles, from DRAM and from L2 alike), capping the kernel at 2.7 TB/s with the arithmetic removed.
-template <bool TMA>
+// MODE 0: both halves by cp.async; MODE 1: both by TMA; MODE 2: the A half (reward, cost, flags) by TMA and the B half
+// (values) by cp.async -- two independent load paths working side by side.
+template <int MODE>
 __global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_constant__ GaeMaps tm, GaeArgs p, double gl8_r, double gl8_c) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     const uint32_t pad = (128u - (s_u32(s_raw) & 127u)) & 127u;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_co
     auto load_A = [&](int k) {
         const int s = k % NSTG, t0 = T - (k + 1) * ST;
         const uint32_t dst = sb + (uint32_t)s * S_STAGE;
-        if constexpr (TMA) {
+        if constexpr (MODE != 0) {
             if (tid == 0) {
                 s_mbar_expect_tx(fullA(s), 2 * S_PLANE + S_FLAGS);
                 s_tma_load(dst + S_OFF_REW, &tm.rew, env0, t0, fullA(s));
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_co
     auto load_B = [&](int k) {
         const int s = k % NSTG, t0 = T - (k + 1) * ST;
         const uint32_t dst = sb + (uint32_t)s * S_STAGE;
-        if constexpr (TMA) {
+        if constexpr (MODE == 1) {
             if (tid == 0) {
                 s_mbar_expect_tx(fullB(s), 2 * S_PLANE_V);
                 s_tma_load(dst + S_OFF_VR, &tm.val_r, env0, t0, fullB(s));
@@ -435,8 +437,7 @@ __global__ void __launch_bounds__(STHREADS, 1) gae_stream_kernel(const __grid_co
         }
     };
     if (tid == 0) {
-        const uint32_t cnt = TMA ? 1u : (uint32_t)STHREADS;
-        for (int i = 0; i < NSTG; ++i) { s_mbar_init(fullA(i), cnt); s_mbar_init(fullB(i), cnt); }
+        for (int i = 0; i < NSTG; ++i) { s_mbar_init(fullA(i), MODE != 0 ? 1u : (uint32_t)STHREADS); s_mbar_init(fullB(i), MODE == 1 ? 1u : (uint32_t)STHREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (tid < 2 * 2 * 32) sCarry[tid] = 0.0;
@@ -726,7 +727,8 @@ static int osb_gae_stream_launch(const GaeArgs& a, cudaStream_t s) {
     if (legacy || (a.N & 15) != 0) return 1;                      // row strides of the u8 plane must be 16 B multiples
     const uintptr_t al = (uintptr_t)a.rew | (uintptr_t)a.cost | (uintptr_t)a.val_r | (uintptr_t)a.val_c | (uintptr_t)a.flags;
     if (al & 15u) return 1;
-    static const bool use_tma = getenv("OSB_GAE_LDGSTS") == nullptr;
+    static const int mode = getenv("OSB_GAE_LDGSTS") ? 0 : getenv("OSB_GAE_TMA") ? 1 : getenv("OSB_GAE_MIXED") ? 2 : 1;
+    const bool use_tma = mode != 0;
     static GaeMaps maps = {};
     if (use_tma) {
         struct Key { const void* p[5]; int T, N; };
@@ -742,14 +744,17 @@ static int osb_gae_stream_launch(const GaeArgs& a, cudaStream_t s) {
     }
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(gae_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess ||
-            cudaFuncSetAttribute(gae_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+        if (cudaFuncSetAttribute(gae_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess ||
+            cudaFuncSetAttribute(gae_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess ||
+            cudaFuncSetAttribute(gae_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_SMEM + 128)) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
         attr = true;
     }
     double g8r = 1.0, g8c = 1.0;
     for (int i = 0; i < SL; ++i) { g8r *= a.gl_r; g8c *= a.gl_c; }
-    if (use_tma) gae_stream_kernel<true><<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
-    else gae_stream_kernel<false><<<(a.N + SE - 1) / SE, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    const int nblk = (a.N + SE - 1) / SE;
+    if (mode == 1) gae_stream_kernel<1><<<nblk, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    else if (mode == 2) gae_stream_kernel<2><<<nblk, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
+    else gae_stream_kernel<0><<<nblk, STHREADS, S_SMEM + 128, s>>>(maps, a, g8r, g8c);
     return 0;
 }
 

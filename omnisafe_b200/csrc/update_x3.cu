@@ -30,7 +30,7 @@ using namespace x3;
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }      // epilogue warps only
 __device__ __forceinline__ void loss_bar_sync() { asm volatile("bar.sync 2, 128;\n" ::: "memory"); }     // loss warps (h == 0)
 
-enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_COST = 3, X3_FVP = 4 };   // X3_FVP: dOUT supplied (Fisher-vector product)
+enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_FOCOPS = 2, X3_COST = 3, X3_FVP = 4 };   // X3_FVP: dOUT supplied (Fisher-vector product)
 
 struct X3Batch {
     const float* obs; const float* act; const float* logp; const float* adv_r; const float* adv_c;
@@ -60,6 +60,9 @@ struct X3Args {
     int world, rank;
     unsigned int step_base;      // exchange step id of this launch's first minibatch (identical on all ranks)
     int* error_flag;
+    // X3_FOCOPS (first_order/focops.py:L62-108; stepwise launches only): old policy per sample, the minibatch mean of the
+    // KL mask from the forward-only pass 1 (null in pass 1), forward_only = statistics only
+    const float* mu_old; const float* logstd_old; const float* focops_mask_mean; float focops_lam, focops_eta; int forward_only;
     const float* fvp_dmu;        // X3_FVP: tangent of mu per slab row [total][A] (fvp_tangent_x3_kernel)
     const float* fvp_vec;        // X3_FVP: direction v (its log_std block gives the log_std block of F v)
     float fvp_scale;             // X3_FVP: 1 / (rows * A)
@@ -78,7 +81,7 @@ constexpr uint32_t OFF_X = 0, OFF_H1 = OFF_X + ACT_X3, OFF_H2 = OFF_H1 + ACT_X3,
                    OFF_MISC = OFF_ONES + 512;
 // misc region (floats unless noted)
 constexpr int MF_B1 = 0, MF_B2 = 64, MF_B3 = 128, MF_LS = 144 /* logstd[16] sigma[16] dlogstd acc[16] */, MF_STAT = 192,
-              MF_RED = 200 /* [4*8 + 4*16 + 4*16] */, MF_B3ACC = 360, MF_PART = 376 /* [2][256] */, MF_SCAL = 888 /* [16] */, MF_END = 904;
+              MF_RED = 200 /* [4*8 + 4*16 + 4*16] */, MF_B3ACC = 360, MF_PART = 376 /* [2][256] */, MF_SCAL = 888 /* [16] */, MF_OLD = 904 /* log sigma_old[16], 1 / sigma_old^2 [16] */, MF_END = 936;
 constexpr uint32_t OFF_ROWS = OFF_MISC + MF_END * 4;                 // long long [2][128]
 constexpr uint32_t OFF_BARS = OFF_ROWS + 2 * XT * 8;                 // uint64 [NBAR]
 enum Bar { RDY_X0 = 0, RDY_X1, RDY_H1_0, RDY_H1_1, RDY_H2_0, RDY_H2_1, RDY_D, RDY_DZ2_0, RDY_DZ2_1, RDY_DZ1,
@@ -226,6 +229,11 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     if (!is_mma_warp) {
         stage_weights_x3(sbase, misc, theta, L, net, O, A, tid);
         if (tid < 128) reinterpret_cast<uint32_t*>(gbase + OFF_ONES)[tid] = 0x3F803F80u;       // bf16 1.0 x 256
+        if (tid < 16 && (!FUSED && p.kind == X3_FOCOPS)) {
+            const float lo = (tid < A) ? __ldg(p.logstd_old + tid) : 0.f;
+            const float so = expf(lo);
+            misc[MF_OLD + tid] = lo; misc[MF_OLD + 16 + tid] = 1.f / (so * so);
+        }
     } else {
         if (lane == 0) {
             for (int i = 0; i < NBAR; ++i) {
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 __syncwarp();
                 // db2 of the PREVIOUS tile (dZ2 still sits in the H2 buffer until this tile's E2): runs under E1,
                 // completes before Z2 (in-order pipe), so DONE_C2 covers it
-                if (!first) gemm_x3_warp(leader, tmem + T_DB2, dH2, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, tile != (int)blockIdx.x + G);
+                if (!first && !(!FUSED && p.forward_only)) gemm_x3_warp(leader, tmem + T_DB2, dH2, ACT_SUB, 2048u, dOnes, 0u, 0u, id_dw16, 8, tile != (int)blockIdx.x + G);
                 // Z2 = H1 W2^T
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 }
                 if (leader) mma_commit_a(bar(DONE_C3));
                 __syncwarp();
+                if (!FUSED && p.forward_only) continue;              // statistics pass (FOCOPS mask mean): no backward
                 // dZ2' = dOUT W3 ; dW3^T += H2^T dOUT
                 mbar_wait_a(bar(RDY_D), par);
                 tc_fence_after();
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
         int step_t0 = 0;
         if (FUSED) step_t0 = p.adam_step[net];
         // per-thread partial sums of the loss warps over the tiles of one minibatch (reduced once per minibatch)
-        float acc_st[4] = {0.f, 0.f, 0.f, 0.f}, acc_dls[AP], acc_db[AP];
+        float acc_st[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_dls[AP], acc_db[AP];      // loss, ratio, kl, count, FOCOPS mask
 #pragma unroll
         for (int a = 0; a < AP; ++a) { acc_dls[a] = 0.f; acc_db[a] = 0.f; }
 
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 // ---- E0: X tile (prefetched registers -> bf16x3) ------------------------------------------------
                 stamp(0);
                 if (has_next) tile_rows(mb, tile + G, sRowNext);
-                if (it > 0) mbar_wait_a(bar(DONE_C6), par ^ 1u);          // previous tile's dW1 / db1 read X and dZ1
+                if (it > 0 && !(!FUSED && p.forward_only)) mbar_wait_a(bar(DONE_C6), par ^ 1u);   // previous tile's dW1 / db1 read X and dZ1
                 stamp(1);
                 tc_fence_after();
 #pragma unroll
@@ -584,18 +593,46 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                                 dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
                             } else if (p.kind == X3_RATIO) {
                                 loss = -ratio * adv; dlogp = -adv * ratio * inv_b;
-                            } else {
+                            } else if (p.kind == X3_COST) {
                                 loss = ratio * adv_c; dlogp = adv_c * ratio * inv_b;
+                            }
+                            float dmask = 0.f, dmo[AP];
+#pragma unroll
+                            for (int a = 0; a < AP; ++a) dmo[a] = 0.f;
+                            if ((!FUSED && p.kind == X3_FOCOPS)) {
+                                // The reference forms (kl[b,1] - ratio[b] adv[b] / lam) * mask[b,1] and takes the mean of the
+                                // [b,b] matrix (first_order/focops.py:L85-89):  loss = mean_i(mask_i kl_i) - mean_i(mask_i)
+                                // mean_j(ratio_j adv_j) / lam;  mean_i(mask_i) of this minibatch comes from the forward-only pass 1.
+                                const float* sOld = misc + MF_OLD;
+                                float kl = 0.f;
+#pragma unroll
+                                for (int a = 0; a < AP; ++a)
+                                    if (a < A) {
+                                        const float sn = sLs[16 + a];
+                                        dmo[a] = (o[a] + sB3[a]) - __ldg(p.mu_old + prow * A + a);
+                                        kl += (sOld[a] - sLs[a]) + (sn * sn + dmo[a] * dmo[a]) * (0.5f * sOld[16 + a]) - 0.5f;
+                                    }
+                                dmask = (kl <= p.focops_eta) ? 1.f : 0.f;
+                                const float mbar = p.focops_mask_mean ? __ldg(p.focops_mask_mean) : dmask;
+                                loss = kl * dmask - mbar * ratio * adv / p.focops_lam;
+                                dlogp = -mbar * adv * ratio / p.focops_lam * inv_b;
+                                acc_st[2] += kl; acc_st[4] += dmask;
                             }
                             acc_st[0] += loss; acc_st[1] += ratio; acc_st[3] += 1.f;
 #pragma unroll
                             for (int a = 0; a < AP; ++a)
                                 if (a < A) {
                                     const float iv = sLs[32 + a];
-                                    const float dm = dlogp * diff[a] * iv;
+                                    float dm = dlogp * diff[a] * iv;
+                                    float dl = dlogp * (diff[a] * diff[a] * iv - 1.f);
+                                    if ((!FUSED && p.kind == X3_FOCOPS)) {
+                                        const float sn = sLs[16 + a];
+                                        dm += dmask * inv_b * dmo[a] * (misc + MF_OLD)[16 + a];
+                                        dl += dmask * inv_b * (sn * sn * (misc + MF_OLD)[16 + a] - 1.f);
+                                    }
                                     d16[a] = dm;
                                     acc_db[a] += dm;
-                                    acc_dls[a] += dlogp * (diff[a] * diff[a] * iv - 1.f);
+                                    acc_dls[a] += dl;
                                 }
                         }
                     }
@@ -604,6 +641,12 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     stamp(8);
                 }
                 stamp(9);
+                if (!FUSED && p.forward_only) {                                      // statistics pass: no backward; H2 is free once OUT is done
+                    if (has_next) prefetch_x(sRowNext);
+                    if (h != 0) { mbar_wait_a(bar(DONE_C3), par); tc_fence_after(); }
+                    rpar ^= 1;
+                    continue;
+                }
                 // ---- E4: dZ2 = (dOUT W3) (1 - H2^2), stored over H2 once dW3 has read it --------------------------
                 if (has_next) prefetch_x(sRowNext);                        // next tile's rows fly during the backward half
                 mbar_wait_a(bar(DONE_C4A), par);
@@ -674,19 +717,27 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 // loss-warp sums: lanes -> warp (butterfly) -> the four loss warps (fixed order)
                 if (h == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc_st[i] = warp_sum(acc_st[i]);
+                    for (int i = 0; i < 5; ++i) acc_st[i] = warp_sum(acc_st[i]);
 #pragma unroll
                     for (int a = 0; a < AP; ++a) { acc_dls[a] = warp_sum(acc_dls[a]); acc_db[a] = warp_sum(acc_db[a]); }
                     if (lane == 0) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) sRed[q * 8 + i] = acc_st[i];
+                        for (int i = 0; i < 5; ++i) sRed[q * 8 + i] = acc_st[i];
 #pragma unroll
                         for (int a = 0; a < AP; ++a) { sRed[32 + q * 16 + a] = acc_dls[a]; sRed[96 + q * 16 + a] = acc_db[a]; }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc_st[i] = 0.f;
+                    for (int i = 0; i < 5; ++i) acc_st[i] = 0.f;
 #pragma unroll
                     for (int a = 0; a < AP; ++a) { acc_dls[a] = 0.f; acc_db[a] = 0.f; }
+                }
+                if (!FUSED && p.forward_only) {
+                    epi_bar_sync();                    // sRed of the four loss warps
+                    if (tid >= 64 && tid < 72) {
+                        const int i = tid - 64;
+                        __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + i, (i < 5) ? (sRed[i] + sRed[8 + i]) + (sRed[16 + i] + sRed[24 + i]) : 0.f);
+                    }
+                    break;
                 }
                 mbar_wait_a(bar(DONE_C6), (uint32_t)((it - 1) & 1));
                 tc_fence_after();
@@ -740,13 +791,13 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 if (net == 0 && tid >= 32 && tid < 32 + A) {
                     const int a = tid - 32;
                     float g = (sRed[32 + a] + sRed[48 + a]) + (sRed[64 + a] + sRed[80 + a]);
-                    if (blockIdx.x == 0 && p.kind == X3_PPO_CLIP) g -= p.entropy_coef / (float)A;
+                    if (blockIdx.x == 0 && (p.kind == X3_PPO_CLIP || (!FUSED && p.kind == X3_FOCOPS))) g -= p.entropy_coef / (float)A;
                     if (p.kind == X3_FVP) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + a) : 0.f;
                     __stcg(gout + L.off_logstd + a, g);
                 }
                 if (tid >= 64 && tid < 72) {
                     const int i = tid - 64;
-                    __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + i, (i < 4) ? (sRed[i] + sRed[8 + i]) + (sRed[16 + i] + sRed[24 + i]) : 0.f);
+                    __stcg(p.stats_part + ((size_t)blockIdx.x * 3 + net) * 8 + i, (i < 5) ? (sRed[i] + sRed[8 + i]) + (sRed[16 + i] + sRed[24 + i]) : 0.f);
                 }
             } else {
                 for (int i = tid; i < L.size; i += NEPI) __stcg(gout + i, 0.f);      // no tile of this (short) minibatch
@@ -902,6 +953,15 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     if (is_mma_warp) tmem_dealloc(tmem, T_COLS);
 }
 
+// mean_i 1{KL_i <= eta} of a minibatch from the forward-only pass (statistic slot 4 / slot 3 of the actor rows)
+__global__ void x3_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
+                                    const int* __restrict__ stop_flag) {
+    if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    float m = 0.f, n = 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + 4]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
+    out[0] = n > 0.f ? m / n : 0.f;
+}
+
 }  // namespace osb
 
 using namespace osb;
@@ -937,14 +997,15 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
                           float entropy_coef, float focops_lam, float focops_eta,
                           const float* lagrange, const float* logstd_old, int net_mask, float* gpart,
                           float* stats_part, const int* stop_flag, void* stream) {
-    (void)mu_old; (void)focops_lam; (void)focops_eta; (void)logstd_old;
     OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
     OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "bf16x3 path needs O <= 64, A <= 16");
     OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
-    OSB_CHECK_ARG(loss_kind == X3_PPO_CLIP || loss_kind == X3_RATIO || loss_kind == X3_COST, "loss kind not on the bf16x3 path");
+    OSB_CHECK_ARG(loss_kind == X3_PPO_CLIP || loss_kind == X3_RATIO || loss_kind == X3_COST || loss_kind == X3_FOCOPS, "loss kind not on the bf16x3 path");
+    OSB_CHECK_ARG(loss_kind != X3_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old / logstd_old");
     OSB_CHECK_ARG(net_mask > 0 && net_mask < 8, "net_mask");
     X3Args p = {};
     p.b = X3Batch{obs, act, logp, adv_r, adv_c, tv_r, tv_c, moments, perm, total, perm_seed, mb_start, mb_count, 0};
+    p.mu_old = mu_old; p.logstd_old = logstd_old; p.focops_lam = focops_lam; p.focops_eta = focops_eta;
     p.kind = loss_kind; p.clip = clip; p.entropy_coef = entropy_coef; p.lagrange = lagrange;
     p.theta = theta; p.gpart = gpart; p.stats_part = stats_part; p.stop_flag = stop_flag;
     p.O = O; p.A = A; p.P = actor_layout(O, A).size + 2 * critic_layout(O, A).size; p.net_mask = net_mask;
@@ -953,6 +1014,20 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
     int rc = x3_set_attr();
     if (rc) return rc;
     const bool single = (net_mask & (net_mask - 1)) == 0;
+    if (loss_kind == X3_FOCOPS && (net_mask & 1)) {
+        // pass 1: actor forward only -> mean of the KL mask over the minibatch (the reference's [b,1] x [b] broadcast)
+        static float* d_mask_mean = nullptr;
+        if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
+        X3Args q = p;
+        q.forward_only = 1; q.net_mask = 1;
+        const int nb1 = osb_tc_grid_blocks(mb_count, 1);
+        if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb1, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(q);
+        else minibatch_grad_x3_kernel<false, 16><<<dim3(nb1, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(q);
+        OSB_LAUNCH_CHECK();
+        x3_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag);
+        OSB_LAUNCH_CHECK();
+        p.focops_mask_mean = d_mask_mean;
+    }
     if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
     else minibatch_grad_x3_kernel<false, 16><<<dim3(nb, single ? 1 : 3), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(p);
     OSB_LAUNCH_CHECK();

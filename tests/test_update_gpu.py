@@ -215,13 +215,15 @@ def test_fvp_cg_eval_golden(cuda, golden_dir, precision):
     np.testing.assert_allclose(ev2['loss_r'], lr_, rtol=1e-4, atol=1e-6)
 
 
-def test_focops_update_epoch_golden(cuda, golden_dir):
+@pytest.mark.parametrize('precision', [0, 2])      # exact fp32 FMA tiles / split-bf16 tensor-core tiles (stepwise launches): same bar
+def test_focops_update_epoch_golden(cuda, golden_dir, precision):
     """FOCOPS on the device (incl. the reference's broadcast quirk, via the forward-only mask pass)
     vs the unmodified FOCOPS._update: same parameters afterwards."""
     g = np.load(os.path.join(golden_dir, 'update_focops.npz'))
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
     N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
     agent, buf, eng = _setup(cuda, data, N, T, O, A, g['theta0'])
+    eng.precision = precision
     lag = torch.tensor([float(g['lam1']), 0, 0, 0], dtype=torch.float32, device=cuda)
     perms = torch.as_tensor(np.stack([_rows(p_, N, T) for p_ in g['perms'][::2]])).to(cuda)
     eng.ppo_epoch(loss_kind=2, lagrange=lag, net_mask=7, batch_size=int(g['batch_size']),
