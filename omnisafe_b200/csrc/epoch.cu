@@ -194,7 +194,7 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     // precision 1 = TF32 tcgen05 tiles (O <= 64, loss kinds 0/1/3); otherwise the fp32 FMA parity path
     // precision 2 = split-bf16 ("bf16x3") tcgen05 tiles: fp32-level results on the tensor cores (O <= 64,
     // loss kinds 0/1/3)
-    const bool use_x3 = precision == 2 && O <= 64 && (loss_kind == 0 || loss_kind == 1 || loss_kind == 2 || loss_kind == 3);   // FOCOPS (2): stepwise launches
+    const bool use_x3 = precision == 2 && O <= 64 && (loss_kind == 0 || loss_kind == 1 || loss_kind == 2 || loss_kind == 3 || loss_kind == 5);   // FOCOPS (2), P3O (5): stepwise launches
     const bool use_x3e = precision == 2 && O <= 64;
     const bool use_tc = precision == 1 && O <= 512;
     const bool train_actor = (net_mask & 1) != 0;
@@ -209,7 +209,7 @@ int osb_ppo_update_epoch(float* theta, float* grad, float* adam_m, float* adam_v
     const float gscale = 1.0f / (float)world_size;
     // bf16x3 + (one rank | NVLink peer exchange): the whole iteration is one persistent kernel with the optimiser inside
     const bool p2p_ok = world_size > 1 && peer_buf && peer_flag && p2p_error;
-    const bool fuse_x3 = use_x3 && loss_kind != 2 && (world_size == 1 || p2p_ok) && !getenv("OSB_X3_NO_FUSE");
+    const bool fuse_x3 = use_x3 && loss_kind != 2 && loss_kind != 5 && (world_size == 1 || p2p_ok) && !getenv("OSB_X3_NO_FUSE");
     for (int it = 0; it < update_iters; ++it) {
         const int* perm_it = perm ? perm + (size_t)it * total : nullptr;
         if (fuse_x3) {

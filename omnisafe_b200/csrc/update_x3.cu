@@ -30,7 +30,7 @@ using namespace x3;
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }      // epilogue warps only
 __device__ __forceinline__ void loss_bar_sync() { asm volatile("bar.sync 2, 128;\n" ::: "memory"); }     // loss warps (h == 0)
 
-enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_FOCOPS = 2, X3_COST = 3, X3_FVP = 4 };   // X3_FVP: dOUT supplied (Fisher-vector product)
+enum X3Loss { X3_PPO_CLIP = 0, X3_RATIO = 1, X3_FOCOPS = 2, X3_COST = 3, X3_FVP = 4, X3_P3O = 5 };   // X3_FVP: dOUT supplied (Fisher-vector product)
 
 struct X3Batch {
     const float* obs; const float* act; const float* logp; const float* adv_r; const float* adv_c;
@@ -586,11 +586,20 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                             const float adv_c = pf_advc - m_c;
                             const float adv = (adv_r - lam * adv_c) * inv_1lam;
                             float dlogp, loss;
-                            if (p.kind == X3_PPO_CLIP) {
+                            if (p.kind == X3_PPO_CLIP || (!FUSED && p.kind == X3_P3O)) {
                                 const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
                                 const float s1 = ratio * adv, s2 = rc * adv;
                                 loss = -fminf(s1, s2);
                                 dlogp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
+                                if (!FUSED && p.kind == X3_P3O) {
+                                    // P3O (penalty_function/p3o.py:L48-91): + kappa * relu(mean_j(ratio_j adv_c_j) + Jc - limit); the gate
+                                    // (kappa when the minibatch mean makes the relu active) comes from the forward-only pass 1.
+                                    // Statistic slot 2: pass 1 -> ratio * adv_c; pass 2 -> the penalty term (Loss/Loss_pi_cost).
+                                    const bool pass2 = p.focops_mask_mean != nullptr;
+                                    const float gate = pass2 ? __ldg(p.focops_mask_mean) : 0.f;
+                                    dlogp += gate * adv_c * ratio * inv_b;
+                                    acc_st[2] += pass2 ? gate * (ratio * adv_c + p.focops_eta) : ratio * adv_c;
+                                }
                             } else if (p.kind == X3_RATIO) {
                                 loss = -ratio * adv; dlogp = -adv * ratio * inv_b;
                             } else if (p.kind == X3_COST) {
@@ -791,7 +800,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 if (net == 0 && tid >= 32 && tid < 32 + A) {
                     const int a = tid - 32;
                     float g = (sRed[32 + a] + sRed[48 + a]) + (sRed[64 + a] + sRed[80 + a]);
-                    if (blockIdx.x == 0 && (p.kind == X3_PPO_CLIP || (!FUSED && p.kind == X3_FOCOPS))) g -= p.entropy_coef / (float)A;
+                    if (blockIdx.x == 0 && (p.kind == X3_PPO_CLIP || (!FUSED && (p.kind == X3_FOCOPS || p.kind == X3_P3O)))) g -= p.entropy_coef / (float)A;
                     if (p.kind == X3_FVP) g = (blockIdx.x == 0) ? 2.f / (float)A * __ldg(p.fvp_vec + L.off_logstd + a) : 0.f;
                     __stcg(gout + L.off_logstd + a, g);
                 }
@@ -955,11 +964,13 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
 
 // mean_i 1{KL_i <= eta} of a minibatch from the forward-only pass (statistic slot 4 / slot 3 of the actor rows)
 __global__ void x3_mask_mean_kernel(const float* __restrict__ stats_part, int nblocks, float* __restrict__ out,
-                                    const int* __restrict__ stop_flag) {
+                                    const int* __restrict__ stop_flag, int kind, float kappa, float jc_minus_limit) {
     if (threadIdx.x != 0 || (stop_flag && *stop_flag)) return;
+    const int slot = (kind == X3_P3O) ? 2 : 4;
     float m = 0.f, n = 0.f;
-    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + 4]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
-    out[0] = n > 0.f ? m / n : 0.f;
+    for (int b = 0; b < nblocks; ++b) { m += stats_part[((size_t)b * 3) * 8 + slot]; n += stats_part[((size_t)b * 3) * 8 + 3]; }
+    const float mean = n > 0.f ? m / n : 0.f;
+    out[0] = (kind == X3_P3O) ? ((mean + jc_minus_limit > 0.f) ? kappa : 0.f) : mean;
 }
 
 }  // namespace osb
@@ -1000,7 +1011,7 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
     OSB_CHECK_ARG(theta && obs && act && logp && adv_r && adv_c && tv_r && tv_c && moments, "null input");
     OSB_CHECK_ARG(O > 0 && O <= 64 && A > 0 && A <= 16 && mb_count > 0 && total > 0, "bf16x3 path needs O <= 64, A <= 16");
     OSB_CHECK_ARG(mb_start >= 0 && mb_start + mb_count <= total, "minibatch window out of range");
-    OSB_CHECK_ARG(loss_kind == X3_PPO_CLIP || loss_kind == X3_RATIO || loss_kind == X3_COST || loss_kind == X3_FOCOPS, "loss kind not on the bf16x3 path");
+    OSB_CHECK_ARG(loss_kind == X3_PPO_CLIP || loss_kind == X3_RATIO || loss_kind == X3_COST || loss_kind == X3_FOCOPS || loss_kind == X3_P3O, "loss kind not on the bf16x3 path");
     OSB_CHECK_ARG(loss_kind != X3_FOCOPS || (mu_old && logstd_old), "FOCOPS needs mu_old / logstd_old");
     OSB_CHECK_ARG(net_mask > 0 && net_mask < 8, "net_mask");
     X3Args p = {};
@@ -1014,8 +1025,9 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
     int rc = x3_set_attr();
     if (rc) return rc;
     const bool single = (net_mask & (net_mask - 1)) == 0;
-    if (loss_kind == X3_FOCOPS && (net_mask & 1)) {
-        // pass 1: actor forward only -> mean of the KL mask over the minibatch (the reference's [b,1] x [b] broadcast)
+    if ((loss_kind == X3_FOCOPS || loss_kind == X3_P3O) && (net_mask & 1)) {
+        // pass 1: actor forward only -> mean of the KL mask over the minibatch (FOCOPS: the reference's [b,1] x [b] broadcast) or
+        // the relu gate of the minibatch-mean cost surrogate (P3O: focops_lam carries kappa, focops_eta carries Jc - limit)
         static float* d_mask_mean = nullptr;
         if (!d_mask_mean) OSB_CUDA(cudaMalloc(&d_mask_mean, sizeof(float)));
         X3Args q = p;
@@ -1024,7 +1036,7 @@ int osb_minibatch_grad_x3(const float* theta, int O, int A, const float* obs, co
         if (A <= 8) minibatch_grad_x3_kernel<false, 8><<<dim3(nb1, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(q);
         else minibatch_grad_x3_kernel<false, 16><<<dim3(nb1, 1), NTX3, 1024 + X3_SMEM, (cudaStream_t)stream>>>(q);
         OSB_LAUNCH_CHECK();
-        x3_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag);
+        x3_mask_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_part, nb1, d_mask_mean, stop_flag, loss_kind, focops_lam, focops_eta);
         OSB_LAUNCH_CHECK();
         p.focops_mask_mean = d_mask_mean;
     }

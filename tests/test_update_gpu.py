@@ -239,13 +239,15 @@ def test_focops_update_epoch_golden(cuda, golden_dir, precision):
     np.testing.assert_allclose(ts[0, 0] / ts[0, 3], g['loss_pi'].mean(), rtol=2e-3, atol=1e-5)
 
 
-def test_p3o_update_epoch_golden(cuda, golden_dir):
+@pytest.mark.parametrize('precision', [0, 2])
+def test_p3o_update_epoch_golden(cuda, golden_dir, precision):
     """P3O on the device (forward-only pass for the minibatch-mean relu gate) vs the unmodified
     P3O._update: same parameters afterwards."""
     g = np.load(os.path.join(golden_dir, 'update_p3o.npz'))
     data = {k[5:]: g[k] for k in g.files if k.startswith('data_')}
     N, T, O, A = int(g['N']), int(g['T']), int(g['O']), int(g['A'])
     agent, buf, eng = _setup(cuda, data, N, T, O, A, g['theta0'])
+    eng.precision = precision
     perms = torch.as_tensor(np.stack([_rows(p_, N, T) for p_ in g['perms'][::2]])).to(cuda)
     eng.ppo_epoch(loss_kind=5, lagrange=None, net_mask=7, batch_size=int(g['batch_size']),
                   update_iters=int(g['update_iters']), clip=0.2, entropy_coef=0.0, focops_lam=float(g['kappa']),
