@@ -60,6 +60,8 @@ struct X3Args {
     int world, rank;
     unsigned int step_base;      // exchange step id of this launch's first minibatch (identical on all ranks)
     int* error_flag;
+    uint8_t* wimg;               // FUSED: [3 nets][W_IMG] bf16x3 images of the weight tiles (W1 | W2 | W3), written by the Adam owners,
+                                 // pulled into shared memory with one bulk copy (TMA) after every optimiser step
     // X3_FOCOPS (first_order/focops.py:L62-108; stepwise launches only): old policy per sample, the minibatch mean of the
     // KL mask from the forward-only pass 1 (null in pass 1), forward_only = statistics only
     const float* mu_old; const float* logstd_old; const float* focops_mask_mean; float focops_lam, focops_eta; int forward_only;
@@ -76,6 +78,7 @@ constexpr uint32_t ACT_SUB = XT * 128, ACT_X3 = 3 * ACT_SUB;        // [128][64]
 constexpr uint32_t D_SUB = XT * 32, D_X3 = 3 * D_SUB;               // [128][16] bf16 (SW32)
 constexpr uint32_t W_SUB = 64 * 128, W_X3 = 3 * W_SUB;              // [64][64]
 constexpr uint32_t W3_SUB = 16 * 128, W3_X3 = 3 * W3_SUB;           // [16][64]
+constexpr uint32_t W_IMG = 2 * W_X3 + W3_X3;                         // 55 296 B: the weight tiles W1 | W2 | W3 as they sit in shared memory
 constexpr uint32_t OFF_X = 0, OFF_H1 = OFF_X + ACT_X3, OFF_H2 = OFF_H1 + ACT_X3, OFF_D = OFF_H2 + ACT_X3,
                    OFF_W1 = OFF_D + D_X3, OFF_W2 = OFF_W1 + W_X3, OFF_W3 = OFF_W2 + W_X3, OFF_ONES = OFF_W3 + W3_X3,
                    OFF_MISC = OFF_ONES + 512;
@@ -85,7 +88,7 @@ constexpr int MF_B1 = 0, MF_B2 = 64, MF_B3 = 128, MF_LS = 144 /* logstd[16] sigm
 constexpr uint32_t OFF_ROWS = OFF_MISC + MF_END * 4;                 // long long [2][128]
 constexpr uint32_t OFF_BARS = OFF_ROWS + 2 * XT * 8;                 // uint64 [NBAR]
 enum Bar { RDY_X0 = 0, RDY_X1, RDY_H1_0, RDY_H1_1, RDY_H2_0, RDY_H2_1, RDY_D, RDY_DZ2_0, RDY_DZ2_1, RDY_DZ1,
-           DONE_C1, DONE_C2, DONE_C3, DONE_C4A, DONE_C4B, DONE_C5A, DONE_C5B, DONE_C6, NBAR };
+           DONE_C1, DONE_C2, DONE_C3, DONE_C4A, DONE_C4B, DONE_C5A, DONE_C5B, DONE_C6, RDY_W, NBAR };
 constexpr uint32_t OFF_TMEMSLOT = OFF_BARS + NBAR * 8;
 constexpr uint32_t OFF_PF = OFF_TMEMSLOT + 16;                        // float [128][12]: per-sample loss inputs (AP == 8), copied asynchronously
 constexpr int PF_LD = 12;
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
     } else {
         if (lane == 0) {
             for (int i = 0; i < NBAR; ++i) {
-                const uint32_t cnt = (i >= DONE_C1) ? 1u : (i == RDY_D ? 4u : 16u);
+                const uint32_t cnt = (i >= DONE_C1) ? 1u : (i == RDY_D ? 4u : 16u);      // (RDY_W: one expect_tx arrival)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar(i)), "r"(cnt) : "memory");
             }
             mbar_init_fence();
@@ -412,6 +415,19 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
         };
         int step_t0 = 0;
         if (FUSED) step_t0 = p.adam_step[net];
+        // FUSED: where this thread's parameter (the first of its slice chunk) lives inside the weight-tile image, or -1
+        // (log_std, b2, b3, and b1 when it is not folded into W1): byte offset of the hi piece, stride between pieces
+        int img_off = -1; uint32_t img_sub = 0;
+        if (FUSED) {
+            const int Sx = (L.size + G - 1) / G, px = (int)blockIdx.x * Sx + tid;
+            if (tid < Sx && px < L.size) {
+                if (px >= L.off_w1 && px < L.off_b1) { const int e = px - L.off_w1; img_off = (int)off128(e / O, e % O); img_sub = W_SUB; }
+                else if (px >= L.off_b1 && px < L.off_w2) { if (ones_col) { img_off = (int)off128(px - L.off_b1, 63); img_sub = W_SUB; } }
+                else if (px >= L.off_w2 && px < L.off_b2) { const int e = px - L.off_w2; img_off = (int)(W_X3 + off128(e >> 6, e & 63)); img_sub = W_SUB; }
+                else if (px >= L.off_w3 && px < L.off_b3) { const int e = px - L.off_w3; img_off = (int)(2 * W_X3 + off128(e >> 6, e & 63)); img_sub = W3_SUB; }
+            }
+        }
+        uint8_t* wimg = FUSED ? p.wimg + (size_t)net * W_IMG : nullptr;
         // per-thread partial sums of the loss warps over the tiles of one minibatch (reduced once per minibatch)
         float acc_st[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_dls[AP], acc_db[AP];      // loss, ratio, kl, count, FOCOPS mask
 #pragma unroll
@@ -943,15 +959,42 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                         m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));                       // exp_avg.lerp_(grad, 1 - beta1)
                         v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
                         const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
-                        __stcg(p.theta_rw + qg, __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(m, denom))));
+                        const float th_new = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+                        __stcg(p.theta_rw + qg, th_new);
                         __stcg(p.adam_m + qg, m); __stcg(p.adam_v + qg, v);
+                        if (pre && img_off >= 0) {       // the parameter's three bf16 pieces, where the weight tiles expect them
+                            uint32_t w0, w1, w2;
+                            split2(th_new, 0.f, w0, w1, w2);
+                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off), (unsigned short)w0);
+                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + img_sub), (unsigned short)w1);
+                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + 2 * img_sub), (unsigned short)w2);
+                        }
                     }
                 }
             }
             stamp(26);
             net_barrier();                                             // the new parameters of this network are in L2
             stamp(27);
-            stage_weights_x3(sbase, misc, theta, L, net, O, A, tid);   // visible to the tensor core with the next X announce
+            if (S <= NEPI) {
+                // weights: ONE bulk copy (TMA) of the image the Adam owners just wrote; biases / log_std: a few scalar loads
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.global;\n" ::: "memory");       // generic-proxy writes (other SMs, acquired above) -> async-proxy read
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar(RDY_W)), "r"(W_IMG) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 ::"r"(sbase + OFF_W1), "l"(wimg), "r"(W_IMG), "r"(bar(RDY_W)) : "memory");
+                }
+                if (tid >= 64 && tid < 128) { const int i = tid - 64; if (!ones_col) misc[MF_B1 + i] = __ldcg(theta + L.off_b1 + i); misc[MF_B2 + i] = __ldcg(theta + L.off_b2 + i); }
+                if (tid >= 128 && tid < 144) {
+                    const int i = tid - 128;
+                    misc[MF_B3 + i] = (i < L.out) ? __ldcg(theta + L.off_b3 + i) : 0.f;
+                    const float ls = (net == 0 && i < A) ? __ldcg(theta + L.off_logstd + i) : 0.f;
+                    const float sd = expf(ls);
+                    misc[MF_LS + i] = ls; misc[MF_LS + 16 + i] = sd; misc[MF_LS + 32 + i] = 1.f / (sd * sd);
+                }
+                mbar_wait_a(bar(RDY_W), (uint32_t)(mb & 1));
+            } else {
+                stage_weights_x3(sbase, misc, theta, L, net, O, A, tid);   // slices longer than the block: the image is incomplete
+            }
             epi_bar_sync();
             stamp(28);
         }
@@ -1103,6 +1146,13 @@ int osb_ppo_update_iter_x3(float* theta, float* grad, float* adam_m, float* adam
     p.sumsq_part = d_ws + 64; p.train_stats = train_stats; p.bar_ctr = reinterpret_cast<unsigned int*>(d_ws);
     p.peer_buf = (float* const*)peer_buf; p.peer_flag = (unsigned int* const*)peer_flag;
     p.world = world; p.rank = rank; p.error_flag = p2p_error; p.dbg = g_x3_dbg;
+    {   // weight-tile images: padding positions stay zero, so a change of the layout clears them
+        static uint8_t* d_wimg = nullptr;
+        static int img_O = -1, img_A = -1;
+        if (!d_wimg) OSB_CUDA(cudaMalloc(&d_wimg, 3 * W_IMG));
+        if (img_O != O || img_A != A) { OSB_CUDA(cudaMemsetAsync(d_wimg, 0, 3 * W_IMG, s)); img_O = O; img_A = A; }
+        p.wimg = d_wimg;
+    }
     const int n_mb = (int)((total + batch_size - 1) / batch_size);
     p.step_base = step_base + 1u;
     step_base += (unsigned int)n_mb;
