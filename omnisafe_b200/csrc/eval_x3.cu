@@ -137,6 +137,17 @@ __global__ void __launch_bounds__(EX_NT, 2) actor_eval_x3_kernel(EvalX3Args p) {
         }
         fence_async_smem();
         __syncthreads();
+        // per-sample inputs of the final statistics: requested now, they fly under the three layers
+        const long long row = (h == 0) ? sRow[s_row] : -1;
+        float pa[16], pm[16], plogp = 0.f, padvr = 0.f, padvc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) { pa[a] = 0.f; pm[a] = 0.f; }
+        if (row >= 0 && !p.mu_store) {
+#pragma unroll
+            for (int a = 0; a < 16; ++a)
+                if (a < A) { pa[a] = __ldg(p.act + row * A + a); pm[a] = __ldg(p.mu_old + row * A + a); }
+            plogp = __ldg(p.logp + row); padvr = __ldg(p.adv_r + row); padvc = __ldg(p.adv_c + row);
+        }
         if (warp == 0) {
             tc_fence_after();
             gemm_x3_warp(leader, tmem + C_Z, dAct, EX_SUB, 32u, dW1, EX_WSUB, 32u, id_fwd, 4, false);
@@ -180,17 +191,6 @@ __global__ void __launch_bounds__(EX_NT, 2) actor_eval_x3_kernel(EvalX3Args p) {
             gemm_x3_warp(leader, tmem + C_OUT, dAct, EX_SUB, 32u, dW3, EX_W3SUB, 32u, id_out, 4, false);
             if (leader) mma_commit_a(bar);
             __syncwarp();
-        }
-        // prefetch per-sample scalars while the MMAs run
-        const long long row = (h == 0) ? sRow[s_row] : -1;
-        float pa[16], pm[16], plogp = 0.f, padvr = 0.f, padvc = 0.f;
-#pragma unroll
-        for (int a = 0; a < 16; ++a) { pa[a] = 0.f; pm[a] = 0.f; }
-        if (row >= 0 && !p.mu_store) {
-#pragma unroll
-            for (int a = 0; a < 16; ++a)
-                if (a < A) { pa[a] = __ldg(p.act + row * A + a); pm[a] = __ldg(p.mu_old + row * A + a); }
-            plogp = __ldg(p.logp + row); padvr = __ldg(p.adv_r + row); padvc = __ldg(p.adv_c + row);
         }
         mbar_wait_a(bar, phase); phase ^= 1;
         tc_fence_after();
