@@ -884,6 +884,29 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
             const bool own = tid < S && p0 + tid < L.size;
             float pre_th = 0.f, pre_m = 0.f, pre_v = 0.f;
             if (own) { pre_th = __ldcg(p.theta_rw + noff + p0 + tid); pre_m = __ldcg(p.adam_m + noff + p0 + tid); pre_v = __ldcg(p.adam_v + noff + p0 + tid); }
+            // torch-Adam step of one parameter (+ its three bf16 pieces in the weight-tile image)
+            auto adam_store = [&](int qg, float g, float th, float m, float v, bool img) {
+                const float step_size = sScal[8], bc2_sqrt = sScal[9];
+                m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));                       // exp_avg.lerp_(grad, 1 - beta1)
+                v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
+                const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
+                const float th_new = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+                __stcg(p.theta_rw + qg, th_new);
+                __stcg(p.adam_m + qg, m); __stcg(p.adam_v + qg, v);
+                if (img && img_off >= 0) {           // where the weight tiles expect them
+                    uint32_t w0, w1, w2;
+                    split2(th_new, 0.f, w0, w1, w2);
+                    __stcg(reinterpret_cast<unsigned short*>(wimg + img_off), (unsigned short)w0);
+                    __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + img_sub), (unsigned short)w1);
+                    __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + 2 * img_sub), (unsigned short)w2);
+                }
+            };
+            // One rank: clip_grad_norm_ almost never clips (max_grad_norm 40), so Adam runs SPECULATIVELY with coefficient 1
+            // before the slice norms are known; the barrier that publishes the norms is then also the one that publishes the
+            // new parameters, and only a step that does clip redoes Adam from the saved state (one more barrier).
+            const bool spec = p.world == 1 && S <= NEPI;
+            float g_raw = 0.f;
+            if (spec && own) { g_raw = __ldcg(p.grad + noff + p0 + tid); adam_store(noff + p0 + tid, g_raw, pre_th, pre_m, pre_v, true); }
             stamp(24);
             net_barrier();                                             // every slice norm of this network is in L2
             stamp(25);
@@ -913,9 +936,20 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                 ts[2] += sScal[6] * inv;
                 ts[3] += 1.f;
             }
-            const float clipc = sScal[0], step_size = sScal[8], bc2_sqrt = sScal[9];
+            const float clipc = sScal[0];
             const unsigned int xstep = p.step_base + (unsigned int)mb;
             const int xpar = (int)(xstep & 1u);
+            if (spec) {
+                if (clipc != 1.0f) {                                   // (uniform over the network: same partial norms, same order)
+                    if (own) {
+                        const float g = g_raw * clipc;
+                        __stcg(p.grad + noff + p0 + tid, g);
+                        adam_store(noff + p0 + tid, g, pre_th, pre_m, pre_v, true);
+                    }
+                    stamp(26);
+                    net_barrier();
+                }
+            } else {
                     // clip -> average over ranks -> Adam (policy_gradient.py:L437-443, distributed.py:L193-198).  world > 1: every
             // parameter of the slice travels as ONE 8-byte word {step tag, clipped gradient} stored straight into every peer's
             // receive buffer [parity][source rank][P] over NVLink; the receiver spins on the tag of each word -- data and
@@ -954,26 +988,14 @@ __global__ void __launch_bounds__(NTX3, 1) minibatch_grad_x3_kernel(X3Args p) {
                     if (!fail) {
                         __stcg(p.grad + qg, g);
                         const bool pre = base == 0;                     // first chunk: state prefetched before the barrier
-                        const float th = pre ? pre_th : __ldcg(p.theta_rw + qg);
-                        float m = pre ? pre_m : __ldcg(p.adam_m + qg), v = pre ? pre_v : __ldcg(p.adam_v + qg);
-                        m = __fadd_rn(m, __fmul_rn(0.1f, __fadd_rn(g, -m)));                       // exp_avg.lerp_(grad, 1 - beta1)
-                        v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
-                        const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
-                        const float th_new = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
-                        __stcg(p.theta_rw + qg, th_new);
-                        __stcg(p.adam_m + qg, m); __stcg(p.adam_v + qg, v);
-                        if (pre && img_off >= 0) {       // the parameter's three bf16 pieces, where the weight tiles expect them
-                            uint32_t w0, w1, w2;
-                            split2(th_new, 0.f, w0, w1, w2);
-                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off), (unsigned short)w0);
-                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + img_sub), (unsigned short)w1);
-                            __stcg(reinterpret_cast<unsigned short*>(wimg + img_off + 2 * img_sub), (unsigned short)w2);
-                        }
+                        adam_store(qg, g, pre ? pre_th : __ldcg(p.theta_rw + qg), pre ? pre_m : __ldcg(p.adam_m + qg),
+                                   pre ? pre_v : __ldcg(p.adam_v + qg), pre);
                     }
                 }
             }
             stamp(26);
             net_barrier();                                             // the new parameters of this network are in L2
+            }
             stamp(27);
             if (S <= NEPI) {
                 // weights: ONE bulk copy (TMA) of the image the Adam owners just wrote; biases / log_std: a few scalar loads
