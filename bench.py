@@ -148,8 +148,7 @@ def run_b200(args) -> dict:
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N > 1)'
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: ONE JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # NCCL's version banner / warnings go to stderr: stdout carries ONE JSON line
         distributed.init_process_group('cuda')
     w = WORKLOAD
     T, N, O, A = w['steps_per_env'], w['envs_per_gpu'], args.obs_dim, w['act_dim']
