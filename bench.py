@@ -447,7 +447,17 @@ def main() -> None:
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
-    out = run_reference(args) if args.impl == 'reference' else run_b200(args)
+    # stdout carries exactly ONE JSON line: whatever libraries print while the bench runs (e.g. NCCL's version banner, written
+    # by C code straight to fd 1) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(args) if args.impl == 'reference' else run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if out:
         print(json.dumps(out), flush=True)
 
