@@ -18,7 +18,15 @@
 //                                                                               | dW1 += dZ1^T X,  db1 += dZ1^T 1
 //   Every epilogue writes its activation in two column halves, each announced by its own mbarrier, so the
 //   next layer's MMAs start on k-steps 0-1 while the epilogue still produces k-steps 2-3; weight / bias
-//   gradient MMAs run behind the dependent chain while the epilogue warps work.
+//   gradient MMAs run behind the dependent chain while the epilogue warps work.  The loss warps' per-sample inputs
+//   are copied asynchronously into shared memory (cp.async) at the start of the tile.
+//
+// FUSED instantiation = the persistent cooperative kernel of one update iteration: after each minibatch the partial
+// gradients are reduced slice-wise behind a software grid barrier, clipped per network, (multi-rank) exchanged over
+// NVLink as 8-byte {step tag, value} words, stepped with torch-Adam arithmetic -- speculatively before the norm barrier
+// on one rank -- and the weight tiles come back with one TMA bulk copy of a pre-split bf16x3 image maintained by the
+// Adam owners.  Loss kinds: PPO-clip, ratio, cost surrogate (fused or stepwise), FOCOPS and P3O (stepwise, with a
+// forward-only statistics pass), supplied dOUT (Fisher-vector product backward).
 #include "common.cuh"
 #include "mlp.cuh"
 #include "x3.cuh"
