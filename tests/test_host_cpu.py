@@ -125,3 +125,54 @@ def test_cpo_step_direction_ieee_fallbacks():
     # well-conditioned values still give the closed form
     step, lam, nu = CPO._step_direction(me, 3, 0.5, x, 0.1, -0.1, 0.5, p, 0.1, 1.0, -0.2)
     assert abs(float(step[0]) - math.sqrt(2 * kl / (0.5 + 1e-8))) < 1e-7
+
+
+def test_simmer_controller_matches_reference_sequences():
+    """SimmerPIDAgent (host-side product code) == the reference controller over recorded cost sequences (two gain settings,
+    the clamp to the budget bound included) -- common/simmer_agent.py:L132-186; fixture from the unmodified reference."""
+    from types import SimpleNamespace as NS
+
+    import numpy as np
+    import torch
+
+    from omnisafe_b200.common.simmer_agent import SimmerPIDAgent
+
+    c = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'simmer_controller.npz'))
+    scale = float(c['scale'])
+    for i in range(2):
+        kp, ki, kd, polyak = (float(v) for v in c[f'cfg_{i}'])
+        agent = SimmerPIDAgent(NS(kp=kp, ki=ki, kd=kd, polyak=polyak), torch.ones(3, 1) * 25.0 * scale)
+        budget = torch.ones(3, 1) * 15.0 * scale
+        hist = []
+        for cost in c['costs']:
+            budget = agent.act(budget, torch.as_tensor(cost) * scale)
+            hist.append(budget.numpy().copy())
+        np.testing.assert_array_equal(np.stack(hist), c[f'budget_{i}'])
+
+
+def test_unimplemented_upstream_options_are_refused():
+    """Options the fused path does not implement must not validate silently."""
+    import pytest
+
+    from omnisafe_b200.utils.config import check_all_configs, get_default_kwargs_yaml
+
+    cfgs = get_default_kwargs_yaml('PPOLag', 'SyntheticBox-v0')
+    check_all_configs(cfgs)
+    cfgs.model_cfgs.exploration_noise_anneal = True
+    with pytest.raises(NotImplementedError):
+        check_all_configs(cfgs)
+    cfgs = get_default_kwargs_yaml('CPO', 'SyntheticBox-v0')
+    cfgs.algo_cfgs.fvp_sample_freq = 2
+    with pytest.raises(NotImplementedError):
+        check_all_configs(cfgs)
+
+
+def test_saute_per_step_budget_is_the_reference_fp32_value():
+    """saute_adapter.py:L62-68: a python-double expression multiplied into an fp32 tensor."""
+    import torch
+
+    from omnisafe_b200.adapter.saute_adapter import per_step_budget
+
+    for budget, g, L in ((25.0, 0.999, 1000), (2.0, 0.9, 8), (1.0, 0.9, 8)):
+        ref = (budget * (1 - g ** L) / (1 - g) / L * torch.ones(1, 1))[0, 0].item()
+        assert per_step_budget(budget, g, L) == ref
