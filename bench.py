@@ -236,7 +236,7 @@ def run_b200(args) -> dict:
         ms_k = timed(iter_launch, 10) / 10          # learning rates 0: the parameters stay put
         kname, rows_per_launch = 'minibatch_grad_x3_kernel<fused> (persistent: 1 launch = 1 update iteration)', total
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_ncu_update_x3.md)
-        traffic = 221.7e6 if (O == 60 and A == 8 and total == 524288 and args.algo == 'PPOLag') else None
+        traffic = 218.8e6 if (O == 60 and A == 8 and total == 524288 and args.algo == 'PPOLag') else None
     else:
         fn = lib().osb_minibatch_grad_tc if args.precision == 'tf32' else lib().osb_minibatch_grad
 
@@ -274,7 +274,7 @@ def run_b200(args) -> dict:
                        'bf16x3 mode executes 6 bf16 MMAs per product' if x3_path else peaks['source'] + ' (cuBLAS bf16, sustained)',
         'us_per_launch': ms_k * 1e3, 'us_per_minibatch_step': ms_k * 1e3 / (rows_per_launch // w['batch_size']),
         'mma_executed_tflops': ach_tf * 6.0 if x3_path else None,
-        'ncu': ({'tensor_pipe_active_pct': 18.1, 'dram_bytes_per_launch': 221.7e6, 'source': 'profiles/r02_ncu_update_x3.md (ncu --set full, one launch)'}
+        'ncu': ({'tensor_pipe_active_pct': 18.9, 'dram_bytes_per_launch': 218.8e6, 'source': 'profiles/r02_ncu_update_x3.md (ncu --set full, one launch)'}
                 if (x3_path and O == 60 and args.algo == 'PPOLag') else None),
         'gae': {'kernel': 'gae_stream_kernel<TMA>', 'bound': 'hbm', 'achieved': gae_gbs, 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': gae_gbs / peaks['hbm_gbs'], 'us_per_launch': ms_gae * 1e3, 'bytes_per_sample': 33,
