@@ -310,7 +310,10 @@ __global__ void __launch_bounds__(OT) optim_fused_p2p_kernel(P2POptArgs a) {
         }
     }
     cg::this_grid().sync();
-    if (active && pl < L.size) {
+    // a peer that never published (time-out above) leaves its buffer stale: skip the step instead of applying garbage --
+    // the sticky error flag is raised by the host (distributed.p2p_check), the parameters stay those of the last good step
+    const bool exchange_ok = *((volatile int*)a.error_flag) == 0;
+    if (active && pl < L.size && exchange_ok) {
         float sum = 0.f;
         for (int r = 0; r < a.world; ++r) {
             const float* pb = a.peer_buf[r] + (size_t)par * p.r.P;
