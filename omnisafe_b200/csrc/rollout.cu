@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
         const float* gstd = pass ? p.ns.std : p.ns.std1;
         const bool norm_on = pass ? normalize : (p.es.obs_normalize && __ldcg(p.ns.count + 1) > 1);
         float* obs_out = (pass && net == 0) ? p.sl.obs + (size_t)t * N * On : nullptr;
+        const bool own_state = PERSIST && pass && net == 0 && t > t_first;
         if (tid < 64) { sMean[tid] = (tid < O) ? __ldcg(gmean + tid) : 0.f; sRstd[tid] = (tid < O) ? __ldcg(gstd + tid) : 1.f; }
         __syncthreads();
         if ((O & 3) == 0 && On == O) {   // 128-bit row loads, all 8 in flight per thread
@@ -765,6 +766,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int env = env0 + (tid >> 4) + 16 * j;
+                if (own_state) {          // persistent kernel, actor CTA: the state this CTA wrote in the previous step is still in smem
+                    const float* r = sRaw + ((tid >> 4) + 16 * j) * SNW + k4;
+                    xv[j] = (env < N && k4 < O) ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else
                 xv[j] = (env < N && k4 < O) ? __ldcg(reinterpret_cast<const float4*>(raw + (size_t)env * O + k4))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -808,7 +813,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                 const int env = env0 + e;
                 float v = 0.f;
                 if (env < N && k < O) {
-                    v = __ldcg(raw + (size_t)env * O + k);
+                    v = own_state ? sRaw[e * SNW + k] : __ldcg(raw + (size_t)env * O + k);
                     if (pass && net == 0) sRaw[e * SNW + k] = v;
                     if (norm_on) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v, -mk), sk), -5.f), 5.f);
                     if (obs_out) obs_out[(size_t)env * On + k] = v;
@@ -1047,6 +1052,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rollout_step_tc_kernel(StepArgs p
                             fx += to_fix(sn); fxx += to_fix(__fmul_rn(sn, sn));
                         }
                         s_nxt[(size_t)env * O + j] = nv;
+                        if (PERSIST) sRaw[e * SNW + j] = nv;            // next step's obs staging of this CTA reads it back from here
                         sSn[e * SNW + j] = sn;
                         sx += to_fix(nv); sxx += to_fix(__fmul_rn(nv, nv));
                     }
